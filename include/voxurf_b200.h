@@ -1,0 +1,185 @@
+/*
+ * voxurf_b200.h -- C ABI of libvoxurf_b200.so: the B200-native (sm_100a) operators of Voxurf's
+ * ray-batch volume-rendering hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - fp32 data, int64 indices and 1-byte bools at the reference-facing ("legacy") surface,
+ *     int32 indices on the fused surface;
+ *   - all tensors are contiguous; grids are (C,X,Y,Z) channel-major (channels_last=0, the layout of
+ *     the reference's (1,C,X,Y,Z) Parameter) or (X,Y,Z,C) (channels_last=1);
+ *   - every call is asynchronous on `stream` (the reference launches on the legacy default stream,
+ *     lib/cuda/render_utils_kernel.cu:93; pass the caller's current stream for equivalent ordering);
+ *   - return value 0 = ok, otherwise non-zero and vx_last_error() returns a message
+ *     (the reference raises through TORCH_CHECK, lib/cuda/render_utils.cpp:46-48);
+ *   - n <= 0 inputs are no-ops that return 0 (the reference's early returns, render_utils_kernel.cu:406,465,629).
+ *
+ * Citations `file:line` are relative to the reference repository (wutong16/Voxurf).
+ */
+#ifndef VOXURF_B200_H
+#define VOXURF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* vx_last_error(void);
+int vx_abi_version(void);
+int vx_sm_count(void);
+unsigned long long vx_launch_count(void); /* kernels launched through this library since load */
+
+/* ---- render_utils_cuda (lib/cuda/render_utils.cpp:170-184) --------------------------------- */
+/* infer_t_minmax            render_utils.cpp:50-58,  render_utils_kernel.cu:12-35,82-104 */
+int vx_infer_t_minmax(const float* rays_o, const float* rays_d, const float* xyz_min, const float* xyz_max,
+                      float near, float far, int n_rays, float* t_min, float* t_max, cudaStream_t stream);
+/* infer_n_samples           render_utils.cpp:60-65,  render_utils_kernel.cu:38-55,106-121 */
+int vx_infer_n_samples(const float* rays_d, const float* t_min, const float* t_max, float stepdist, int n_rays,
+                       int64_t* n_samples, cudaStream_t stream);
+/* infer_ray_start_dir       render_utils.cpp:67-72,  render_utils_kernel.cu:58-79,123-139 */
+int vx_infer_ray_start_dir(const float* rays_o, const float* rays_d, const float* t_min, int n_rays,
+                           float* rays_start, float* rays_dir, cudaStream_t stream);
+/* sample_pts_on_rays        render_utils.cpp:74-85,  render_utils_kernel.cu:144-242
+ * two-phase because the output length is data dependent:
+ *   vx_ray_setup  -> t_min, t_max, N_steps, rays_start, rays_dir, offsets[n_rays+1] (exclusive scan, total last)
+ *   (caller reads offsets[n_rays], allocates)   vx_sample_fill -> pts, mask_outbbox, ray_id, step_id */
+int vx_ray_setup(const float* rays_o, const float* rays_d, const float* xyz_min, const float* xyz_max, float near,
+                 float far, float stepdist, int n_rays, float* t_min, float* t_max, int64_t* n_steps,
+                 float* rays_start, float* rays_dir, int64_t* offsets, cudaStream_t stream);
+int vx_sample_fill(const float* rays_start, const float* rays_dir, const float* xyz_min, const float* xyz_max,
+                   const int64_t* offsets, int n_rays, float stepdist, float* rays_pts, bool* mask_outbbox,
+                   int64_t* ray_id, int64_t* step_id, cudaStream_t stream);
+/* sample_ndc_pts_on_rays    render_utils.cpp:87-97,  render_utils_kernel.cu:245-293 */
+int vx_sample_ndc_pts_on_rays(const float* rays_o, const float* rays_d, const float* xyz_min, const float* xyz_max,
+                              int n_samples, int n_rays, float* rays_pts, bool* mask_outbbox, cudaStream_t stream);
+/* sample_bg_pts_on_rays     render_utils.cpp:99-107, render_utils_kernel.cu:301-360 */
+int vx_sample_bg_pts_on_rays(const float* rays_o, const float* rays_d, const float* t_max, float bg_preserve,
+                             int n_samples, int n_rays, float* rays_pts, cudaStream_t stream);
+/* maskcache_lookup          render_utils.cpp:109-116, render_utils_kernel.cu:367-424 */
+int vx_maskcache_lookup(const bool* world, const float* xyz, const float* scale, const float* shift, int sz_i,
+                        int sz_j, int sz_k, int64_t n_pts, bool* out, cudaStream_t stream);
+/* raw2alpha / raw2alpha_nonuni (interval_vec != NULL)   render_utils.cpp:118-128, kernel.cu:430-504 */
+int vx_raw2alpha(const float* density, float shift, const float* interval_vec, float interval, int64_t n,
+                 float* exp_d, float* alpha, cudaStream_t stream);
+/* raw2alpha_backward / _nonuni_backward                  render_utils.cpp:130-140, kernel.cu:506-574 */
+int vx_raw2alpha_backward(const float* exp_d, const float* grad_back, const float* interval_vec, float interval,
+                          int64_t n, float* grad, cudaStream_t stream);
+/* alpha2weight              render_utils.cpp:142-149, render_utils_kernel.cu:576-651 (bit-exact, warp per ray) */
+int vx_alpha2weight(const float* alpha, const int64_t* ray_id, int64_t n_pts, int n_rays, float* weight, float* T,
+                    float* alphainv_last, int64_t* i_start, int64_t* i_end, cudaStream_t stream);
+/* alpha2weight_backward     render_utils.cpp:151-168, render_utils_kernel.cu:653-707 */
+int vx_alpha2weight_backward(const float* alpha, const float* weight, const float* T, const float* alphainv_last,
+                             const int64_t* i_start, const int64_t* i_end, int n_rays, int64_t n_pts,
+                             const float* grad_weights, const float* grad_last, float* grad, cudaStream_t stream);
+
+/* ---- total_variation_cuda (lib/cuda/total_variation.cpp:29-32) ------------------------------ */
+/* total_variation_add_grad (mask == NULL) / total_variation_add_grad_new (float mask)
+ * total_variation.cpp:13-27, total_variation_kernel.cu:14-133; in place on grad */
+int vx_total_variation_add_grad(const float* param, float* grad, const float* mask, float wx, float wy, float wz,
+                                int dense_mode, int64_t sz_i, int64_t sz_j, int64_t sz_k, int64_t numel,
+                                cudaStream_t stream);
+
+/* ---- adam_upd_cuda (lib/cuda/adam_upd.cpp:79-86) -------------------------------------------- */
+/* mode 0 adam_upd, 1 masked_adam_upd, 2 adam_upd_with_perlr   adam_upd.cpp:36-77, adam_upd_kernel.cu:9-132 */
+int vx_adam_upd(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* perlr,
+                int64_t numel, int step, float beta1, float beta2, float lr, float eps, int mode,
+                cudaStream_t stream);
+/* the trainer's optimizer: utils.Adam.step / utils.adam, lib/utils.py:83-199 (dense; optional per-voxel lr,
+ * optional skip of zero gradients, optional fused zero-fill of grad) */
+int vx_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const float* perlr, int64_t numel,
+                 float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                 float sqrt_bias_correction2, float eps, int skip_zero_grad, int zero_grad, cudaStream_t stream);
+
+/* ---- torch_scatter.segment_coo(reduce='sum'), sorted index (lib/voxurf_fine.py:753-777) ----- */
+int vx_segment_coo_sum(const float* src, const int64_t* index, int64_t M, int K, float* out, cudaStream_t stream);
+
+/* ---- grids: F.grid_sample(bilinear, align_corners=True) call sites --------------------------- */
+/* Points are either xyz (P,3) or, when xyz == NULL, implicit (ray_id, step_id) into rays_start/rays_dir:
+ * p = start + dir * (stepdist * step), the formula of render_utils_kernel.cu:184-187.
+ * The point count is n_host, or *n_dev when n_dev != NULL (sync-free pipelines). */
+/* DenseGrid.forward         lib/grid.py:47-58 ; MaskCache gather lib/voxurf_fine.py:936-939 ;
+ * coarse grid_sampler       lib/voxurf_coarse.py:435-452 */
+int vx_grid_gather(const float* grid, int X, int Y, int Z, int C, int channels_last, const float* xyz_min_host,
+                   const float* xyz_max_host, const float* xyz, const int* ray_id, const int* step_id,
+                   const float* rays_start, const float* rays_dir, float stepdist, const int* n_dev,
+                   int64_t n_host, float* out, cudaStream_t stream);
+/* its backward (ATen grid_sampler_3d_backward wrt input): grad_grid += scatter(grad_out) */
+int vx_grid_gather_backward(int X, int Y, int Z, int C, int channels_last, const float* xyz_min_host,
+                            const float* xyz_max_host, const float* xyz, const int* ray_id, const int* step_id,
+                            const float* rays_start, const float* rays_dir, float stepdist, const int* n_dev,
+                            int64_t n_host, const float* grad_out, float* grad_grid, cudaStream_t stream);
+/* Voxurf.grid_sampler (sample_ret + sample_grad)  lib/voxurf_fine.py:502-534  (L=1, xyz_order=1)
+ * Voxurf.sample_sdfs                              lib/voxurf_fine.py:537-577  (L<=8, xyz_order=0) */
+int vx_sdf_taps(const float* grid, int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
+                const float* xyz, const int* ray_id, const int* step_id, const float* rays_start,
+                const float* rays_dir, float stepdist, const int* n_dev, int64_t n_host,
+                const float* displace_host, int L, float voxel_size, int use_grad_norm, int xyz_order,
+                float* out_sdf, float* out_feat, float* out_grad, cudaStream_t stream);
+int vx_sdf_taps_backward(const float* grid, int X, int Y, int Z, const float* xyz_min_host,
+                         const float* xyz_max_host, const float* xyz, const int* ray_id, const int* step_id,
+                         const float* rays_start, const float* rays_dir, float stepdist, const int* n_dev,
+                         int64_t n_host, const float* displace_host, int L, float voxel_size, int use_grad_norm,
+                         int xyz_order, const float* grad_sdf, const float* grad_feat, const float* grad_grad,
+                         float* grad_grid, cudaStream_t stream);
+/* neus_alpha_from_sdf_scatter  lib/voxurf_fine.py:463-500 (== lib/voxurf_coarse.py:348-382); give ray_id (int32)
+ * or ray_id64 */
+int vx_neus_alpha(const float* viewdirs, const int* ray_id, const int64_t* ray_id64, const float* sdf,
+                  const float* gradient, float dist, float inv_s, const int* n_dev, int64_t n_host, float* alpha,
+                  cudaStream_t stream);
+int vx_neus_alpha_backward(const float* viewdirs, const int* ray_id, const int64_t* ray_id64, const float* sdf,
+                           const float* gradient, float dist, float inv_s, const int* n_dev, int64_t n_host,
+                           const float* grad_alpha, int accumulate, float* grad_sdf, float* grad_gradient,
+                           cudaStream_t stream);
+
+/* ---- grid-level stencils ------------------------------------------------------------------- */
+/* neus_sdf_gradient('interpolate')  lib/voxurf_fine.py:440-460 ; grad is (3,X,Y,Z); backward accumulates */
+int vx_fd_gradient(const float* sdf, int X, int Y, int Z, float voxel_size, float* grad, cudaStream_t stream);
+int vx_fd_gradient_backward(const float* dgrad, int X, int Y, int Z, float voxel_size, float* dsdf,
+                            cudaStream_t stream);
+/* _gaussian_3dconv / tv_smooth_conv: Conv3d(1,1,k,padding=k//2,'replicate')  lib/voxurf_fine.py:236-258 ;
+ * B independent volumes; weight_host is (k,k,k) on the HOST, k in {1,3,5} */
+int vx_conv3d_replicate(const float* in, int B, int X, int Y, int Z, const float* weight_host, int ksize,
+                        float* out, cudaStream_t stream);
+int vx_conv3d_replicate_backward(const float* dout, int B, int X, int Y, int Z, const float* weight_host,
+                                 int ksize, int accumulate, float* din, cudaStream_t stream);
+/* density_total_variation(smooth_grad_tv)  lib/voxurf_fine.py:417-420: from the FD gradient G (3,X,Y,Z) and the
+ * bool nonempty mask: dG = dLoss/dG, loss_out[0] = loss.  w_over_3n = smooth_grad_tv_weight / (3 * mask.sum()) */
+int vx_smooth_grad_tv_scratch_floats(void);
+int vx_smooth_grad_tv(const float* G, const bool* mask, int X, int Y, int Z, const float* weight3_host,
+                      float w_over_3n, float* dG, float* scratch, float* loss_out, cudaStream_t stream);
+
+/* ---- fused ray march (replaces sample_pts_on_rays + two compactions + MaskCache.forward) ---- */
+/* lib/voxurf_fine.py:593-617,631-636,917-942.  bits_* need (offsets[n_rays] >> 5) + n_rays + 1 words. */
+int vx_march_flags(const float* rays_start, const float* rays_dir, const float* xyz_min, const float* xyz_max,
+                   const int64_t* offsets, int n_rays, float stepdist, const float* mc_density, int mc_X, int mc_Y,
+                   int mc_Z, const float* mc_min_host, const float* mc_max_host, float act_shift,
+                   float voxel_size_ratio, float thres, uint32_t* bits_inbbox, uint32_t* bits_keep,
+                   int* keep_count, int* keep_off /* n_rays+1 */, cudaStream_t stream);
+/* MaskCache.forward on explicit points  lib/voxurf_fine.py:930-942 */
+int vx_mask_cache_query(const float* mc_density, int mc_X, int mc_Y, int mc_Z, const float* mc_min_host,
+                        const float* mc_max_host, float act_shift, float voxel_size_ratio, float thres,
+                        const float* xyz, int64_t n, bool* out, cudaStream_t stream);
+int vx_march_emit(const int64_t* offsets, int n_rays, const uint32_t* bits_keep, const int* keep_off, int capacity,
+                  int* ray_id, int* step_id, bool* mask_outbbox /* M0 or NULL */, cudaStream_t stream);
+int vx_points_from_steps(const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
+                         float stepdist, const int* n_dev, int64_t n_host, float* out, cudaStream_t stream);
+/* alpha2weight over int32 per-ray segments with an optional keep flag (alpha > thres filter applied in place,
+ * lib/voxurf_fine.py:647-654) and weight > thres flags / per-ray counts (lib/voxurf_fine.py:668-676) */
+int vx_alpha2weight_seg(const float* alpha, const uint8_t* keep, const int* seg_off, int n_rays, float w_thres,
+                        float* weight, float* T, float* alphainv_last, int* i_end, uint8_t* w_keep, int* w_count,
+                        cudaStream_t stream);
+int vx_alpha2weight_seg_backward(const float* alpha, const float* weight, const float* T, const uint8_t* keep,
+                                 const float* alphainv_last, const int* seg_off, const int* i_end, int n_rays,
+                                 const float* grad_weights, const float* grad_last, float* grad,
+                                 cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXURF_B200_H */

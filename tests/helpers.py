@@ -78,3 +78,39 @@ def oracle_coarse_model(sc, requires_grad=True, apply_nonempty=True):
     m['k0'] = T(sc['k0']).clone().requires_grad_(requires_grad)
     m['rgbnet'] = _layers(sc['rgbnet'], requires_grad)
     return m
+
+
+# ------------------------------------------------------------------------------------------------
+# product-side models from the same scenes
+# ------------------------------------------------------------------------------------------------
+def mask_cache_state(sc):
+    return {'MaskCache_kwargs': {'xyz_min': [-1., -1., -1.], 'xyz_max': [1., 1., 1.], 'act_shift': sc['mask_act_shift'],
+                                 'voxel_size_ratio': sc['mask_voxel_size_ratio'], 'nearest': False},
+            'model_state_dict': {'density': T(sc['mask_density'])}}
+
+
+def set_mlp(seq, layers):
+    lin = [m for m in seq.modules() if isinstance(m, torch.nn.Linear)]
+    assert len(lin) == len(layers)
+    for m, (W, b) in zip(lin, layers):
+        m.weight.data = T(W).clone()
+        m.bias.data = T(b).clone()
+
+
+def product_fine_model(sc, device='cuda', apply_nonempty=True, k0_channels_last=False):
+    from voxurf_b200 import voxurf_fine as VF
+    G = sc['G']
+    cfg = {k: v for k, v in S.FINE_CFG.items() if k != 'stepsize'}
+    m = VF.Voxurf(xyz_min=[-1., -1., -1.], xyz_max=[1., 1., 1.], num_voxels=G ** 3, num_voxels_base=G ** 3,
+                  rgbnet_dim=sc['C'], rgbnet_width=sc['width'], k0_channels_last=k0_channels_last,
+                  mask_cache_state=mask_cache_state(sc) if 'mask_density' in sc else None, **cfg)
+    assert tuple(int(w) for w in m.world_size) == (G, G, G)
+    m.sdf.grid.data = T(sc['sdf']).clone()
+    k0 = T(sc['k0']).clone()
+    m.k0.grid.data = k0.contiguous(memory_format=torch.channels_last_3d) if k0_channels_last else k0
+    set_mlp(m.rgbnet, sc['rgbnet'])
+    set_mlp(m.k_rgbnet, sc['k_rgbnet'])
+    m = m.to(device)
+    if m.mask_cache is not None and apply_nonempty:
+        m._set_nonempty_mask()
+    return m

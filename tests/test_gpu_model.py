@@ -1,0 +1,103 @@
+"""GPU: the drop-in fine model (voxurf_b200.voxurf_fine.Voxurf) end to end -- forward, backward, TV add-grad and
+the trainer's Adam -- against (i) the committed golden vectors produced by the reference's own Python and
+(ii) the CPU oracle at a larger size."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import kernels as K
+from oracle import voxurf_ref as R
+from voxurf_b200 import synthetic as S
+from tests.helpers import T, load_golden, oracle_fine_model, product_fine_model
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+RET_KEYS = ['alphainv_cum', 'weights', 'rgb_marched', 'rgb_marched0', 'normal_marched', 'raw_alpha', 'raw_rgb', 'depth',
+            'disp', 'mask', 'mask_outbbox', 'gradient']
+
+
+def close(a, b, rtol=1e-5, atol=1e-6, msg=''):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=msg)
+
+
+def loss_fn(ret, target):
+    loss = F.mse_loss(ret['rgb_marched'], target)
+    pout = ret['alphainv_cum'][..., -1].clamp(1e-6, 1 - 1e-6)
+    loss = loss + 0.001 * (-(pout * torch.log(pout) + (1 - pout) * torch.log(1 - pout)).mean())
+    return loss + 0.5 * F.mse_loss(ret['rgb_marched0'], target)
+
+
+def grad_close(a, b, rtol=1e-4, rel_floor=1e-5, msg=''):
+    """gradient tolerance: rtol 1e-4 with an absolute floor relative to the tensor's largest magnitude."""
+    scale = float(np.abs(b).max()) if not torch.is_tensor(b) else float(b.abs().max())
+    close(a, b, rtol, rel_floor * max(scale, 1e-30), msg)
+
+
+@pytest.mark.parametrize('k0_cl', [False, True])
+def test_fine_model_matches_reference_golden(k0_cl):
+    g = load_golden('fine_forward.npz')
+    sc = S.make_fine_scene(20, 6, 32, seed=3, mask_G=12)
+    m = product_fine_model(sc, k0_channels_last=k0_cl)
+    close(m.sdf.grid, g['sdf_after_mask'], 0, 0)
+    ro, rd, vd = (T(x).to(DEV) for x in S.make_rays(96, seed=777))
+    target = T(S.make_target(vd.cpu().numpy())).to(DEV)
+    rk = dict(near=0.3, far=6.0, bg=0, stepsize=0.5, render_grad=True, render_depth=True)
+    ret = m(ro, rd, vd, global_step=15001, **rk)
+    assert ret['s_val'] == float(g['s_val'])
+    for k in RET_KEYS:
+        if ret[k].dtype == torch.bool:
+            assert (ret[k].cpu().numpy() == g[k]).all(), k
+        else:
+            close(ret[k], g[k], 1e-5, 2e-6, k)
+    close(m.gradient, g['full_gradient'], 1e-5, 1e-6)
+    loss = loss_fn(ret, target)
+    close(loss, g['loss'], 1e-5, 1e-7)
+    loss.backward()
+    grad_close(m.sdf.grid.grad, g['grad_sdf'], msg='grad_sdf'); grad_close(m.k0.grid.grad, g['grad_k0'], msg='grad_k0')
+    for name, net in (('rgbnet', m.rgbnet), ('k_rgbnet', m.k_rgbnet)):
+        for i, l in enumerate([x for x in net.modules() if isinstance(x, torch.nn.Linear)]):
+            grad_close(l.weight.grad, g[f'grad_{name}_W{i}'], msg=f'{name} W{i}'); grad_close(l.bias.grad, g[f'grad_{name}_b{i}'], msg=f'{name} b{i}')
+    # TV add-grad + the trainer's Adam (run.py:641-659)
+    if not k0_cl:
+        from voxurf_b200.optim import Adam
+        m.sdf_total_variation_add_grad(0.01 * 0.1 / 96, True)
+        grad_close(m.sdf.grid.grad, g['grad_sdf_after_tv'], msg='tv')
+        opt = Adam([{'params': [m.sdf.grid], 'lr': 5e-3}, {'params': [m.k0.grid], 'lr': 1e-1}], betas=(0.9, 0.99))
+        opt.step()
+        close(m.sdf.grid, g['sdf_after_adam'], 1e-5, 1e-5); close(m.k0.grid, g['k0_after_adam'], 1e-5, 1e-5)
+        with torch.no_grad():
+            ret_e = m(ro, rd, vd, **rk)
+        close(ret_e['rgb_marched'], g['eval_rgb_marched'], 1e-4, 1e-4)
+        close(ret_e['normal_marched'], g['eval_normal_marched'], 1e-4, 1e-4)
+        close(ret_e['depth'], g['eval_depth'], 1e-4, 1e-4)
+
+
+@pytest.mark.parametrize('G,n_rays,step,C', [(64, 1024, 15001, 6), (48, 512, 200, 12)])
+def test_fine_model_matches_oracle(G, n_rays, step, C):
+    sc = S.make_fine_scene(G, C, 64, seed=G)
+    m = product_fine_model(sc, k0_channels_last=(C == 12))
+    om = oracle_fine_model(sc)
+    ro, rd, vd = (T(x) for x in S.make_rays(n_rays, seed=G + 1))
+    target = T(S.make_target(vd.numpy()))
+    kw = dict(near=0.3, stepsize=0.5, bg=1.0 if C == 12 else 0.0, render_grad=True, render_depth=True)
+    oret = R.fine_forward(om, ro, rd, vd, step, **kw)
+    ret = m(ro.to(DEV), rd.to(DEV), vd.to(DEV), global_step=step, far=6.0, **kw)
+    for k in RET_KEYS:
+        if oret[k].dtype == torch.bool:
+            assert torch.equal(ret[k].cpu(), oret[k]), k
+        else:
+            close(ret[k], oret[k], 1e-5, 3e-6, k)
+    oloss = R.fine_loss(oret, target)
+    loss = loss_fn(ret, target.to(DEV))
+    close(loss, oloss, 1e-5, 1e-7)
+    # + smooth-grad TV regulariser through the full-grid FD gradient (voxurf_fine.py:412-421, run.py:622-625)
+    oloss = oloss + 0.01 * R.smooth_grad_tv(oret['_full_gradient'], om['nonempty_mask'], 0.05)
+    loss = loss + 0.01 * m.density_total_variation(sdf_tv=0, smooth_grad_tv=0.05)
+    oloss.backward(); loss.backward()
+    grad_close(m.sdf.grid.grad, om['sdf'].grad, msg='grad_sdf'); grad_close(m.k0.grid.grad, om['k0'].grad, msg='grad_k0')
+    for net, ol in ((m.rgbnet, om['rgbnet']), (m.k_rgbnet, om['k_rgbnet'])):
+        for l, (W, b) in zip([x for x in net.modules() if isinstance(x, torch.nn.Linear)], ol):
+            grad_close(l.weight.grad, W.grad); grad_close(l.bias.grad, b.grad)

@@ -1,0 +1,352 @@
+"""GPU parity, operator by operator: the CUDA path through the C ABI vs the CPU oracle on the same
+seeded inputs.  Bars: integer / index / bool outputs bit-exact; fp32 forward rtol 1e-5, gradients rtol 1e-4
+(north_star), with small absolute floors written next to each check."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kernels as K
+from oracle import voxurf_ref as R
+from voxurf_b200 import synthetic as S
+from tests.helpers import T
+
+pytestmark = pytest.mark.gpu
+
+XYZ_MIN, XYZ_MAX = torch.tensor([-1., -1., -1.]), torch.tensor([1., 1., 1.])
+MN, MX = [-1., -1., -1.], [1., 1., 1.]
+DEV = 'cuda'
+
+
+def cu(x):
+    return x.to(DEV)
+
+
+def close(a, b, rtol=1e-5, atol=1e-6, msg=''):
+    np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=rtol, atol=atol, err_msg=msg)
+
+
+def exact(a, b, msg=''):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    assert a.shape == b.shape and a.dtype == b.dtype, (msg, a.shape, b.shape, a.dtype, b.dtype)
+    assert torch.equal(a, b), (msg, (a != b).sum().item())
+
+
+def rays(n, seed=777, special=True):
+    o, d, v = (T(x) for x in S.make_rays(n, seed=seed))
+    if special and n >= 8:
+        d[0, 1] = 0.0                                   # zero direction component -> 1e-6 (hazard 1)
+        d[1] = torch.tensor([0.0, 0.0, 1.0]); o[1] = torch.tensor([0.2, -0.3, -3.0])   # axis aligned
+        o[2] = torch.tensor([5.0, 5.0, 5.0]); d[2] = torch.tensor([1.0, 0.2, 0.1])     # misses the box (hazard 2)
+        o[3] = torch.tensor([0.1, 0.1, 0.1])                                           # origin inside the box
+        o[4] = torch.tensor([-3.0, 1.0, 0.0]); d[4] = torch.tensor([1.0, 0.0, 0.0])    # grazes a face (hazard 3)
+    return o, d, v
+
+
+# ------------------------------------------------------------------------------------------------ sampling
+@pytest.mark.parametrize('n,G,near', [(257, 32, 0.3), (8192, 256, 0.3), (1, 16, 0.05), (64, 96, 2.0)])
+def test_sampling_bit_exact(n, G, near):
+    from voxurf_b200 import render_utils_cuda as ru
+    o, d, _ = rays(n, special=n >= 8)
+    stepdist = float(np.float32(0.5 * 2.0 / G))
+    ref = K.sample_pts_on_rays(o, d, XYZ_MIN, XYZ_MAX, near, 1e9, stepdist)
+    t_min, t_max = ru.infer_t_minmax(cu(o), cu(d), cu(XYZ_MIN), cu(XYZ_MAX), near, 1e9)
+    exact(t_min, ref[5], 't_min'); exact(t_max, ref[6], 't_max')
+    exact(ru.infer_n_samples(cu(d), t_min, t_max, stepdist), ref[4], 'n_samples')
+    s, dr = ru.infer_ray_start_dir(cu(o), cu(d), t_min)
+    rs, rd = K.infer_ray_start_dir(o, d, ref[5])
+    exact(s, rs, 'rays_start'); exact(dr, rd, 'rays_dir')
+    out = ru.sample_pts_on_rays(cu(o), cu(d), cu(XYZ_MIN), cu(XYZ_MAX), near, 1e9, stepdist)
+    for a, b, name in zip(out, ref, ['pts', 'mask_outbbox', 'ray_id', 'step_id', 'N_steps', 't_min', 't_max']):
+        exact(a, b, name)
+
+
+def test_sampling_empty_and_misc():
+    from voxurf_b200 import render_utils_cuda as ru
+    e = torch.zeros(0, 3, device=DEV)
+    out = ru.sample_pts_on_rays(e, e, cu(XYZ_MIN), cu(XYZ_MAX), 0.1, 1e9, 0.01)
+    assert out[0].shape == (0, 3) and out[2].shape == (0,) and out[4].shape == (0,)
+    o, d, _ = rays(33)
+    p, m = ru.sample_ndc_pts_on_rays(cu(o), cu(d), cu(XYZ_MIN), cu(XYZ_MAX), 17)
+    rp, rm = K.sample_ndc_pts_on_rays(o, d, XYZ_MIN, XYZ_MAX, 17)
+    exact(p, rp); exact(m, rm)
+    tmax = torch.rand(33) + 3
+    close(ru.sample_bg_pts_on_rays(cu(o), cu(d), cu(tmax), 0.3, 19), K.sample_bg_pts_on_rays(o, d, tmax, 0.3, 19), 1e-6, 1e-7)
+
+
+def test_maskcache_lookup_bit_exact():
+    from voxurf_b200 import render_utils_cuda as ru
+    rs = np.random.RandomState(3)
+    world = T(rs.uniform(0, 1, (9, 10, 11)) > 0.5)
+    q = T(rs.uniform(-1.2, 1.2, (5000, 3)).astype(np.float32))
+    q[:4] = torch.tensor([[-1., -1., -1.], [1., 1., 1.], [0.0, 0.1, -0.1], [-1.1, 0., 0.]])   # .5 rounding, OOB
+    scale, shift = R.mask_grid_params(world.shape, XYZ_MIN, XYZ_MAX)
+    exact(ru.maskcache_lookup(cu(world), cu(q), cu(scale), cu(shift)), K.maskcache_lookup(world, q, scale, shift))
+    assert ru.maskcache_lookup(cu(world), torch.zeros(0, 3, device=DEV), cu(scale), cu(shift)).shape == (0,)
+
+
+def test_fused_march_matches_staged_reference_path():
+    """vx_march_* == sample_pts_on_rays -> in-bbox filter -> MaskCache -> filter (voxurf_fine.py:593-636)."""
+    from tests.helpers import product_fine_model, oracle_fine_model
+    sc = S.make_fine_scene(48, 6, 16, seed=5, mask_G=20)
+    m = product_fine_model(sc, apply_nonempty=False)
+    om = oracle_fine_model(sc, requires_grad=False, apply_nonempty=False)
+    o, d, _ = rays(700)
+    out = m._march(cu(o), cu(d), 0.3, 0.5)
+    pts, rid, sid, mob, _ = R.sample_ray(o, d, XYZ_MIN, XYZ_MAX, 0.3, 0.5, om['voxel_size'])
+    mc = om['mask_cache']
+    keep = R.mask_cache_forward(mc['density'], pts, mc['xyz_min'], mc['xyz_max'], mc['act_shift'], mc['voxel_size_ratio'], mc['thres'])
+    mob[~mob.clone()] |= ~keep
+    exact(out['ray_id'].long(), rid[keep], 'ray_id'); exact(out['step_id'].long(), sid[keep], 'step_id')
+    exact(out['ray_pts'], pts[keep], 'ray_pts'); exact(out['mask_outbbox'], mob, 'mask_outbbox')
+    # standalone MaskCache.forward and hit_coarse_geo
+    exact(m.mask_cache(cu(pts)), keep, 'mask_cache')
+    hit = torch.zeros(700, dtype=torch.bool); hit[rid[keep]] = True
+    exact(m.hit_coarse_geo(cu(o), cu(d), 0.3, 6.0, 0.5), hit, 'hit')
+
+
+# ------------------------------------------------------------------------------------------------ raw2alpha / alpha2weight
+def test_raw2alpha():
+    from voxurf_b200 import render_utils_cuda as ru
+    d = torch.randn(10000) * 8
+    d[:3] = torch.tensor([100., -100., 0.])
+    e, a = ru.raw2alpha(cu(d), -4.0, 0.5)
+    re, ra = K.raw2alpha(d, -4.0, 0.5)
+    close(e, re, 2e-6, 0); close(a, ra, 1e-5, 1e-7)
+    gb = torch.randn(10000)
+    close(ru.raw2alpha_backward(e, cu(gb), 0.5), K.raw2alpha_backward(e.cpu(), gb, 0.5), 1e-5, 1e-9)
+    iv = torch.rand(10000) + 0.1
+    e2, a2 = ru.raw2alpha_nonuni(cu(d), -4.0, cu(iv))
+    close(a2, K.raw2alpha(d, -4.0, iv)[1], 1e-5, 1e-7)
+    close(ru.raw2alpha_nonuni_backward(e2, cu(gb), cu(iv)), K.raw2alpha_backward(e2.cpu(), gb, iv), 1e-5, 1e-9)
+    assert ru.raw2alpha(torch.zeros(0, device=DEV), 0.0, 0.5)[1].shape == (0,)
+
+
+def _ragged_ray_ids(n_rays, rs, max_len=300, empty_frac=0.2):
+    lens = rs.randint(0, max_len, n_rays)
+    lens[rs.uniform(0, 1, n_rays) < empty_frac] = 0
+    return torch.from_numpy(np.repeat(np.arange(n_rays), lens).astype(np.int64))
+
+
+@pytest.mark.parametrize('n_rays,scale', [(64, 0.05), (2048, 0.3), (8192, 0.02)])
+def test_alpha2weight_bit_exact(n_rays, scale):
+    from voxurf_b200 import render_utils_cuda as ru
+    rs = np.random.RandomState(n_rays)
+    rid = _ragged_ray_ids(n_rays, rs)
+    alpha = T((rs.uniform(0, 1, rid.shape[0]) ** 3 * scale * 3).clip(0, 1).astype(np.float32))
+    alpha[::97] = 1.0; alpha[::89] = 0.0
+    out = ru.alpha2weight(cu(alpha), cu(rid), n_rays)
+    ref = K.alpha2weight(alpha, rid, n_rays)
+    for a, b, name in zip(out, ref, ['weight', 'T', 'alphainv_last', 'i_start', 'i_end']):
+        exact(a, b, name)
+    gw = T(rs.standard_normal(rid.shape[0]).astype(np.float32)); gl = T(rs.standard_normal(n_rays).astype(np.float32))
+    g = ru.alpha2weight_backward(cu(alpha), out[0], out[1], out[2], out[3], out[4], n_rays, cu(gw), cu(gl))
+    exact(g, K.alpha2weight_backward(alpha, *ref, n_rays, gw, gl), 'grad_alpha')
+
+
+def test_alpha2weight_empty():
+    from voxurf_b200 import render_utils_cuda as ru
+    out = ru.alpha2weight(torch.zeros(0, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), 5)
+    assert out[0].shape == (0,) and (out[2] == 1).all() and (out[3] == 0).all() and (out[4] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ TV / Adam
+@pytest.mark.parametrize('dense', [True, False])
+@pytest.mark.parametrize('masked', [False, True])
+def test_total_variation_add_grad(dense, masked):
+    from voxurf_b200 import total_variation_cuda as tv
+    rs = np.random.RandomState(5)
+    p = T(rs.standard_normal((1, 3, 13, 11, 17)).astype(np.float32) * 2)
+    g = T(rs.standard_normal((1, 3, 13, 11, 17)).astype(np.float32)); g[rs.uniform(0, 1, g.shape) < 0.5] = 0
+    mk = T((rs.uniform(0, 1, p.shape) > 0.3).astype(np.float32))
+    gg, gr = cu(g.clone()), g.clone()
+    if masked:
+        tv.total_variation_add_grad_new(cu(p), gg, cu(mk), 0.3, 0.5, 0.7, dense)
+        K.total_variation_add_grad(p, gr, 0.3, 0.5, 0.7, dense, mask=mk)
+    else:
+        tv.total_variation_add_grad(cu(p), gg, 0.3, 0.5, 0.7, dense)
+        K.total_variation_add_grad(p, gr, 0.3, 0.5, 0.7, dense)
+    close(gg, gr, 1e-6, 1e-7)
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+def test_adam_upd_reference_cuda_semantics(mode):
+    from voxurf_b200 import adam_upd_cuda as ad
+    rs = np.random.RandomState(7)
+    n = 100003
+    p, m, v = (T(rs.standard_normal(n).astype(np.float32)) for _ in range(3))
+    v = v.abs()
+    perlr = T(rs.uniform(0, 1, n).astype(np.float32))
+    pc, mc, vc = cu(p.clone()), cu(m.clone()), cu(v.clone())
+    for step in (1, 2, 30):
+        g = T(rs.standard_normal(n).astype(np.float32)); g[::3] = 0
+        if mode == 0:
+            ad.adam_upd(pc, cu(g), mc, vc, step, 0.9, 0.99, 0.1, 1e-8)
+        elif mode == 1:
+            ad.masked_adam_upd(pc, cu(g), mc, vc, step, 0.9, 0.99, 0.1, 1e-8)
+        else:
+            ad.adam_upd_with_perlr(pc, cu(g), mc, vc, cu(perlr), step, 0.9, 0.99, 0.1, 1e-8)
+        K.adam_upd(p, g, m, v, step, 0.9, 0.99, 0.1, 1e-8, mode=mode, perlr=perlr if mode == 2 else None)
+        close(pc, p, 1e-6, 1e-7); close(mc, m, 1e-6, 1e-8); close(vc, v, 1e-6, 1e-9)
+
+
+def test_trainer_adam_semantics_and_fused_zero_grad():
+    from voxurf_b200.optim import Adam
+    rs = np.random.RandomState(9)
+    p0 = T(rs.standard_normal((1, 6, 9, 10, 11)).astype(np.float32))
+    for cl in (False, True):
+        p = torch.nn.Parameter(cu(p0.clone()).contiguous(memory_format=torch.channels_last_3d) if cl else cu(p0.clone()))
+        opt = Adam([{'params': [p], 'lr': 0.1}], betas=(0.9, 0.99), zero_grad_in_step=True)
+        rp, rm, rv = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+        rs2 = np.random.RandomState(10)
+        for it in range(3):
+            g = T(rs2.standard_normal(p0.shape).astype(np.float32)); g[..., ::2] = 0
+            p.grad = cu(g.clone()).contiguous(memory_format=torch.channels_last_3d) if cl else cu(g.clone())
+            opt.step()
+            R.python_adam_step(rp, g, rm, rv, it + 1, 0.1)
+            close(p.data, rp, 1e-6, 1e-7)
+            assert (p.grad == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ grid gathers
+def _pts(n, rs, lo=-1.05, hi=1.05):
+    p = T(rs.uniform(lo, hi, (n, 3)).astype(np.float32))
+    p[:6] = torch.tensor([[-1., -1., -1.], [1., 1., 1.], [1., -1., 0.3], [0.999, 0.2, -0.999], [0., 0., 0.], [-1.0, 0.1, 0.2]])
+    return p
+
+
+@pytest.mark.parametrize('C,cl', [(1, False), (3, False), (6, False), (6, True), (12, True), (5, True), (4, True)])
+def test_grid_gather_forward_backward(C, cl):
+    from voxurf_b200 import ops
+    rs = np.random.RandomState(C)
+    grid = T(rs.standard_normal((1, C, 9, 12, 7)).astype(np.float32))
+    pts = _pts(3000, rs)
+    go = T(rs.standard_normal((3000, C)).astype(np.float32)); go[::4] = 0
+    gr = grid.clone().requires_grad_(True)
+    ref = R.grid_trilinear(gr, pts, XYZ_MIN, XYZ_MAX)
+    ref.backward(go)
+    gg = cu(grid.clone())
+    if cl:
+        gg = gg.contiguous(memory_format=torch.channels_last_3d)
+    gg.requires_grad_(True)
+    out = ops.grid_gather(gg, cu(pts), MN, MX)
+    close(out, ref, 1e-5, 1e-6)
+    out.backward(cu(go))
+    close(gg.grad, gr.grad, 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize('disp,norm,xyz_order', [([1.0], False, True), ([0.5, 1.0, 1.5, 2.0], True, False),
+                                                 ([0.5, 1.0, 1.5, 2.0], False, False), ([2.0], True, False)])
+def test_sdf_taps_forward_backward(disp, norm, xyz_order):
+    from voxurf_b200 import ops
+    rs = np.random.RandomState(len(disp))
+    G = 24
+    vs = float(2.0 / G)
+    grid = T(S.sphere_sdf(G, noise=0.05, seed=2))
+    pts = _pts(2500, rs, -1.0, 1.0)
+    gr = grid.clone().requires_grad_(True)
+    L = len(disp)
+    if xyz_order:
+        sdf_r, grad_r, feat_r = R.fine_grid_sampler(pts, gr, XYZ_MIN, XYZ_MAX, torch.tensor(vs))
+    else:
+        feat_r, grad_r = R.sample_sdfs(pts, gr, disp, XYZ_MIN, XYZ_MAX, torch.tensor(vs), use_grad_norm=norm)
+        sdf_r = R.grid_trilinear(gr, pts, XYZ_MIN, XYZ_MAX).squeeze(-1)
+    g1, g2, g3 = (T(rs.standard_normal(t.shape).astype(np.float32)) for t in (sdf_r, feat_r, grad_r))
+    g3[::5] = 0
+    (sdf_r * g1).sum().backward(retain_graph=True); (feat_r * g2).sum().backward(retain_graph=True); (grad_r * g3).sum().backward()
+    gg = cu(grid.clone()).requires_grad_(True)
+    sdf, feat, grad = ops.sdf_taps(gg, cu(pts), MN, MX, disp, vs, use_grad_norm=norm, xyz_order=xyz_order, want_sdf=True)
+    finite = torch.isfinite(grad_r).all(-1)
+    close(sdf, sdf_r, 1e-5, 1e-6); close(feat, feat_r, 1e-5, 1e-6)
+    close(grad[cu(finite)], grad_r[finite], 1e-4 if norm else 2e-5, 1e-5 if norm else 2e-5)
+    ((sdf * cu(g1)).sum() + (feat * cu(g2)).sum() + (grad * cu(g3)).sum()).backward()
+    close(gg.grad, gr.grad, 1e-4, 2e-4 * float(gr.grad.abs().max()))
+
+
+def test_neus_alpha_forward_backward():
+    from voxurf_b200 import ops
+    rs = np.random.RandomState(4)
+    n, n_rays = 20000, 64
+    vd = T(S.make_rays(n_rays, seed=5)[2])
+    rid = T(np.sort(rs.randint(0, n_rays, n)).astype(np.int64))
+    sdf = T((rs.standard_normal(n) * 0.02).astype(np.float32)).requires_grad_(True)
+    grad = T(rs.standard_normal((n, 3)).astype(np.float32)).requires_grad_(True)
+    s_val = float(torch.ones(1) * R.s_val_schedule(15001, 50, 0.05))
+    dist = float(np.float32(0.5 * 2 / 256))
+    ref = R.neus_alpha_from_sdf_scatter(vd, rid, dist, sdf, grad, s_val)
+    ga = T(rs.standard_normal(n).astype(np.float32))
+    ref.backward(ga)
+    s2, g2 = cu(sdf.detach()).requires_grad_(True), cu(grad.detach()).requires_grad_(True)
+    for ids in (cu(rid), cu(rid).int()):
+        s2.grad = g2.grad = None
+        out = ops.neus_alpha(cu(vd), ids, s2, g2, dist, float(np.float32(1.0) / np.float32(s_val)))
+        close(out, ref, 1e-5, 2e-6)
+        out.backward(cu(ga))
+        scale = float(sdf.grad.abs().max())
+        close(s2.grad, sdf.grad, 1e-4, 1e-4 * scale); close(g2.grad, grad.grad, 1e-4, 1e-4 * float(grad.grad.abs().max()))
+
+
+def test_segment_coo():
+    from voxurf_b200.torch_scatter import segment_coo
+    rs = np.random.RandomState(6)
+    rid = _ragged_ray_ids(500, rs, max_len=40)
+    for K_ in (1, 3, 7):
+        src = T(rs.standard_normal((rid.shape[0], K_)).astype(np.float32)).requires_grad_(True)
+        ref = R.segment_coo(src, rid, torch.zeros(500, K_))
+        go = T(rs.standard_normal((500, K_)).astype(np.float32))
+        ref.backward(go)
+        s2 = cu(src.detach()).requires_grad_(True)
+        out = segment_coo(s2, cu(rid), out=torch.zeros(500, K_, device=DEV), reduce='sum')
+        close(out, ref, 1e-6, 1e-6)
+        out.backward(cu(go))
+        exact(s2.grad, src.grad)
+
+
+# ------------------------------------------------------------------------------------------------ stencils
+def test_fd_gradient_and_backward():
+    from voxurf_b200 import ops
+    for shape in [(11, 9, 13), (3, 3, 3), (2, 5, 4)]:
+        rs = np.random.RandomState(sum(shape))
+        sdf = T(rs.standard_normal((1, 1) + shape).astype(np.float32)).requires_grad_(True)
+        vs = torch.tensor(0.0625)
+        ref = R.sdf_gradient_grid(sdf, vs)
+        go = T(rs.standard_normal(ref.shape).astype(np.float32))
+        ref.backward(go)
+        s2 = cu(sdf.detach()).requires_grad_(True)
+        out = ops.fd_gradient(s2, float(vs))
+        close(out, ref, 1e-6, 1e-6)
+        out.backward(cu(go))
+        close(s2.grad, sdf.grad, 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize('k,sigma', [(5, 0.8), (3, 0.5), (5, 1.0)])
+def test_gaussian_conv_and_backward(k, sigma):
+    from voxurf_b200 import ops
+    from voxurf_b200.voxurf_fine import SmoothConv
+    for shape in [(12, 10, 14), (5, 4, 6), (2, 3, 2)]:
+        rs = np.random.RandomState(k)
+        x = T(rs.standard_normal((1, 1) + shape).astype(np.float32)).requires_grad_(True)
+        ref = R.conv3d_replicate(x, R.gaussian_kernel3d(k, sigma))
+        go = T(rs.standard_normal(ref.shape).astype(np.float32))
+        ref.backward(go)
+        x2 = cu(x.detach()).requires_grad_(True)
+        out = SmoothConv(k, sigma)(x2)
+        close(out, ref, 1e-5, 1e-6)
+        out.backward(cu(go))
+        close(x2.grad, x.grad, 1e-4, 1e-5)
+
+
+def test_smooth_grad_tv_value_and_gradient():
+    from voxurf_b200 import ops
+    from voxurf_b200.voxurf_fine import _binomial_weights
+    rs = np.random.RandomState(8)
+    shape = (14, 12, 10)
+    sdf = T(rs.standard_normal((1, 1) + shape).astype(np.float32)).requires_grad_(True)
+    mask = T(rs.uniform(0, 1, (1, 1) + shape) > 0.4)
+    vs = torch.tensor(0.1)
+    ref = R.smooth_grad_tv(R.sdf_gradient_grid(sdf, vs), mask, 0.05)
+    ref.backward()
+    s2 = cu(sdf.detach()).requires_grad_(True)
+    out = ops.smooth_grad_tv(ops.fd_gradient(s2, float(vs)), cu(mask[0, 0]), _binomial_weights(), 0.05, int(mask.sum()))
+    close(out, ref, 1e-5, 1e-8)
+    (out * 1.0).backward()
+    close(s2.grad, sdf.grad, 1e-4, 1e-5 * float(sdf.grad.abs().max()))

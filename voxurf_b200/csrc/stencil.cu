@@ -1,0 +1,297 @@
+// Grid-level stencils (SURVEY.md 8a rows A13, A14, A20 and the smooth-gradient TV regulariser).
+//   * finite-difference SDF gradient grid, fwd + adjoint      lib/voxurf_fine.py:440-460
+//   * Gaussian / binomial smoothing Conv3d(k, replicate pad)   lib/voxurf_fine.py:246-258, 236-242
+//     fwd + adjoint (the coarse stage back-propagates through it every iteration, voxurf_coarse.py:531)
+//   * smooth-gradient TV loss                                 lib/voxurf_fine.py:412-421
+//   * total_variation_add_grad / _new                         lib/cuda/total_variation_kernel.cu:14-133
+// All are HBM-bound streaming kernels over (X,Y,Z) grids with Z fastest: threads map to
+// consecutive Z so every access of a warp is one or two 128-byte lines; neighbour planes come
+// from L1/L2.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// central-difference gradient grid ('interpolate' mode): zero on the two boundary planes of an axis
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fd_gradient(const float* __restrict__ sdf, int X, int Y, int Z, float voxel_size,
+                              float* __restrict__ grad /* (3,X,Y,Z) */) {
+  const int64_t V = (int64_t)X * Y * Z;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+    const int k = v % Z, j = (v / Z) % Y, i = v / ((int64_t)Z * Y);
+    const int64_t sX = (int64_t)Y * Z;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (i > 0 && i < X - 1) gx = __fdiv_rn(__fdiv_rn(__fsub_rn(__ldg(sdf + v + sX), __ldg(sdf + v - sX)), 2.f), voxel_size);
+    if (j > 0 && j < Y - 1) gy = __fdiv_rn(__fdiv_rn(__fsub_rn(__ldg(sdf + v + Z), __ldg(sdf + v - Z)), 2.f), voxel_size);
+    if (k > 0 && k < Z - 1) gz = __fdiv_rn(__fdiv_rn(__fsub_rn(__ldg(sdf + v + 1), __ldg(sdf + v - 1)), 2.f), voxel_size);
+    grad[v] = gx; grad[V + v] = gy; grad[2 * V + v] = gz;
+  }
+}
+
+// adjoint: dsdf[u] += dG_x[u - eX]/(2 vs) (if u-eX interior in x) - dG_x[u + eX]/(2 vs) (if interior) + ...
+__global__ void k_fd_gradient_bwd(const float* __restrict__ dgrad, int X, int Y, int Z, float voxel_size,
+                                  float* __restrict__ dsdf) {
+  const int64_t V = (int64_t)X * Y * Z;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+    const int k = v % Z, j = (v / Z) % Y, i = v / ((int64_t)Z * Y);
+    const int64_t sX = (int64_t)Y * Z;
+    float acc = 0.f;
+    if (i - 1 > 0 && i - 1 < X - 1) acc += __ldg(dgrad + v - sX);
+    if (i + 1 > 0 && i + 1 < X - 1) acc -= __ldg(dgrad + v + sX);
+    if (j - 1 > 0 && j - 1 < Y - 1) acc += __ldg(dgrad + V + v - Z);
+    if (j + 1 > 0 && j + 1 < Y - 1) acc -= __ldg(dgrad + V + v + Z);
+    if (k - 1 > 0 && k - 1 < Z - 1) acc += __ldg(dgrad + 2 * V + v - 1);
+    if (k + 1 > 0 && k + 1 < Z - 1) acc -= __ldg(dgrad + 2 * V + v + 1);
+    dsdf[v] += (acc / voxel_size) * 0.5f;
+  }
+}
+
+static int grid_blocks(int64_t V) { return (int)min((int64_t)vx_blocks(V, 256), (int64_t)vx_num_sms() * 16); }
+
+VX_API int vx_fd_gradient(const float* sdf, int X, int Y, int Z, float voxel_size, float* grad, cudaStream_t st) {
+  const int64_t V = (int64_t)X * Y * Z;
+  if (V <= 0) return 0;
+  k_fd_gradient<<<grid_blocks(V), 256, 0, st>>>(sdf, X, Y, Z, voxel_size, grad);
+  return vx_check_launch("vx_fd_gradient");
+}
+
+VX_API int vx_fd_gradient_backward(const float* dgrad, int X, int Y, int Z, float voxel_size, float* dsdf,
+                                   cudaStream_t st) {
+  const int64_t V = (int64_t)X * Y * Z;
+  if (V <= 0) return 0;
+  k_fd_gradient_bwd<<<grid_blocks(V), 256, 0, st>>>(dgrad, X, Y, Z, voxel_size, dsdf);
+  return vx_check_launch("vx_fd_gradient_backward");
+}
+
+// ---------------------------------------------------------------------------------------------
+// k^3 convolution with replicate padding over B independent (X,Y,Z) volumes, k in {3,5};
+// weights (k,k,k) in constant-cache friendly kernel-argument space.
+// ---------------------------------------------------------------------------------------------
+struct VxKernel3 {
+  int k;
+  float w[125];
+};
+
+__global__ void k_conv3d_replicate(const float* __restrict__ in, int B, int X, int Y, int Z, VxKernel3 ker,
+                                   float* __restrict__ out) {
+  const int64_t V = (int64_t)X * Y * Z;
+  const int p = ker.k / 2;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < V * B; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t % V;
+    const float* src = in + (t / V) * V;
+    const int z = v % Z, y = (v / Z) % Y, x = v / ((int64_t)Z * Y);
+    float acc = 0.f;
+    for (int a = 0; a < ker.k; ++a) {
+      const int xx = min(max(x + a - p, 0), X - 1);
+      for (int b = 0; b < ker.k; ++b) {
+        const int yy = min(max(y + b - p, 0), Y - 1);
+        const float* row = src + ((int64_t)xx * Y + yy) * Z;
+        for (int c = 0; c < ker.k; ++c) {
+          const int zz = min(max(z + c - p, 0), Z - 1);
+          acc += __ldg(row + zz) * ker.w[(a * ker.k + b) * ker.k + c];
+        }
+      }
+    }
+    out[t] = acc;
+  }
+}
+
+// adjoint (gather form): din[u] = sum_o w[o] * sum_{v : clamp(v + o) == u} dout[v].  Per axis the
+// pre-image of u under v -> clamp(v + o) is the single point u - o for interior u and a short
+// range on the two boundary planes.
+__device__ __forceinline__ void preimage(int u, int o, int n, int& lo, int& hi) {
+  if (u > 0 && u < n - 1) { lo = hi = u - o; if (lo < 0 || lo > n - 1) { lo = 1; hi = 0; } }
+  else if (n == 1) { lo = 0; hi = 0; }
+  else if (u == 0) { lo = 0; hi = min(-o, n - 1); }           // v + o <= 0
+  else { lo = max(n - 1 - o, 0); hi = n - 1; }                // v + o >= n-1
+}
+
+__global__ void k_conv3d_replicate_bwd(const float* __restrict__ dout, int B, int X, int Y, int Z, VxKernel3 ker,
+                                       int accumulate, float* __restrict__ din) {
+  const int64_t V = (int64_t)X * Y * Z;
+  const int p = ker.k / 2;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < V * B; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t % V;
+    const float* src = dout + (t / V) * V;
+    const int z = v % Z, y = (v / Z) % Y, x = v / ((int64_t)Z * Y);
+    float acc = 0.f;
+    for (int a = 0; a < ker.k; ++a) {
+      int xl, xh;
+      preimage(x, a - p, X, xl, xh);
+      for (int b = 0; b < ker.k; ++b) {
+        int yl, yh;
+        preimage(y, b - p, Y, yl, yh);
+        for (int c = 0; c < ker.k; ++c) {
+          int zl, zh;
+          preimage(z, c - p, Z, zl, zh);
+          float s = 0.f;
+          for (int xx = xl; xx <= xh; ++xx)
+            for (int yy = yl; yy <= yh; ++yy)
+              for (int zz = zl; zz <= zh; ++zz) s += __ldg(src + ((int64_t)xx * Y + yy) * Z + zz);
+          acc += s * ker.w[(a * ker.k + b) * ker.k + c];
+        }
+      }
+    }
+    din[t] = accumulate ? din[t] + acc : acc;
+  }
+}
+
+static int fill_kernel(VxKernel3& k, const float* w_host, int ksize) {
+  if (ksize != 1 && ksize != 3 && ksize != 5) return -1;
+  k.k = ksize;
+  for (int i = 0; i < ksize * ksize * ksize; ++i) k.w[i] = w_host[i];
+  return 0;
+}
+
+VX_API int vx_conv3d_replicate(const float* in, int B, int X, int Y, int Z, const float* weight_host, int ksize,
+                               float* out, cudaStream_t st) {
+  VxKernel3 ker;
+  VX_REQUIRE(fill_kernel(ker, weight_host, ksize) == 0, "vx_conv3d_replicate", "ksize must be 1, 3 or 5");
+  const int64_t n = (int64_t)X * Y * Z * B;
+  if (n <= 0) return 0;
+  k_conv3d_replicate<<<grid_blocks(n), 256, 0, st>>>(in, B, X, Y, Z, ker, out);
+  return vx_check_launch("vx_conv3d_replicate");
+}
+
+VX_API int vx_conv3d_replicate_backward(const float* dout, int B, int X, int Y, int Z, const float* weight_host,
+                                        int ksize, int accumulate, float* din, cudaStream_t st) {
+  VxKernel3 ker;
+  VX_REQUIRE(fill_kernel(ker, weight_host, ksize) == 0, "vx_conv3d_replicate_backward", "ksize must be 1, 3 or 5");
+  const int64_t n = (int64_t)X * Y * Z * B;
+  if (n <= 0) return 0;
+  k_conv3d_replicate_bwd<<<grid_blocks(n), 256, 0, st>>>(dout, B, X, Y, Z, ker, accumulate, din);
+  return vx_check_launch("vx_conv3d_replicate_backward");
+}
+
+// ---------------------------------------------------------------------------------------------
+// smooth-gradient TV (lib/voxurf_fine.py:417-420):
+//   E_a = tv_smooth_conv(G_a).detach() - G_a ;  loss = w * mean(E[mask x 3]^2)
+// pass 1 (this kernel): E from the materialised FD gradient G (3,X,Y,Z); writes dL/dG (3,X,Y,Z)
+//   = -2 * w / (3 * n_mask) * E * mask  and per-block partial sums of E^2 (deterministic 2-stage sum).
+// pass 2: vx_fd_gradient_backward pushes dL/dG into the sdf gradient.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_smooth_grad_tv(const float* __restrict__ G, const bool* __restrict__ mask, int X, int Y, int Z,
+                                 VxKernel3 ker, float scale /* w / (3 n_mask) */, float* __restrict__ dG,
+                                 float* __restrict__ partial) {
+  __shared__ float red[32];
+  const int64_t V = (int64_t)X * Y * Z;
+  float local = 0.f;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 3 * V; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t % V;
+    float d = 0.f;
+    if (mask[v]) {
+      const float* src = G + (t / V) * V;
+      const int z = v % Z, y = (v / Z) % Y, x = v / ((int64_t)Z * Y);
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const int xx = min(max(x + a - 1, 0), X - 1);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const int yy = min(max(y + b - 1, 0), Y - 1);
+          const float* row = src + ((int64_t)xx * Y + yy) * Z;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc += __ldg(row + min(max(z + c - 1, 0), Z - 1)) * ker.w[(a * 3 + b) * 3 + c];
+        }
+      }
+      const float e = acc - __ldg(src + v);
+      local += e * e;
+      d = -2.f * scale * e;
+    }
+    dG[t] = d;
+  }
+  // block reduction in a fixed order
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void k_sum_partials(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) out[0] = t * scale;
+  }
+}
+
+// scratch: at least vx_smooth_grad_tv_scratch_floats() floats
+VX_API int vx_smooth_grad_tv_scratch_floats() { return vx_num_sms() * 16; }
+
+VX_API int vx_smooth_grad_tv(const float* G, const bool* mask, int X, int Y, int Z, const float* weight3_host,
+                             float w_over_3n, float* dG, float* scratch, float* loss_out, cudaStream_t st) {
+  VxKernel3 ker;
+  VX_REQUIRE(fill_kernel(ker, weight3_host, 3) == 0, "vx_smooth_grad_tv", "bad kernel");
+  const int64_t n = (int64_t)X * Y * Z * 3;
+  if (n <= 0) return 0;
+  const int blocks = grid_blocks(n);
+  k_smooth_grad_tv<<<blocks, 256, 0, st>>>(G, mask, X, Y, Z, ker, w_over_3n, dG, scratch);
+  int rc = vx_check_launch("vx_smooth_grad_tv");
+  if (rc) return rc;
+  if (loss_out) {
+    k_sum_partials<<<1, 1024, 0, st>>>(scratch, blocks, w_over_3n, loss_out);
+    rc = vx_check_launch("vx_smooth_grad_tv(sum)");
+  }
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// total_variation_add_grad (total_variation_kernel.cu:14-35; axis-weight quirk kept: the k and the i
+// axis both use wz, wx is unused) and total_variation_add_grad_new (:39-66; wx on k, wy on j, wz on i,
+// each term times mask[idx]*mask[nb]).  Host divides the weights by 6 (:76-78).
+// ---------------------------------------------------------------------------------------------
+// One neighbour's contribution: w * clamp(p - q, -1, 1) [* mask_here * mask_there].  The six
+// contributions are accumulated in the reference's order (k-, k+, j-, j+, i-, i+) into a local sum
+// that is added to grad once, so rounding matches the reference kernel.
+template <bool kMasked>
+__device__ __forceinline__ float tv_pull(const float* __restrict__ param, const float* __restrict__ mask, size_t here,
+                                         size_t there, float w) {
+  float t = w * fminf(fmaxf(param[here] - param[there], -1.f), 1.f);
+  if (kMasked) t = t * mask[here] * mask[there];
+  return t;
+}
+
+template <bool kDense, bool kMasked>
+__global__ void k_total_variation_add_grad(const float* __restrict__ param, float* __restrict__ grad,
+                                           const float* __restrict__ mask, float w_fast, float w_mid, float w_slow,
+                                           size_t nx, size_t ny, size_t nz, size_t N) {
+  const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  if (!kDense && grad[v] == 0) return;  // sparse mode touches only voxels that already have a gradient
+  const size_t z = v % nz, y = (v / nz) % ny, x = (v / nz / ny) % nx;  // (channel folds into the leading index)
+  const size_t sy = nz, sx = nz * ny;
+  float add = 0;
+  if (z != 0) add += tv_pull<kMasked>(param, mask, v, v - 1, w_fast);
+  if (z != nz - 1) add += tv_pull<kMasked>(param, mask, v, v + 1, w_fast);
+  if (y != 0) add += tv_pull<kMasked>(param, mask, v, v - sy, w_mid);
+  if (y != ny - 1) add += tv_pull<kMasked>(param, mask, v, v + sy, w_mid);
+  if (x != 0) add += tv_pull<kMasked>(param, mask, v, v - sx, w_slow);
+  if (x != nx - 1) add += tv_pull<kMasked>(param, mask, v, v + sx, w_slow);
+  grad[v] += add;
+}
+
+// param/grad: (C, nx, ny, nz) channel-major contiguous, N = numel.  Weight routing follows the
+// reference: without a mask the fastest AND the slowest axis use wz and wx is ignored
+// (total_variation_kernel.cu:27-32); with a mask it is wx (fastest), wy, wz (slowest) (:53-58).
+VX_API int vx_total_variation_add_grad(const float* param, float* grad, const float* mask, float wx, float wy, float wz,
+                                       int dense_mode, int64_t sz_i, int64_t sz_j, int64_t sz_k, int64_t N,
+                                       cudaStream_t st) {
+  if (N <= 0) return 0;
+  const int threads = 256;
+  const int blocks = (int)((N + threads - 1) / threads);
+  wx /= 6; wy /= 6; wz /= 6;  // :76-78
+  const float w_fast = mask ? wx : wz, w_mid = wy, w_slow = wz;
+#define VX_TV(D, M) k_total_variation_add_grad<D, M><<<blocks, threads, 0, st>>>(param, grad, mask, w_fast, w_mid, w_slow, (size_t)sz_i, (size_t)sz_j, (size_t)sz_k, (size_t)N)
+  if (mask) { if (dense_mode) VX_TV(true, true); else VX_TV(false, true); }
+  else { if (dense_mode) VX_TV(true, false); else VX_TV(false, false); }
+#undef VX_TV
+  return vx_check_launch("vx_total_variation_add_grad");
+}
