@@ -154,6 +154,12 @@ int vx_smooth_grad_tv_scratch_floats(void);
 int vx_smooth_grad_tv(const float* G, const bool* mask, int X, int Y, int Z, const float* weight3_host,
                       float w_over_3n, float* dG, float* scratch, float* loss_out, cudaStream_t stream);
 
+/* total_variation(v, mask)  lib/voxurf_fine.py:956-969 (autograd form used by the coarse stage): loss_out[0] = tv,
+ * grad = d tv / d v.  mask (X,Y,Z) bool shared by the C channels or NULL; inv_cnt_host[a] = 1/(3 * #pairs on axis a);
+ * scratch: 3 * vx_smooth_grad_tv_scratch_floats() floats */
+int vx_total_variation_l1(const float* v, const bool* mask, int C, int X, int Y, int Z, const float* inv_cnt_host,
+                          float* grad, float* scratch, float* loss_out, cudaStream_t stream);
+
 /* ---- fused ray march (replaces sample_pts_on_rays + two compactions + MaskCache.forward) ---- */
 /* lib/voxurf_fine.py:593-617,631-636,917-942.  bits_* need (offsets[n_rays] >> 5) + n_rays + 1 words. */
 int vx_march_flags(const float* rays_start, const float* rays_dir, const float* xyz_min, const float* xyz_max,

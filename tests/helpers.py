@@ -114,3 +114,22 @@ def product_fine_model(sc, device='cuda', apply_nonempty=True, k0_channels_last=
     if m.mask_cache is not None and apply_nonempty:
         m._set_nonempty_mask()
     return m
+
+
+def product_coarse_model(sc, device='cuda', apply_nonempty=True, k0_channels_last=False):
+    from voxurf_b200 import voxurf_coarse as VC
+    G = sc['G']
+    cfg = {k: v for k, v in S.COARSE_CFG.items() if k != 'stepsize'}
+    cfg['rgbnet_dim'], cfg['rgbnet_width'] = sc['C'], sc['width']
+    m = VC.Voxurf(xyz_min=[-1., -1., -1.], xyz_max=[1., 1., 1.], num_voxels=G ** 3, num_voxels_base=G ** 3,
+                  rgbnet_direct=True, k0_channels_last=k0_channels_last,
+                  mask_cache_state=mask_cache_state(sc) if 'mask_density' in sc else None, **cfg)
+    assert tuple(int(w) for w in m.world_size) == (G, G, G)
+    m.sdf.grid.data = T(sc['sdf']).clone()
+    k0 = T(sc['k0']).clone()
+    m.k0.grid.data = k0.contiguous(memory_format=torch.channels_last_3d) if k0_channels_last else k0
+    set_mlp(m.rgbnet, sc['rgbnet'])
+    m = m.to(device)
+    if m.mask_cache is not None and apply_nonempty:
+        m._set_nonempty_mask()
+    return m

@@ -186,7 +186,7 @@ def test_adam_upd_reference_cuda_semantics(mode):
         else:
             ad.adam_upd_with_perlr(pc, cu(g), mc, vc, cu(perlr), step, 0.9, 0.99, 0.1, 1e-8)
         K.adam_upd(p, g, m, v, step, 0.9, 0.99, 0.1, 1e-8, mode=mode, perlr=perlr if mode == 2 else None)
-        close(pc, p, 1e-6, 1e-7); close(mc, m, 1e-6, 1e-8); close(vc, v, 1e-6, 1e-9)
+        close(pc, p, 1e-6, 1e-6); close(mc, m, 1e-6, 1e-7); close(vc, v, 1e-6, 1e-8)
 
 
 def test_trainer_adam_semantics_and_fused_zero_grad():

@@ -137,4 +137,4 @@ def test_adam_upd_vs_reference(mode):
             ad.adam_upd_with_perlr(B[0], gd, B[1], B[2], perlr, step, 0.9, 0.99, 0.1, 1e-8)
         K.adam_upd(C[0], g, C[1], C[2], step, 0.9, 0.99, 0.1, 1e-8, mode=mode, perlr=perlr.cpu() if mode == 2 else None)
         for x, y, z in zip(A, B, C):
-            close(y, x, 1e-6, 1e-7, 'ours vs reference'); close(z, x, 1e-6, 1e-7, 'C oracle vs reference')
+            close(y, x, 1e-6, 1e-6, 'ours vs reference'); close(z, x, 1e-6, 1e-6, 'C oracle vs reference')

@@ -295,3 +295,86 @@ VX_API int vx_total_variation_add_grad(const float* param, float* grad, const fl
 #undef VX_TV
   return vx_check_launch("vx_total_variation_add_grad");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Autograd-form total variation (lib/voxurf_fine.py:956-969, used by the coarse stage through
+// density_total_variation(sdf_tv) / k0_total_variation, lib/voxurf_coarse.py:300-320):
+//   tv = (mean_x + mean_y + mean_z) / 3,  mean_a = mean over neighbour pairs along a with both voxels in the mask
+//        of |v[next] - v[here]|
+// One pass produces the three pair sums (deterministic two-stage reduction) and d tv / d v in gather form.
+// mask: (X,Y,Z) bool shared by all channels, or nullptr.  inv_cnt_host[a] = 1 / (3 * number of masked pairs on a).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sgnf(float d) { return (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); }
+
+__global__ void k_tv_l1(const float* __restrict__ v, const bool* __restrict__ mask, int C, int X, int Y, int Z,
+                        float sx, float sy, float sz, float* __restrict__ grad, float* __restrict__ partial) {
+  __shared__ float red[3][32];
+  const int64_t V = (int64_t)X * Y * Z;
+  float lx = 0.f, ly = 0.f, lz = 0.f;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < V * C; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = t % V;
+    const int k = u % Z, j = (u / Z) % Y, i = u / ((int64_t)Z * Y);
+    const int64_t sX = (int64_t)Y * Z;
+    const bool here = mask ? mask[u] : true;
+    float g = 0.f;
+    if (here) {
+      const float c = __ldg(v + t);
+      if (i + 1 < X && (!mask || mask[u + sX])) { const float d = __ldg(v + t + sX) - c; lx += fabsf(d); g -= sgnf(d) * sx; }
+      if (i > 0 && (!mask || mask[u - sX])) { g += sgnf(c - __ldg(v + t - sX)) * sx; }
+      if (j + 1 < Y && (!mask || mask[u + Z])) { const float d = __ldg(v + t + Z) - c; ly += fabsf(d); g -= sgnf(d) * sy; }
+      if (j > 0 && (!mask || mask[u - Z])) { g += sgnf(c - __ldg(v + t - Z)) * sy; }
+      if (k + 1 < Z && (!mask || mask[u + 1])) { const float d = __ldg(v + t + 1) - c; lz += fabsf(d); g -= sgnf(d) * sz; }
+      if (k > 0 && (!mask || mask[u - 1])) { g += sgnf(c - __ldg(v + t - 1)) * sz; }
+    }
+    grad[t] = g;
+  }
+  float l[3] = {lx, ly, lz};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int o = 16; o > 0; o >>= 1) l[a] += __shfl_down_sync(0xffffffffu, l[a], o);
+    if ((threadIdx.x & 31) == 0) red[a][threadIdx.x >> 5] = l[a];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float s = (threadIdx.x < (blockDim.x >> 5)) ? red[a][threadIdx.x] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (threadIdx.x == 0) partial[a * gridDim.x + blockIdx.x] = s;
+    }
+  }
+}
+
+__global__ void k_tv_l1_finish(const float* __restrict__ partial, int n, float sx, float sy, float sz,
+                               float* __restrict__ out) {
+  __shared__ float red[32];
+  float tot = 0.f;
+  for (int a = 0; a < 3; ++a) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[a * n + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      if (threadIdx.x == 0) tot += t * (a == 0 ? sx : (a == 1 ? sy : sz));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = tot;
+}
+
+// scratch: 3 * vx_smooth_grad_tv_scratch_floats() floats
+VX_API int vx_total_variation_l1(const float* v, const bool* mask, int C, int X, int Y, int Z,
+                                 const float* inv_cnt_host, float* grad, float* scratch, float* loss_out,
+                                 cudaStream_t st) {
+  const int64_t n = (int64_t)X * Y * Z * C;
+  if (n <= 0) return 0;
+  const int blocks = grid_blocks(n);
+  k_tv_l1<<<blocks, 256, 0, st>>>(v, mask, C, X, Y, Z, inv_cnt_host[0], inv_cnt_host[1], inv_cnt_host[2], grad, scratch);
+  int rc = vx_check_launch("vx_total_variation_l1");
+  if (rc) return rc;
+  k_tv_l1_finish<<<1, 1024, 0, st>>>(scratch, blocks, inv_cnt_host[0], inv_cnt_host[1], inv_cnt_host[2], loss_out);
+  return vx_check_launch("vx_total_variation_l1(sum)");
+}

@@ -48,8 +48,8 @@ class _GridGather(torch.autograd.Function):
     def backward(ctx, grad_out):
         (xyz,) = ctx.saved_tensors
         X, Y, Z, C, cl, xyz_min, xyz_max, shape = ctx.geom
-        gg = torch.zeros(shape, dtype=torch.float32, device=xyz.device,
-                         memory_format=torch.channels_last_3d if cl else torch.contiguous_format)
+        gg = torch.empty(shape, dtype=torch.float32, device=xyz.device,
+                         memory_format=torch.channels_last_3d if cl else torch.contiguous_format).zero_()
         call('vx_grid_gather_backward', X, Y, Z, C, cl, xyz_min, xyz_max, xyz, None, None, None, None, 0.0, None,
              xyz.shape[0], grad_out.contiguous(), _dense_storage(gg))
         return gg, None, None, None
@@ -224,3 +224,38 @@ class _SmoothGradTV(torch.autograd.Function):
 def smooth_grad_tv(gradient, nonempty_mask, weight3_host, smooth_grad_tv_weight, n_mask):
     return _SmoothGradTV.apply(gradient.contiguous(), nonempty_mask.contiguous(), weight3_host,
                                float(smooth_grad_tv_weight) / (3.0 * float(n_mask)))
+
+
+class _TotalVariationL1(torch.autograd.Function):
+    """total_variation(v, mask): lib/voxurf_fine.py:956-969."""
+
+    @staticmethod
+    def forward(ctx, v, mask, inv_cnt):
+        C, X, Y, Z = v.shape[1:]
+        grad = torch.empty_like(v)
+        scratch = torch.empty(3 * int(call('vx_smooth_grad_tv_scratch_floats')), dtype=torch.float32, device=v.device)
+        loss = torch.empty(1, dtype=torch.float32, device=v.device)
+        call('vx_total_variation_l1', v, mask, C, X, Y, Z, inv_cnt, grad, scratch, loss)
+        ctx.save_for_backward(grad)
+        return loss[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+def tv_pair_counts(mask, shape):
+    """Number of neighbour pairs per axis with both voxels inside `mask` ((X,Y,Z) bool or None). One-off, host side."""
+    X, Y, Z = shape
+    if mask is None:
+        return [(X - 1) * Y * Z, X * (Y - 1) * Z, X * Y * (Z - 1)]
+    return [int((mask[:-1] & mask[1:]).sum()), int((mask[:, :-1] & mask[:, 1:]).sum()),
+            int((mask[:, :, :-1] & mask[:, :, 1:]).sum())]
+
+
+def total_variation_l1(v, mask, pair_counts):
+    """v (1,C,X,Y,Z) channel-major; mask (X,Y,Z) bool or None; pair_counts from tv_pair_counts (per channel)."""
+    inv = [1.0 / (3.0 * max(c, 1) * v.shape[1]) for c in pair_counts]
+    return _TotalVariationL1.apply(v.contiguous(), mask, inv)

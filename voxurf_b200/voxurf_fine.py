@@ -30,42 +30,10 @@ from ._lib import call
 from .grid import MaskCache  # noqa: F401  (lib/voxurf_fine.py:917 lives next to the model in the reference)
 from .ops import Alphas2Weights  # noqa: F401
 from .torch_scatter import segment_coo
+from ._base import SmoothConv, VoxurfBase, _binomial_weights, _gaussian_weights, _mlp  # noqa: F401
 
 
-def _gaussian_weights(ksize, sigma):
-    """lib/voxurf_fine.py:246-254 -> flat python list (k^3,), float32-rounded like the reference's Conv3d weight."""
-    r = np.arange(-(ksize // 2), ksize // 2 + 1, 1)
-    xx, yy, zz = np.meshgrid(r, r, r)
-    k = torch.from_numpy(np.exp(-(xx ** 2 + yy ** 2 + zz ** 2) / (2 * sigma ** 2))).float()
-    return (k / k.sum()).flatten().tolist()
-
-
-def _binomial_weights():
-    """tv_smooth_conv weights, lib/voxurf_fine.py:208-239 with sigma = 0."""
-    k = np.asarray([[[1, 2, 1], [2, 4, 2], [1, 2, 1]], [[2, 4, 2], [4, 8, 4], [2, 4, 2]], [[1, 2, 1], [2, 4, 2], [1, 2, 1]]],
-                   dtype=np.float64)
-    return torch.from_numpy(k / k.sum()).float().flatten().tolist()
-
-
-class SmoothConv:
-    """Callable stand-in for the frozen nn.Conv3d the reference builds in _gaussian_3dconv."""
-
-    def __init__(self, ksize, sigma):
-        self.ksize, self.sigma = ksize, sigma
-        self.weight_host = _gaussian_weights(ksize, sigma)
-
-    def __call__(self, x):
-        return ops.conv3d_replicate(x, self.weight_host, self.ksize)
-
-
-def _mlp(dim0, width, depth):
-    return nn.Sequential(
-        nn.Linear(dim0, width), nn.ReLU(inplace=True),
-        *[nn.Sequential(nn.Linear(width, width), nn.ReLU(inplace=True)) for _ in range(depth - 2)],
-        nn.Linear(width, 3))
-
-
-class Voxurf(nn.Module):
+class Voxurf(VoxurfBase):
     def __init__(self, xyz_min, xyz_max, num_voxels=0, num_voxels_base=0, alpha_init=None, nearest=False,
                  mask_cache_path=None, mask_cache_thres=1e-3, fast_color_thres=0, rgbnet_dim=0, rgbnet_direct=False,
                  rgbnet_full_implicit=False, rgbnet_depth=3, rgbnet_width=128, posbase_pe=5, viewbase_pe=4,
@@ -79,27 +47,9 @@ class Voxurf(nn.Module):
         if nearest or use_layer_norm or s_learn or rgbnet_dim <= 0 or not use_rgb_k or use_rgbnet_k0 \
                 or not (k_detach_1 and k_detach_2) or grad_mode != 'interpolate':
             raise NotImplementedError('option outside the configurations the reference ships (configs/*/fine.py)')
-        self.register_buffer('xyz_min', torch.Tensor(list(xyz_min)))
-        self.register_buffer('xyz_max', torch.Tensor(list(xyz_max)))
-        self._min_host = [float(v) for v in xyz_min]
-        self._max_host = [float(v) for v in xyz_max]
-        self.fast_color_thres = fast_color_thres
-        self.nearest = nearest
+        self._init_common(xyz_min, xyz_max, num_voxels, num_voxels_base, alpha_init, s_ratio, s_start, s_learn,
+                          step_start, fast_color_thres, nearest)
         self.smooth_scale = smooth_scale
-        self.s_ratio, self.s_start, self.s_learn, self.step_start = s_ratio, s_start, s_learn, step_start
-        self.s_val = nn.Parameter(torch.ones(1) * s_start, requires_grad=False)   # lib/voxurf_fine.py:61-62
-        self.sdf_init_mode = 'ball_init'
-        self.num_voxels_base = num_voxels_base
-        self.voxel_size_base = ((self.xyz_max - self.xyz_min).prod() / self.num_voxels_base).pow(1 / 3)
-        self.alpha_init = alpha_init
-        self.act_shift = np.log(1 / (1 - alpha_init) - 1)
-        self._set_grid_resolution(num_voxels)
-        self.density = nn.Parameter(torch.zeros([1, 1, *self.world_size]))
-        self.sdf = grid.create_grid('DenseGrid', channels=1, world_size=self.world_size, xyz_min=self.xyz_min,
-                                    xyz_max=self.xyz_max)
-        ws = [int(w) for w in self.world_size]
-        x, y, z = np.mgrid[-1.0:1.0:ws[0] * 1j, -1.0:1.0:ws[1] * 1j, -1.0:1.0:ws[2] * 1j]
-        self.sdf.grid.data = torch.from_numpy((x ** 2 + y ** 2 + z ** 2) ** 0.5 - 1).float()[None, None, ...]
         self.init_smooth_conv(smooth_ksize, smooth_sigma)
         self.rgbnet_kwargs = {'rgbnet_dim': rgbnet_dim, 'rgbnet_direct': rgbnet_direct,
                               'rgbnet_full_implicit': rgbnet_full_implicit, 'rgbnet_depth': rgbnet_depth,
@@ -126,34 +76,10 @@ class Voxurf(nn.Module):
         k_dim0 += (3 if k_res else 0) + (1 if k_center_sdf else 0) + len(self.k_grad_feat) * 3 + len(self.k_sdf_feat) * 6
         self.k_rgbnet = _mlp(k_dim0, rgbnet_width, k_rgbnet_depth)
         # (the reference zeroes rgbnet[-1].bias twice and leaves k_rgbnet's at its default, lib/voxurf_fine.py:185)
-        self.mask_cache_path, self.mask_cache_thres = mask_cache_path, mask_cache_thres
-        if mask_cache_state is not None or (mask_cache_path is not None and mask_cache_path):
-            self.mask_cache = MaskCache(path=mask_cache_path, mask_cache_thres=mask_cache_thres, state=mask_cache_state)
-        else:
-            self.mask_cache = None
-        self.nonempty_mask = None
+        self._init_mask_cache(mask_cache_path, mask_cache_thres, mask_cache_state)
         self.grad_mode = grad_mode
-        self._tv_smooth_w = _binomial_weights()
-        self.gradient = None
 
     # ------------------------------------------------------------------ construction helpers
-    def _set_grid_resolution(self, num_voxels):
-        """lib/voxurf_fine.py:315-324"""
-        self.num_voxels = num_voxels
-        self.voxel_size = ((self.xyz_max - self.xyz_min).prod() / num_voxels).pow(1 / 3)
-        self.world_size = ((self.xyz_max - self.xyz_min) / self.voxel_size).long()
-        self.voxel_size_ratio = self.voxel_size / self.voxel_size_base
-        self._voxel_size_host = float(self.voxel_size)
-
-    def init_smooth_conv(self, ksize=3, sigma=1):
-        """lib/voxurf_fine.py:268-272"""
-        self.smooth_sdf = ksize > 0
-        if self.smooth_sdf:
-            self.smooth_conv = SmoothConv(ksize, sigma)
-
-    def _gaussian_3dconv(self, ksize=3, sigma=1):
-        return SmoothConv(ksize, sigma)
-
     def get_kwargs(self):
         """lib/voxurf_fine.py:326-342"""
         return {'xyz_min': self.xyz_min.cpu().numpy(), 'xyz_max': self.xyz_max.cpu().numpy(),
@@ -162,25 +88,6 @@ class Voxurf(nn.Module):
                 'mask_cache_thres': self.mask_cache_thres, 'fast_color_thres': self.fast_color_thres,
                 'grad_feat': self.grad_feat, 'sdf_feat': self.sdf_feat, 'k_grad_feat': self.k_grad_feat,
                 'k_sdf_feat': self.k_sdf_feat, **self.rgbnet_kwargs}
-
-    def get_MaskCache_kwargs(self):
-        """lib/voxurf_fine.py:344-351"""
-        return {'xyz_min': self.xyz_min.cpu().numpy(), 'xyz_max': self.xyz_max.cpu().numpy(),
-                'act_shift': self.act_shift, 'voxel_size_ratio': self.voxel_size_ratio, 'nearest': self.nearest}
-
-    @torch.no_grad()
-    def _set_nonempty_mask(self):
-        """lib/voxurf_fine.py:353-367: mask-cache query on the grid lattice; empty voxels get sdf = 1."""
-        dev = self.sdf.grid.device
-        ws = self.density.shape[2:]
-        xyz = torch.stack(torch.meshgrid(
-            torch.linspace(self._min_host[0], self._max_host[0], ws[0]),
-            torch.linspace(self._min_host[1], self._max_host[1], ws[1]),
-            torch.linspace(self._min_host[2], self._max_host[2], ws[2]), indexing='ij'), -1).to(dev)
-        self.nonempty_mask = self.mask_cache(xyz)[None, None].contiguous()
-        self._n_nonempty = int(self.nonempty_mask.sum().item())
-        self.density[~self.nonempty_mask] = -100
-        self.sdf.grid[~self.nonempty_mask] = 1
 
     def init_sdf_from_sdf(self, sdf0=None, smooth=False, reduce=1., ksize=3, sigma=1., zero2neg=True):
         """lib/voxurf_fine.py:280-296 (coarse -> fine hand-off; once, off the hot path)."""
@@ -198,28 +105,7 @@ class Voxurf(nn.Module):
                 self.sdf.grid = nn.Parameter(SmoothConv(5, 1)(self.sdf.grid.data))
             self.gradient = self.neus_sdf_gradient()
 
-    @torch.no_grad()
-    def scale_volume_grid(self, num_voxels):
-        """lib/voxurf_fine.py:384-397"""
-        self._set_grid_resolution(num_voxels)
-        ws = tuple(int(w) for w in self.world_size)
-        self.density = nn.Parameter(F.interpolate(self.density.data, size=ws, mode='trilinear', align_corners=True))
-        self.sdf.scale_volume_grid(self.world_size)
-        self.k0.scale_volume_grid(self.world_size)
-        if self.mask_cache is not None:
-            self._set_nonempty_mask()
-
     # ------------------------------------------------------------------ regularisers
-    def sdf_total_variation_add_grad(self, weight, dense_mode):
-        """lib/voxurf_fine.py:403-405"""
-        w = weight * int(self.world_size.max()) / 128
-        self.sdf.total_variation_add_grad(w, w, w, dense_mode)
-
-    def k0_total_variation_add_grad(self, weight, dense_mode):
-        """lib/voxurf_fine.py:407-409"""
-        w = weight * int(self.world_size.max()) / 128
-        self.k0.total_variation_add_grad(w, w, w, dense_mode)
-
     def density_total_variation(self, sdf_tv=0, smooth_grad_tv=0, grad_tv=0, smooth_sdf_tv=0):
         """lib/voxurf_fine.py:412-421 (the smooth_grad_tv branch is the one the shipped configs use)."""
         tv = 0
@@ -229,12 +115,6 @@ class Voxurf(nn.Module):
             tv = tv + ops.smooth_grad_tv(self.gradient, self.nonempty_mask[0, 0], self._tv_smooth_w, smooth_grad_tv,
                                          self._n_nonempty)
         return tv
-
-    def neus_sdf_gradient(self, mode=None, sdf=None):
-        """lib/voxurf_fine.py:440-460 ('interpolate')"""
-        if sdf is None:
-            sdf = self.sdf.grid
-        return ops.fd_gradient(sdf, self._voxel_size_host)
 
     # ------------------------------------------------------------------ samplers
     def grid_sampler(self, xyz, *grids, mode=None, align_corners=True, sample_ret=True, sample_grad=False, displace=0.1,
@@ -255,55 +135,6 @@ class Voxurf(nn.Module):
         return ops.sdf_taps(grids[0], xyz, self._min_host, self._max_host, list(displace_list), self._voxel_size_host,
                             use_grad_norm=use_grad_norm, xyz_order=False, want_sdf=False)
 
-    def _max_steps(self, stepdist):
-        diag = math.sqrt(sum((b - a) ** 2 for a, b in zip(self._min_host, self._max_host)))
-        return int(math.ceil(diag / stepdist)) + 2
-
-    def _march(self, rays_o, rays_d, near, stepsize, want_mask_outbbox=True):
-        """Fused lib/voxurf_fine.py:593-617 + :631-636.  -> dict with int32 ray_id/step_id (M2,), start, dirs, ..."""
-        from . import render_utils_cuda as ru
-        far = 1e9
-        rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
-        N, dev = rays_o.shape[0], rays_o.device
-        stepdist = float(stepsize) * self._voxel_size_host
-        stepdist = float(np.float32(stepdist))
-        t_min, t_max, n_steps, start, dirs, offsets = ru.ray_setup(rays_o, rays_d, self.xyz_min, self.xyz_max, near, far, stepdist)
-        words = N * (self._max_steps(stepdist) // 32 + 2) + 1
-        bits_in = torch.empty(words, dtype=torch.int32, device=dev)
-        bits_keep = torch.empty(words, dtype=torch.int32, device=dev)
-        keep_count = torch.empty(N, dtype=torch.int32, device=dev)
-        keep_off = torch.empty(N + 1, dtype=torch.int32, device=dev)
-        mc = self.mask_cache.march_args() if self.mask_cache is not None else (None, 1, 1, 1, [0., 0., 0.], [1., 1., 1.], 0., 1., 0.)
-        call('vx_march_flags', start, dirs, self.xyz_min, self.xyz_max, offsets, N, stepdist, *mc, bits_in, bits_keep,
-             keep_count, keep_off)
-        totals = torch.stack([offsets[N], keep_off[N].to(torch.int64)]).cpu()   # the ONE sync of sampling
-        M0, M2 = int(totals[0]), int(totals[1])
-        ray_id = torch.empty(M2, dtype=torch.int32, device=dev)
-        step_id = torch.empty(M2, dtype=torch.int32, device=dev)
-        mask_outbbox = torch.empty(M0, dtype=torch.bool, device=dev) if want_mask_outbbox else None
-        call('vx_march_emit', offsets, N, bits_keep, keep_off, M2, ray_id, step_id, mask_outbbox)
-        pts = torch.empty(M2, 3, dtype=torch.float32, device=dev)
-        call('vx_points_from_steps', ray_id, step_id, start, dirs, stepdist, None, M2, pts)
-        return dict(ray_pts=pts, ray_id=ray_id, step_id=step_id, mask_outbbox=mask_outbbox, n_steps=n_steps,
-                    keep_off=keep_off, start=start, dirs=dirs, stepdist=stepdist, t_min=t_min, t_max=t_max)
-
-    def sample_ray(self, rays_o, rays_d, near, far, stepsize, **render_kwargs):
-        """lib/voxurf_fine.py:593-617 (legacy form: in-bbox samples only, int64 ids)."""
-        from . import render_utils_cuda as ru
-        stepdist = float(np.float32(float(stepsize) * self._voxel_size_host))
-        ray_pts, mask_outbbox, ray_id, step_id, N_steps, t_min, t_max = ru.sample_pts_on_rays(
-            rays_o.contiguous(), rays_d.contiguous(), self.xyz_min, self.xyz_max, near, 1e9, stepdist)
-        N_steps = ray_id.unique(return_counts=True)[1]
-        inb = ~mask_outbbox
-        return ray_pts[inb], ray_id[inb], step_id[inb], mask_outbbox, N_steps
-
-    def hit_coarse_geo(self, rays_o, rays_d, near, far, stepsize, **render_kwargs):
-        """lib/voxurf_fine.py:579-591: which rays have at least one sample inside the mask cache."""
-        shape = rays_o.shape[:-1]
-        m = self._march(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), near, stepsize, want_mask_outbbox=False)
-        cnt = m['keep_off'][1:] - m['keep_off'][:-1]
-        return (cnt > 0).reshape(shape)
-
     # ------------------------------------------------------------------ forward
     def forward(self, rays_o, rays_d, viewdirs, global_step=None, **render_kwargs):
         """Volume rendering, lib/voxurf_fine.py:620-802."""
@@ -318,15 +149,7 @@ class Voxurf(nn.Module):
         sdf, gradient, feat = self.grid_sampler(ray_pts, sdf_grid, sample_ret=True, sample_grad=True, displace=1.0)
 
         dist = render_kwargs['stepsize'] * self._voxel_size_host
-        if global_step is not None:   # lib/voxurf_fine.py:466-469
-            s_val = 1. / (global_step + self.s_ratio / self.s_start - self.step_start) * self.s_ratio
-            self.s_val.data = torch.ones_like(self.s_val) * s_val
-            self._s_val_host = float(np.float32(s_val))
-        else:
-            s_val = 0
-            if not hasattr(self, '_s_val_host'):
-                self._s_val_host = float(self.s_val.item())
-        inv_s = float(np.float32(1.0) / np.float32(self._s_val_host))
+        s_val, inv_s = self._update_s_val(global_step)
         alpha = ops.neus_alpha(viewdirs, ray_id, sdf, gradient, float(np.float32(dist)), inv_s)
 
         mask = None
