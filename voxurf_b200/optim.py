@@ -38,6 +38,7 @@ class Adam(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
         self.per_lr = None
         self.zero_grad_in_step = zero_grad_in_step
+        self.timed_param, self.timings = None, []   # bench.py: CUDA events around one parameter's kernel
         super().__init__(params, defaults)
 
     def set_pervoxel_lr(self, count):
@@ -72,9 +73,16 @@ class Adam(torch.optim.Optimizer):
                         g.stride() != p.stride():
                     g = g.contiguous(memory_format=torch.preserve_format) if g.stride() == p.stride() else \
                         torch.empty_like(p).copy_(g)
+                timed = p is self.timed_param
+                if timed:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
                 call('vx_adam_step', _storage(p.data), _storage(g), _storage(state['exp_avg']),
                      _storage(state['exp_avg_sq']), per_lr, p.numel(), beta1, beta2, 1 - beta1, 1 - beta2, step_size,
                      math.sqrt(bias_correction2), group['eps'], 0, int(self.zero_grad_in_step))
+                if timed:
+                    ev[1].record()
+                    self.timings.append(ev)
         return loss
 
 
