@@ -47,6 +47,7 @@ def parse():
     ap.add_argument('--layout', default='channels_last', choices=['channels_last', 'channel_major'])
     ap.add_argument('--cpu-rays', type=int, default=256, help='ray sample of the CPU baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--path', default='fused', choices=['fused', 'dropin'], help='fused = sync-free FusedFineStep; dropin = Voxurf.forward + autograd')
     ap.add_argument('--phases', action='store_true', help='also print a per-phase CUDA-event breakdown to stderr')
     return ap.parse_args()
 
@@ -221,7 +222,7 @@ def main():
     C, G = args.k0_channels, args.grid
     workload = (f'voxurf_fine fwd+bwd+TV+Adam, {G}^3 SDF + {C}-ch k0, rgbnet 79->192^3->3 + k_rgbnet, {args.rays}-ray batch/GPU, '
                 f'synthetic sphere scene, step {START_STEP}+, TV every 3rd iter, smooth_ksize={args.smooth}')
-    config = {'workload': workload, 'grid': G, 'k0_channels': C, 'rays_per_gpu': args.rays, 'k0_layout': args.layout,
+    config = {'workload': workload, 'path': args.path, 'grid': G, 'k0_channels': C, 'rays_per_gpu': args.rays, 'k0_layout': args.layout,
               'l2_policy': 'inputs larger than L2 (grids + moments 0.27 GB x (1+C) >> 126 MB)', 'parallelism': f'dp{world} over rays'}
 
     if args.impl == 'reference':
@@ -247,12 +248,28 @@ def main():
     from voxurf_b200 import parallel
 
     model = build_model(args, device)
-    sync = parallel.GradSync(model, world) if world > 1 else None
-    trainer = Trainer(model, FINE_TRAIN, RENDER_KW, zero_grad_in_step=False, grad_sync=sync)
-    trainer.global_batch = args.rays * world
     pool = ray_pool(8, args.rays, rank)
     dev_pool = [tuple(t.to(device) for t in b) for b in pool]
     pin_pool = [tuple(t.pin_memory() for t in b) for b in pool]
+    sync = parallel.GradSync(model, world) if world > 1 else None
+    fused = None
+    if args.path == 'fused':
+        from voxurf_b200.fused import FusedFineStep
+        fused = FusedFineStep(model, args.rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank)
+        fused.calibrate(*dev_pool[0][:3], global_step=START_STEP, headroom=1.35)
+        if sync is not None:
+            sync = parallel.GradSync(model, world, extra=[fused.mlp1.flat, fused.mlp2.flat], only_large=True)
+
+        class _T:   # same surface as Trainer for the loops below
+            optimizer = fused
+
+            @staticmethod
+            def step(ro, rd, vd, tg, global_step):
+                return fused.step(ro, rd, vd, tg, global_step, grad_sync=sync), None
+        trainer = _T
+    else:
+        trainer = Trainer(model, FINE_TRAIN, RENDER_KW, zero_grad_in_step=False, grad_sync=sync)
+        trainer.global_batch = args.rays * world
 
     def barrier():
         if world > 1:
@@ -277,7 +294,8 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()
-    trainer.optimizer.timed_param = model.k0.grid
+    if fused is None:
+        trainer.optimizer.timed_param = model.k0.grid
     trainer.optimizer.timings = []
     with ClockSampler(local_rank) as clk:
         ev0.record()
@@ -287,7 +305,10 @@ def main():
     launches = _lib.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
     adam_ms = [a.elapsed_time(b) for a, b in trainer.optimizer.timings]
-    trainer.optimizer.timed_param = None
+    if fused is None:
+        trainer.optimizer.timed_param = None
+    else:
+        fused.timings = None
     # ---- end-to-end timing (pinned host -> device inputs, device -> host loss, every step)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -306,15 +327,18 @@ def main():
         value = total_rays / (ms * 1e-3)
         V = G ** 3
         peak, peak_src = measured_peak()
-        adam_bytes = 32 * V * C if not trainer.zero_grad_in_step else 32 * V * C
-        adam_bytes = 28 * V * C   # read p,g,m,v + write p,m,v (the zero-fill of grad is charged to the scatter)
+        adam_bytes = 28 * V * C   # read p,g,m,v + write p,m,v (the fused zero-fill of grad is the "1 grad write")
         adam_t = float(np.mean(adam_ms)) if adam_ms else None
         roof = {'bound': 'hbm', 'kernel': 'k_adam (k0 grid, %d x %d^3 fp32)' % (C, G), 'achieved': (adam_bytes / (adam_t * 1e-3) / 1e9) if adam_t else None,
                 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'traffic': None, 'ms_per_launch': adam_t,
                 'algorithmic_bytes_per_launch': adam_bytes, 'share_of_step': (adam_t / (ms / args.steps)) if adam_t else None}
         roof['frac'] = roof['achieved'] / peak if roof['achieved'] else None
-        M4 = int(ret['weights'].shape[0]); M3 = int(ret['mask'].shape[0]); M0 = int(ret['mask_outbbox'].shape[0])
-        M2 = int((~ret['mask_outbbox']).sum())
+        if fused is not None:
+            M0, M2, M4 = fused.counts()
+            M3 = int(fused.keep[:M2].sum())
+        else:
+            M4 = int(ret['weights'].shape[0]); M3 = int(ret['mask'].shape[0]); M0 = int(ret['mask_outbbox'].shape[0])
+            M2 = int((~ret['mask_outbbox']).sum())
         B = algorithmic_bytes(V, C, 1 / 3, M2, M3, M4, args.rays, 1 / 3)
         step_roof = {'algorithmic_bytes_per_step': B, 'achieved_gbs': B / (ms / args.steps * 1e-3) / 1e9,
                      'frac_of_hbm': B / (ms / args.steps * 1e-3) / 1e9 / peak, 'M0': M0, 'M2': M2, 'M3': M3, 'M4': M4}

@@ -185,6 +185,58 @@ int vx_alpha2weight_seg_backward(const float* alpha, const float* weight, const 
                                  const float* grad_weights, const float* grad_last, float* grad,
                                  cudaStream_t stream);
 
+/* exclusive scan of n int32 (n ~ rays per batch), out[n] = total */
+int vx_scan_i32(const int* in, int n, int* out, cudaStream_t stream);
+int vx_sum_f32(const float* x, int n, float* out, cudaStream_t stream);
+
+/* ---- fused, sync-free fine-stage step (every count is read from device memory) -------------------------
+ * One Voxurf.forward + loss + backward, lib/voxurf_fine.py:620-802 + run.py:604-639, between the march above and
+ * the optimizer: see voxurf_b200/fused.py for the sequence and DESIGN.md for the buffer layout. */
+/* grid_sampler(sample_grad) + neus_alpha_from_sdf_scatter + alpha > thres flag   lib/voxurf_fine.py:640-648 */
+int vx_fused_sdf_alpha(const float* grid, int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
+                       const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
+                       float stepdist, const int* n_dev, const float* viewdirs, float voxel_size, float dist,
+                       float inv_s, float thres, float* sdf, float* grad, float* alpha, uint8_t* keep, float* d_w,
+                       float* d_sdf_s, float* d_grad_s, cudaStream_t stream);
+/* weights > thres compaction as an index list                                   lib/voxurf_fine.py:668-676 */
+int vx_fused_emit_rows(const uint8_t* w_keep, const int* seg_off, const int* off4, int n_rays, int capacity,
+                       int* idx4, int* overflow, cudaStream_t stream);
+/* k0 gather + sample_sdfs + positional encodings -> the two MLP input matrices   lib/voxurf_fine.py:678-739 */
+int vx_fused_row_features(const float* sdf_grid, const float* k0_grid, int X, int Y, int Z, int C, int k0_channels_last,
+                          const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
+                          const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
+                          const int* n_rows_dev, int capacity, const float* viewdirs, const float* sdf_s,
+                          const float* grad_s, float voxel_size, int use_grad_norm, int P, int Vp, int P2, int V2,
+                          const float* displace_host, int L, int ld1, int ld2, float* X1, float* X2,
+                          cudaStream_t stream);
+int vx_fused_fill_logit_cols(const float* logit, int ld_logit, const int* n_rows_dev, int capacity, int col, int ld2,
+                             float* X2, cudaStream_t stream);
+/* sigmoid + segment_coo compositing + losses + their backward                   lib/voxurf_fine.py:749-763, run.py:604-636 */
+int vx_fused_composite_loss(const float* logit1, const float* k_out, int ld_out, const int* idx4, const int* off4,
+                            int capacity, const float* weight_s, const float* alphainv_last, const float* target,
+                            int n_rays, float w_main, float w_rgb0, float w_ent, float ent_scale, float bg, int train,
+                            float* rgb_marched, float* rgb_marched0, float* d_logit1, float* d_kout, float* d_w_s,
+                            float* d_last, float* loss_ray, cudaStream_t stream);
+/* normal_marched / depth                                                        lib/voxurf_fine.py:765-777 */
+int vx_fused_composite_aux(const int* idx4, const int* off4, int capacity, const float* weight_s, const float* grad_s,
+                           const int* step_id, float dist, int n_rays, float* normal_marched, float* depth,
+                           cudaStream_t stream);
+/* backward of the row features into the k0 / sdf gradient grids */
+int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int C, int k0_channels_last,
+                          const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
+                          const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
+                          const int* n_rows_dev, int capacity, float voxel_size, int use_grad_norm, int P, int Vp,
+                          int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
+                          const float* dX2, float* d_sdf_s, float* d_grad_s, float* sdf_grad, float* k0_grad,
+                          cudaStream_t stream);
+/* NeuS-alpha backward + the 7-tap scatter of every M2 sample into the sdf gradient grid */
+int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
+                                const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
+                                float stepdist, const int* n_dev, const float* viewdirs, const float* sdf,
+                                const float* grad, const uint8_t* keep, const float* d_alpha, const float* d_sdf_s,
+                                const float* d_grad_s, float voxel_size, float dist, float inv_s, float* sdf_grad,
+                                cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

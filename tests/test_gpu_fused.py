@@ -1,0 +1,107 @@
+"""GPU: the sync-free fused step (voxurf_b200.fused.FusedFineStep) against the CPU oracle and against the drop-in
+autograd path -- losses, grid / MLP gradients, TV iterations, Adam updates over several steps, and render()."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kernels as K
+from oracle import voxurf_ref as R
+from voxurf_b200 import synthetic as S
+from tests.helpers import T, oracle_fine_model, product_fine_model
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+RK = dict(near=0.3, far=6.0, bg=0.0, stepsize=0.5)
+
+
+def close(a, b, rtol=1e-5, atol=1e-6, msg=''):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=msg)
+
+
+def grad_close(a, b, msg=''):
+    b = b.detach().cpu()
+    close(a, b, 1e-4, 1e-4 * max(float(b.abs().max()), 1e-30), msg)
+
+
+@pytest.mark.parametrize('G,C,cl,n_rays,bg', [(48, 6, True, 1024, 0.0), (40, 12, True, 640, 1.0), (32, 6, False, 512, 0.0)])
+def test_fused_forward_backward_matches_oracle(G, C, cl, n_rays, bg):
+    from voxurf_b200.fused import FusedFineStep
+    from voxurf_b200.trainer import FINE_TRAIN
+    sc = S.make_fine_scene(G, C, 64, seed=G + C)
+    m = product_fine_model(sc, k0_channels_last=cl)
+    om = oracle_fine_model(sc)
+    ro, rd, vd = (T(x) for x in S.make_rays(n_rays, seed=G))
+    target = T(S.make_target(vd.numpy()))
+    rk = dict(RK, bg=bg)
+    fs = FusedFineStep(m, n_rays, FINE_TRAIN, rk, row_capacity=4096)
+    step = 15003   # TV iteration
+    fs.calibrate(ro.to(DEV), rd.to(DEV), vd.to(DEV), global_step=step)
+    loss = fs.forward_backward(ro.to(DEV), rd.to(DEV), vd.to(DEV), target.to(DEV), step)
+    oret = R.fine_forward(om, ro, rd, vd, step, near=0.3, stepsize=0.5, bg=bg)
+    oloss = R.fine_loss(oret, target)
+    M0, M2, M4 = fs.counts()
+    assert M0 == oret['mask_outbbox'].shape[0] and M2 == int((~oret['mask_outbbox']).sum()) and M4 == oret['weights'].shape[0]
+    close(loss, oloss, 1e-5, 1e-7)
+    close(fs.rgb_marched, oret['rgb_marched'], 1e-5, 3e-6); close(fs.rgb_marched0, oret['rgb_marched0'], 1e-5, 3e-6)
+    close(fs.alphainv_last, oret['alphainv_cum'], 1e-5, 1e-6)
+    oloss.backward()
+    grad_close(m.sdf.grid.grad, om['sdf'].grad, 'grad_sdf'); grad_close(m.k0.grid.grad, om['k0'].grad, 'grad_k0')
+    for mlp, ol in ((fs.mlp1, om['rgbnet']), (fs.mlp2, om['k_rgbnet'])):
+        for l, (W, b) in zip(mlp.linears, ol):
+            grad_close(l.weight.grad, W.grad, 'W'); grad_close(l.bias.grad, b.grad, 'b')
+    # regularisers on top (smooth-grad TV through the FD gradient, TV add-grad), then Adam
+    fs.regularise(step)
+    om['sdf'].grad = None
+    (oloss.detach() * 0 + 0.01 * R.smooth_grad_tv(R.sdf_gradient_grid(om['sdf'], om['voxel_size']), om['nonempty_mask'], 0.05)).backward()
+    # (first backward's grads were dropped above; compare the regulariser's own contribution)
+    g_reg = om['sdf'].grad.clone().contiguous()
+    w = 0.01 * 0.1 / n_rays * G / 128
+    base = torch.zeros_like(g_reg)
+    K.total_variation_add_grad(om['sdf'].detach().contiguous(), base, w, w, w, True)
+    g_reg = g_reg + base
+    oret2 = R.fine_forward(om, ro, rd, vd, step, near=0.3, stepsize=0.5, bg=bg)
+    om['sdf'].grad = None
+    R.fine_loss(oret2, target).backward()
+    grad_close(m.sdf.grid.grad, om['sdf'].grad + g_reg, 'grad_sdf + regularisers')
+
+
+def test_fused_steps_match_dropin_autograd_path():
+    """Three iterations (one of them a TV iteration): identical parameters from both execution paths."""
+    from voxurf_b200.fused import FusedFineStep
+    from voxurf_b200.trainer import FINE_TRAIN, Trainer
+    sc = S.make_fine_scene(40, 6, 64, seed=21)
+    ma, mb = product_fine_model(sc, k0_channels_last=True), product_fine_model(sc, k0_channels_last=True)
+    n_rays = 768
+    tr = Trainer(ma, FINE_TRAIN, RK, zero_grad_in_step=False)
+    fs = FusedFineStep(mb, n_rays, FINE_TRAIN, RK, row_capacity=8192)
+    for it, step in enumerate([15001, 15002, 15003]):
+        ro, rd, vd = (T(x).to(DEV) for x in S.make_rays(n_rays, seed=100 + it))
+        target = T(S.make_target(vd.cpu().numpy(), seed=it)).to(DEV)
+        la, _ = tr.step(ro, rd, vd, target, step)
+        lb = fs.step(ro, rd, vd, target, step)
+        close(lb, la, 1e-5, 1e-7, f'loss step {step}')
+        fs.counts()
+        # Adam's first steps are sign-like (|dp| ~ lr): compare with an absolute floor of a fraction of lr
+        close(mb.sdf.grid, ma.sdf.grid, 1e-4, 2e-2 * 5e-3, f'sdf step {step}')
+        close(mb.k0.grid, ma.k0.grid, 1e-4, 2e-2 * 1e-1, f'k0 step {step}')
+        for la_, lb_ in zip([x for x in ma.rgbnet.modules() if isinstance(x, torch.nn.Linear)], fs.mlp1.linears):
+            close(lb_.weight, la_.weight, 1e-3, 5e-2 * 3e-3, 'rgbnet W')
+    assert (mb.sdf.grid.grad == 0).all() and (mb.k0.grid.grad == 0).all()   # zeroed inside the Adam pass
+
+
+def test_fused_render_matches_dropin_forward():
+    from voxurf_b200.fused import FusedFineStep
+    sc = S.make_fine_scene(48, 12, 64, seed=33)
+    m = product_fine_model(sc, k0_channels_last=True)
+    n_rays = 900
+    ro, rd, vd = (T(x).to(DEV) for x in S.make_rays(n_rays, seed=5))
+    rk = dict(RK, bg=1.0)
+    with torch.no_grad():
+        ref = m(ro, rd, vd, render_grad=True, render_depth=True, **rk)
+    fs = FusedFineStep(m, n_rays, None, rk, row_capacity=4096)
+    fs.calibrate(ro, rd, vd)
+    out = fs.render(ro, rd, vd)
+    for k in ['rgb_marched', 'rgb_marched0', 'normal_marched', 'depth', 'alphainv_cum']:
+        close(out[k], ref[k], 1e-5, 3e-6, k)

@@ -1,0 +1,682 @@
+// Fused, sync-free fine-stage step: the kernels between the
+// ray march (sampling.cu) and the optimizer (adam.cu) of one Voxurf.forward + loss + backward
+// (lib/voxurf_fine.py:620-802, run.py:604-639).
+//
+// Layout in HBM (all persistent, capacity sized once; nothing is allocated per step):
+//   M2-level arrays ("samples that survived bbox + mask cache", ray-sorted, ~2 M):
+//     ray_id, step_id (int32), sdf, grad[3], alpha, keep (u8: alpha > thres), weight, T,
+//     d_w, d_alpha, d_sdf_s, d_grad_s[3]
+//   M4-level arrays ("rows": samples with weight > thres, ray-sorted, ~0.06-0.16 M):
+//     idx4 (row -> M2 index), X1 [rows, ld1] rgbnet input, X2 [rows, ld2] k_rgbnet input
+//   per-ray arrays: keep_off (M2 segment offsets), off4 (row segment offsets), alphainv_last, i_end
+// Every count lives on the device (keep_off[N] = M2, off4[N] = M4): no host round trip, the whole step is
+// CUDA-graph capturable.  Threshold compactions of the reference (6-7 boolean-index gathers each,
+// lib/voxurf_fine.py:647-676) become a keep flag (first threshold) and one index list (second threshold).
+#include "common.cuh"
+#include "taps.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// S4: SDF value + 6-neighbour gradient + NeuS alpha for every M2 sample
+//     (grid_sampler(sample_grad=True) lib/voxurf_fine.py:640 + neus_alpha_from_sdf_scatter :643 + mask :648)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sdf_alpha_fwd(VxGrid g, const float* __restrict__ grid, VxPts pts, const int* __restrict__ n_dev,
+                                const float* __restrict__ viewdirs, float voxel_size, float dist, float inv_s,
+                                float thres, float* __restrict__ sdf, float* __restrict__ grad,
+                                float* __restrict__ alpha, uint8_t* __restrict__ keep, float* __restrict__ d_w,
+                                float* __restrict__ d_sdf_s, float* __restrict__ d_grad_s) {
+  const int64_t n = *n_dev;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    float px, py, pz;
+    vx_load_pt(pts, p, px, py, pz);
+    VxTap t;
+    float ix, iy, iz;
+    point_to_index(g, px, py, pz, ix, iy, iz);
+    vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+    const float s = vx_tap_eval(grid, t);
+    SdfTapCoords tc;
+    sdf_tap_setup(g, px, py, pz, tc);
+    float gr[3];  // reference axis order z,y,x
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float cm = sdf_tap_coords(g, tc, a, -1.f, ix, iy, iz);
+      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+      const float fm = vx_tap_eval(grid, t);
+      const float cp = sdf_tap_coords(g, tc, a, 1.f, ix, iy, iz);
+      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+      const float fp = vx_tap_eval(grid, t);
+      gr[a] = __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp, cm)), voxel_size);
+    }
+    const float gx = gr[2], gy = gr[1], gz = gr[0];
+    const int r = pts.ray_id[p];
+    const float true_cos = __fadd_rn(__fadd_rn(__fmul_rn(viewdirs[3 * r], gx), __fmul_rn(viewdirs[3 * r + 1], gy)),
+                                     __fmul_rn(viewdirs[3 * r + 2], gz));
+    const float iter_cos = -fmaxf(-true_cos, 0.f);
+    const float h = __fmul_rn(__fmul_rn(iter_cos, dist), 0.5f);
+    const float prev = sigmoidf_(__fmul_rn(__fsub_rn(s, h), inv_s));
+    const float next = sigmoidf_(__fmul_rn(__fadd_rn(s, h), inv_s));
+    float a_ = __fdiv_rn(__fadd_rn(__fsub_rn(prev, next), 1e-5f), __fadd_rn(prev, 1e-5f));
+    a_ = fminf(fmaxf(a_, 0.f), 1.f);
+    sdf[p] = s;
+    grad[3 * p] = gx; grad[3 * p + 1] = gy; grad[3 * p + 2] = gz;
+    alpha[p] = a_;
+    keep[p] = a_ > thres;
+    d_w[p] = 0.f; d_sdf_s[p] = 0.f;
+    d_grad_s[3 * p] = 0.f; d_grad_s[3 * p + 1] = 0.f; d_grad_s[3 * p + 2] = 0.f;
+  }
+}
+
+VX_API int vx_fused_sdf_alpha(const float* grid, int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
+                              const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
+                              float stepdist, const int* n_dev, const float* viewdirs, float voxel_size, float dist,
+                              float inv_s, float thres, float* sdf, float* grad, float* alpha, uint8_t* keep, float* d_w,
+                              float* d_sdf_s, float* d_grad_s, cudaStream_t st) {
+  VX_REQUIRE(n_dev != nullptr, "vx_fused_sdf_alpha", "n_dev required");
+  const VxGrid g = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
+  const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
+  k_sdf_alpha_fwd<<<vx_num_sms() * 8, 256, 0, st>>>(g, grid, pts, n_dev, viewdirs, voxel_size, dist, inv_s, thres, sdf,
+                                                    grad, alpha, keep, d_w, d_sdf_s, d_grad_s);
+  return vx_check_launch("vx_fused_sdf_alpha");
+}
+
+// ---------------------------------------------------------------------------------------------
+// S6: rows = samples with weight > thres, in ray order (lib/voxurf_fine.py:668-676)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_emit_rows(const uint8_t* __restrict__ w_keep, const int* __restrict__ seg_off, const int* __restrict__ off4,
+                            int n_rays, int capacity, int* __restrict__ idx4, int* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * warps_per_block) {
+    const int i_s = seg_off[r], i_e = seg_off[r + 1];
+    int out = off4[r];
+    for (int base = i_s; base < i_e; base += 32) {
+      const int i = base + lane;
+      const bool f = (i < i_e) && w_keep[i];
+      const uint32_t m = __ballot_sync(0xffffffffu, f);
+      if (f) {
+        const int dst = out + __popc(m & ((1u << lane) - 1u));
+        if (dst < capacity) idx4[dst] = i;
+      }
+      out += __popc(m);
+    }
+    if (r == n_rays - 1 && lane == 0 && out > capacity) *overflow = out;
+  }
+}
+
+VX_API int vx_fused_emit_rows(const uint8_t* w_keep, const int* seg_off, const int* off4, int n_rays, int capacity,
+                              int* idx4, int* overflow, cudaStream_t st) {
+  if (n_rays <= 0) return 0;
+  const int blocks = min(vx_blocks((int64_t)n_rays * 32, 256), vx_num_sms() * 8);
+  k_emit_rows<<<blocks, 256, 0, st>>>(w_keep, seg_off, off4, n_rays, capacity, idx4, overflow);
+  return vx_check_launch("vx_fused_emit_rows");
+}
+
+// ---------------------------------------------------------------------------------------------
+// S7: MLP input rows (lib/voxurf_fine.py:678-739).  Column layout (P = posbase_pe, Vp = viewbase_pe, L):
+//   X1: [xyz 3 | sin 3P | cos 3P | view 3 | sin 3Vp | cos 3Vp | sdf 1 | all_feat 6L | all_grad 3L]      = D1
+//   X2: [k0 C | xyz 3 | sin 3P2 | cos 3P2 | view 3 | sin 3V2 | cos 3V2 | gradient 3 | rgb_logit 3 (later)] = D2
+// Rows >= M4 (up to `capacity`) are zero-filled so a fixed-shape GEMM over the capacity is harmless.
+// ---------------------------------------------------------------------------------------------
+struct VxRowLayout {
+  int P, Vp, P2, V2, L, C;
+  int ld1, ld2;   // row strides (>= D1, D2)
+  float disp[VX_MAX_L];
+};
+
+template <int kC>
+__global__ void k_row_features(VxGrid gs, const float* __restrict__ sdf_grid, VxGrid gk, const float* __restrict__ k0_grid,
+                               VxPts pts, const int* __restrict__ idx4, const int* __restrict__ n_rows_dev, int capacity,
+                               const float* __restrict__ viewdirs, const float* __restrict__ sdf_s,
+                               const float* __restrict__ grad_s, float voxel_size, int use_grad_norm, VxRowLayout lay,
+                               float* __restrict__ X1, float* __restrict__ X2) {
+  const int n = min(*n_rows_dev, capacity);
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < capacity; row += gridDim.x * blockDim.x) {
+    float* x1 = X1 + (int64_t)row * lay.ld1;
+    float* x2 = X2 + (int64_t)row * lay.ld2;
+    if (row >= n) {
+      for (int c = 0; c < lay.ld1; ++c) x1[c] = 0.f;
+      for (int c = 0; c < lay.ld2; ++c) x2[c] = 0.f;
+      continue;
+    }
+    const int i = idx4[row];
+    float p[3];
+    vx_load_pt(pts, i, p[0], p[1], p[2]);
+    const int r = pts.ray_id[i];
+    // ---- positional encodings (lib/voxurf_fine.py:694-698, 723-726)
+    float xn[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xn[d] = __fdiv_rn(__fsub_rn(p[d], gs.min[d]), __fsub_rn(gs.max[d], gs.min[d]));
+    int c1 = 0, c2 = kC;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { x1[c1 + d] = xn[d]; x2[c2 + d] = xn[d]; }
+    c1 += 3; c2 += 3;
+    for (int d = 0; d < 3; ++d)
+      for (int f = 0; f < lay.P; ++f) {
+        const float e = __fmul_rn(xn[d], (float)(1 << f));
+        x1[c1 + d * lay.P + f] = sinf(e);
+        x1[c1 + 3 * lay.P + d * lay.P + f] = cosf(e);
+      }
+    c1 += 6 * lay.P;
+    for (int d = 0; d < 3; ++d)
+      for (int f = 0; f < lay.P2; ++f) {
+        const float e = __fmul_rn(xn[d], (float)(1 << f));
+        x2[c2 + d * lay.P2 + f] = sinf(e);
+        x2[c2 + 3 * lay.P2 + d * lay.P2 + f] = cosf(e);
+      }
+    c2 += 6 * lay.P2;
+    float vd[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { vd[d] = viewdirs[3 * r + d]; x1[c1 + d] = vd[d]; x2[c2 + d] = vd[d]; }
+    c1 += 3; c2 += 3;
+    for (int d = 0; d < 3; ++d)
+      for (int f = 0; f < lay.Vp; ++f) {
+        const float e = __fmul_rn(vd[d], (float)(1 << f));
+        x1[c1 + d * lay.Vp + f] = sinf(e);
+        x1[c1 + 3 * lay.Vp + d * lay.Vp + f] = cosf(e);
+      }
+    c1 += 6 * lay.Vp;
+    for (int d = 0; d < 3; ++d)
+      for (int f = 0; f < lay.V2; ++f) {
+        const float e = __fmul_rn(vd[d], (float)(1 << f));
+        x2[c2 + d * lay.V2 + f] = sinf(e);
+        x2[c2 + 3 * lay.V2 + d * lay.V2 + f] = cosf(e);
+      }
+    c2 += 6 * lay.V2;
+    // ---- centre sdf, gradient (values of the M2-level pass)
+    x1[c1] = sdf_s[i];
+    c1 += 1;
+    x2[c2] = grad_s[3 * i]; x2[c2 + 1] = grad_s[3 * i + 1]; x2[c2 + 2] = grad_s[3 * i + 2];
+    c2 += 3;
+    x2[c2] = 0.f; x2[c2 + 1] = 0.f; x2[c2 + 2] = 0.f;   // rgb_logit.detach(), filled after the first MLP
+    for (int c = c2 + 3; c < lay.ld2; ++c) x2[c] = 0.f;
+    // ---- sample_sdfs (displacement list, normalised gradients) lib/voxurf_fine.py:688
+    const int L = lay.L;
+    SdfTapCoords tc;
+    sdf_tap_setup(gs, p[0], p[1], p[2], tc);
+    VxTap t;
+    for (int l = 0; l < L; ++l) {
+      float gr[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float ix, iy, iz;
+        const float cm = sdf_tap_coords(gs, tc, a, -lay.disp[l], ix, iy, iz);
+        vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
+        const float fm = vx_tap_eval(sdf_grid, t);
+        const float cp = sdf_tap_coords(gs, tc, a, lay.disp[l], ix, iy, iz);
+        vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
+        const float fp = vx_tap_eval(sdf_grid, t);
+        gr[a] = __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp, cm)), voxel_size);
+        x1[c1 + (a * 2 + 0) * L + l] = fm;
+        x1[c1 + (a * 2 + 1) * L + l] = fp;
+      }
+      if (use_grad_norm) {
+        const float nrm = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]) + 1e-5f;
+        gr[0] = gr[0] / nrm; gr[1] = gr[1] / nrm; gr[2] = gr[2] / nrm;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) x1[c1 + 6 * L + a * L + l] = gr[a];
+    }
+    for (int c = c1 + 9 * L; c < lay.ld1; ++c) x1[c] = 0.f;
+    // ---- k0 trilinear gather (DenseGrid.forward lib/grid.py:47-58) into X2[:, 0:C]
+    {
+      float ix, iy, iz;
+      point_to_index(gk, p[0], p[1], p[2], ix, iy, iz);
+      vx_make_tap(ix, iy, iz, gk.X, gk.Y, gk.Z, t);
+      const int64_t V = (int64_t)gk.X * gk.Y * gk.Z;
+      float acc[kC];
+#pragma unroll
+      for (int c = 0; c < kC; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (t.off[k] < 0) continue;
+        if (gk.cl) {
+          const float* src = k0_grid + (int64_t)t.off[k] * kC;
+          if (kC % 4 == 0) {
+#pragma unroll
+            for (int c = 0; c < kC; c += 4) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+              acc[c] += v.x * t.w[k]; acc[c + 1] += v.y * t.w[k]; acc[c + 2] += v.z * t.w[k]; acc[c + 3] += v.w * t.w[k];
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < kC; c += 2) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(src + c));
+              acc[c] += v.x * t.w[k]; acc[c + 1] += v.y * t.w[k];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kC; ++c) acc[c] += __ldg(k0_grid + c * V + t.off[k]) * t.w[k];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kC; ++c) x2[c] = acc[c];
+    }
+  }
+}
+
+static int fill_layout(VxRowLayout& lay, int P, int Vp, int P2, int V2, int L, int C, int ld1, int ld2, const float* disp_host) {
+  if (L < 0 || L > VX_MAX_L) return -1;
+  lay.P = P; lay.Vp = Vp; lay.P2 = P2; lay.V2 = V2; lay.L = L; lay.C = C; lay.ld1 = ld1; lay.ld2 = ld2;
+  for (int i = 0; i < VX_MAX_L; ++i) lay.disp[i] = i < L ? disp_host[i] : 0.f;
+  const int D1 = 3 + 6 * P + 3 + 6 * Vp + 1 + 9 * L, D2 = C + 3 + 6 * P2 + 3 + 6 * V2 + 3 + 3;
+  return (ld1 >= D1 && ld2 >= D2) ? 0 : -2;
+}
+
+VX_API int vx_fused_row_features(const float* sdf_grid, const float* k0_grid, int X, int Y, int Z, int C, int k0_channels_last,
+                                 const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
+                                 const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
+                                 const int* n_rows_dev, int capacity, const float* viewdirs, const float* sdf_s,
+                                 const float* grad_s, float voxel_size, int use_grad_norm, int P, int Vp, int P2, int V2,
+                                 const float* displace_host, int L, int ld1, int ld2, float* X1, float* X2,
+                                 cudaStream_t st) {
+  if (capacity <= 0) return 0;
+  VxRowLayout lay;
+  VX_REQUIRE(fill_layout(lay, P, Vp, P2, V2, L, C, ld1, ld2, displace_host) == 0, "vx_fused_row_features", "bad layout");
+  VX_REQUIRE(C == 6 || C == 12, "vx_fused_row_features", "k0 channels must be 6 or 12");
+  const VxGrid gs = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
+  const VxGrid gk = make_grid(X, Y, Z, C, k0_channels_last, xyz_min_host, xyz_max_host);
+  const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
+  const int blocks = min(vx_blocks(capacity, 128), vx_num_sms() * 16);
+  if (C == 6)
+    k_row_features<6><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, k0_grid, pts, idx4, n_rows_dev, capacity, viewdirs, sdf_s,
+                                              grad_s, voxel_size, use_grad_norm, lay, X1, X2);
+  else
+    k_row_features<12><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, k0_grid, pts, idx4, n_rows_dev, capacity, viewdirs, sdf_s,
+                                               grad_s, voxel_size, use_grad_norm, lay, X1, X2);
+  return vx_check_launch("vx_fused_row_features");
+}
+
+// rgb_logit.detach() into X2's last 3 feature columns (k_res, lib/voxurf_fine.py:741-744)
+__global__ void k_fill_logit_cols(const float* __restrict__ logit, int ld_logit, const int* __restrict__ n_rows_dev,
+                                  int capacity, int col, int ld2, float* __restrict__ X2) {
+  const int n = min(*n_rows_dev, capacity);
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    X2[(int64_t)row * ld2 + col] = logit[(int64_t)row * ld_logit];
+    X2[(int64_t)row * ld2 + col + 1] = logit[(int64_t)row * ld_logit + 1];
+    X2[(int64_t)row * ld2 + col + 2] = logit[(int64_t)row * ld_logit + 2];
+  }
+}
+
+VX_API int vx_fused_fill_logit_cols(const float* logit, int ld_logit, const int* n_rows_dev, int capacity, int col, int ld2,
+                                    float* X2, cudaStream_t st) {
+  if (capacity <= 0) return 0;
+  k_fill_logit_cols<<<min(vx_blocks(capacity, 256), vx_num_sms() * 8), 256, 0, st>>>(logit, ld_logit, n_rows_dev, capacity, col, ld2, X2);
+  return vx_check_launch("vx_fused_fill_logit_cols");
+}
+
+// ---------------------------------------------------------------------------------------------
+// S9: compositing + losses + their backward, one warp per ray (lib/voxurf_fine.py:749-763, run.py:604-636).
+//   rgb = sigmoid(logit1); k_rgb = sigmoid(logit1.detach() + k_out)
+//   rgb_marched0 = sum_i w_i rgb_i + alphainv_last * bg ; rgb_marched = clamp(sum_i w_i k_rgb_i + alphainv_last * bg, 0, 1)
+//   loss = w_main * mse(rgb_marched, target) + w_rgb0 * mse(rgb_marched0, target) + w_ent * entropy(alphainv_last[N-1])
+// train != 0: writes d_logit1, d_kout (rows), d_w (scattered to the M2 index of each row), d_last (rays), per-ray loss.
+// Segmented sums are done by fixed-pattern warp reductions: deterministic, no atomics (torch_scatter uses atomics
+// at segment boundaries).
+// ---------------------------------------------------------------------------------------------
+struct VxLossCfg {
+  float w_main, w_rgb0, w_ent, ent_scale;  // ent_scale: 1 on a single GPU; see parallel.py for ray-sharded runs
+  float inv_3n;                            // 1 / (3 * N_local): F.mse_loss mean
+  float bg;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void k_composite_loss(const float* __restrict__ logit1, const float* __restrict__ k_out, int ld_out,
+                                 const int* __restrict__ idx4, const int* __restrict__ off4, int capacity,
+                                 const float* __restrict__ weight_s, const float* __restrict__ alphainv_last,
+                                 const float* __restrict__ target, int n_rays, VxLossCfg cfg, int train,
+                                 float* __restrict__ rgb_marched, float* __restrict__ rgb_marched0,
+                                 float* __restrict__ d_logit1, float* __restrict__ d_kout, float* __restrict__ d_w_s,
+                                 float* __restrict__ d_last, float* __restrict__ loss_ray) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * warps_per_block) {
+    const int b = min(off4[r], capacity), e = min(off4[r + 1], capacity);
+    float s0[3] = {0.f, 0.f, 0.f}, sk[3] = {0.f, 0.f, 0.f};
+    for (int row = b + lane; row < e; row += 32) {
+      const float w = weight_s[idx4[row]];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float l1 = logit1[(int64_t)row * ld_out + c];
+        s0[c] += w * sigmoidf_(l1);
+        sk[c] += w * sigmoidf_(l1 + k_out[(int64_t)row * ld_out + c]);
+      }
+    }
+    const float al = alphainv_last[r];
+    float g0[3], gk[3], lsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float m0 = warp_sum(s0[c]) + al * cfg.bg;
+      const float mk_raw = warp_sum(sk[c]) + al * cfg.bg;
+      const float mk = fminf(fmaxf(mk_raw, 0.f), 1.f);
+      const float tg = target ? target[3 * r + c] : 0.f;
+      if (lane == 0) { rgb_marched0[3 * r + c] = m0; rgb_marched[3 * r + c] = mk; }
+      const float e0 = m0 - tg, ek = mk - tg;
+      g0[c] = cfg.w_rgb0 * 2.f * e0 * cfg.inv_3n;
+      gk[c] = (mk_raw >= 0.f && mk_raw <= 1.f) ? cfg.w_main * 2.f * ek * cfg.inv_3n : 0.f;
+      lsum += cfg.w_rgb0 * e0 * e0 * cfg.inv_3n + cfg.w_main * ek * ek * cfg.inv_3n;
+    }
+    if (!train) continue;
+    float dl = (g0[0] + g0[1] + g0[2] + gk[0] + gk[1] + gk[2]) * cfg.bg;
+    if (r == n_rays - 1 && cfg.w_ent > 0.f && cfg.ent_scale != 0.f) {  // run.py:607-610: the last ray only
+      const float pc = fminf(fmaxf(al, 1e-6f), 1.f - 1e-6f);
+      lsum += cfg.ent_scale * cfg.w_ent * (-(pc * logf(pc) + (1.f - pc) * logf(1.f - pc)));
+      if (al >= 1e-6f && al <= 1.f - 1e-6f) dl += cfg.ent_scale * cfg.w_ent * (logf(1.f - pc) - logf(pc));
+    }
+    if (lane == 0) { d_last[r] = dl; loss_ray[r] = lsum; }
+    for (int row = b + lane; row < e; row += 32) {
+      const int i = idx4[row];
+      const float w = weight_s[i];
+      float dw = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float l1 = logit1[(int64_t)row * ld_out + c];
+        const float rgb = sigmoidf_(l1);
+        const float krgb = sigmoidf_(l1 + k_out[(int64_t)row * ld_out + c]);
+        dw += g0[c] * rgb + gk[c] * krgb;
+        d_logit1[(int64_t)row * ld_out + c] = w * g0[c] * rgb * (1.f - rgb);
+        d_kout[(int64_t)row * ld_out + c] = w * gk[c] * krgb * (1.f - krgb);
+      }
+      d_w_s[i] = dw;
+    }
+  }
+}
+
+__global__ void k_zero_tail_rows(float* __restrict__ a, float* __restrict__ b, int ld, const int* __restrict__ n_rows_dev,
+                                 int capacity) {
+  const int n = min(*n_rows_dev, capacity);
+  for (int64_t t = (int64_t)n * ld + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)capacity * ld;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    a[t] = 0.f;
+    b[t] = 0.f;
+  }
+}
+
+VX_API int vx_fused_composite_loss(const float* logit1, const float* k_out, int ld_out, const int* idx4, const int* off4,
+                                   int capacity, const float* weight_s, const float* alphainv_last, const float* target,
+                                   int n_rays, float w_main, float w_rgb0, float w_ent, float ent_scale, float bg, int train,
+                                   float* rgb_marched, float* rgb_marched0, float* d_logit1, float* d_kout, float* d_w_s,
+                                   float* d_last, float* loss_ray, cudaStream_t st) {
+  if (n_rays <= 0) return 0;
+  VxLossCfg cfg{w_main, w_rgb0, w_ent, ent_scale, 1.f / (3.f * (float)n_rays), bg};
+  if (train) {  // rows beyond M4 must carry zero output gradients (fixed-shape GEMM backward over the capacity)
+    k_zero_tail_rows<<<vx_num_sms() * 2, 256, 0, st>>>(d_logit1, d_kout, ld_out, off4 + n_rays, capacity);
+    int rc = vx_check_launch("vx_fused_composite_loss(tail)");
+    if (rc) return rc;
+  }
+  const int blocks = min(vx_blocks((int64_t)n_rays * 32, 256), vx_num_sms() * 8);
+  k_composite_loss<<<blocks, 256, 0, st>>>(logit1, k_out, ld_out, idx4, off4, capacity, weight_s, alphainv_last, target,
+                                           n_rays, cfg, train, rgb_marched, rgb_marched0, d_logit1, d_kout, d_w_s, d_last,
+                                           loss_ray);
+  return vx_check_launch("vx_fused_composite_loss");
+}
+
+// render-only extras (lib/voxurf_fine.py:765-777): normal_marched (+1e-6 normalisation) and depth
+__global__ void k_composite_aux(const int* __restrict__ idx4, const int* __restrict__ off4, int capacity,
+                                const float* __restrict__ weight_s, const float* __restrict__ grad_s,
+                                const int* __restrict__ step_id, float dist, int n_rays, float* __restrict__ normal_marched,
+                                float* __restrict__ depth) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * warps_per_block) {
+    const int b = min(off4[r], capacity), e = min(off4[r + 1], capacity);
+    float nx = 0.f, ny = 0.f, nz = 0.f, dp = 0.f;
+    for (int row = b + lane; row < e; row += 32) {
+      const int i = idx4[row];
+      const float w = weight_s[i];
+      const float gx = grad_s[3 * i], gy = grad_s[3 * i + 1], gz = grad_s[3 * i + 2];
+      const float nrm = sqrtf(gx * gx + gy * gy + gz * gz) + 1e-6f;
+      nx += w * (gx / nrm); ny += w * (gy / nrm); nz += w * (gz / nrm);
+      dp += __fmul_rn(__fmul_rn(w, (float)step_id[i]), dist);
+    }
+    nx = warp_sum(nx); ny = warp_sum(ny); nz = warp_sum(nz); dp = warp_sum(dp);
+    if (lane == 0) {
+      if (normal_marched) { normal_marched[3 * r] = nx; normal_marched[3 * r + 1] = ny; normal_marched[3 * r + 2] = nz; }
+      if (depth) depth[r] = dp;
+    }
+  }
+}
+
+VX_API int vx_fused_composite_aux(const int* idx4, const int* off4, int capacity, const float* weight_s, const float* grad_s,
+                                  const int* step_id, float dist, int n_rays, float* normal_marched, float* depth,
+                                  cudaStream_t st) {
+  if (n_rays <= 0) return 0;
+  const int blocks = min(vx_blocks((int64_t)n_rays * 32, 256), vx_num_sms() * 8);
+  k_composite_aux<<<blocks, 256, 0, st>>>(idx4, off4, capacity, weight_s, grad_s, step_id, dist, n_rays, normal_marched, depth);
+  return vx_check_launch("vx_fused_composite_aux");
+}
+
+// ---------------------------------------------------------------------------------------------
+// S11: backward of the row features: dX1 -> sdf-grid scatter (all_feat, all_grad) + d_sdf_s (centre sdf);
+//      dX2 -> k0-grid scatter + d_grad_s (gradient feature of k_rgbnet).  One thread per row.
+// ---------------------------------------------------------------------------------------------
+template <int kC>
+__global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, VxGrid gk, VxPts pts,
+                               const int* __restrict__ idx4, const int* __restrict__ n_rows_dev, int capacity,
+                               float voxel_size, int use_grad_norm, VxRowLayout lay, const float* __restrict__ dX1,
+                               const float* __restrict__ dX2, float* __restrict__ d_sdf_s, float* __restrict__ d_grad_s,
+                               float* __restrict__ sdf_grad, float* __restrict__ k0_grad) {
+  const int n = min(*n_rows_dev, capacity);
+  const int L = lay.L;
+  const int col_sdf = 3 + 6 * lay.P + 3 + 6 * lay.Vp;
+  const int col_grad2 = kC + 3 + 6 * lay.P2 + 3 + 6 * lay.V2;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    const float* g1 = dX1 + (int64_t)row * lay.ld1;
+    const float* g2 = dX2 + (int64_t)row * lay.ld2;
+    const int i = idx4[row];
+    float p[3];
+    vx_load_pt(pts, i, p[0], p[1], p[2]);
+    d_sdf_s[i] = g1[col_sdf];
+    d_grad_s[3 * i] = g2[col_grad2]; d_grad_s[3 * i + 1] = g2[col_grad2 + 1]; d_grad_s[3 * i + 2] = g2[col_grad2 + 2];
+    // ---- k0 scatter
+    {
+      float go[kC];
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < kC; ++c) { go[c] = g2[c]; any |= go[c] != 0.f; }
+      if (any) {
+        float ix, iy, iz;
+        point_to_index(gk, p[0], p[1], p[2], ix, iy, iz);
+        VxTap t;
+        vx_make_tap(ix, iy, iz, gk.X, gk.Y, gk.Z, t);
+        const int64_t V = (int64_t)gk.X * gk.Y * gk.Z;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (t.off[k] < 0) continue;
+          if (gk.cl) {
+            float* dst = k0_grad + (int64_t)t.off[k] * kC;
+            if (kC % 4 == 0) {
+#pragma unroll
+              for (int c = 0; c < kC; c += 4)
+                atomicAdd(reinterpret_cast<float4*>(dst + c),
+                          make_float4(go[c] * t.w[k], go[c + 1] * t.w[k], go[c + 2] * t.w[k], go[c + 3] * t.w[k]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < kC; c += 2)
+                atomicAdd(reinterpret_cast<float2*>(dst + c), make_float2(go[c] * t.w[k], go[c + 1] * t.w[k]));
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) atomicAdd(k0_grad + c * V + t.off[k], go[c] * t.w[k]);
+          }
+        }
+      }
+    }
+    // ---- sample_sdfs backward
+    const float* dfeat = g1 + col_sdf + 1;
+    const float* dgrad = dfeat + 6 * L;
+    SdfTapCoords tc;
+    sdf_tap_setup(gs, p[0], p[1], p[2], tc);
+    VxTap t, tm;
+    for (int l = 0; l < L; ++l) {
+      float dgr[3] = {dgrad[0 * L + l], dgrad[1 * L + l], dgrad[2 * L + l]};
+      if (use_grad_norm && (dgr[0] != 0.f || dgr[1] != 0.f || dgr[2] != 0.f)) {
+        float gr[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          float ix, iy, iz;
+          const float cm = sdf_tap_coords(gs, tc, a, -lay.disp[l], ix, iy, iz);
+          vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
+          const float fm = vx_tap_eval(sdf_grid, t);
+          const float cp = sdf_tap_coords(gs, tc, a, lay.disp[l], ix, iy, iz);
+          vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
+          const float fp = vx_tap_eval(sdf_grid, t);
+          gr[a] = __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp, cm)), voxel_size);
+        }
+        const float nrm = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
+        const float den = nrm + 1e-5f;
+        const float dot = dgr[0] * gr[0] + dgr[1] * gr[1] + dgr[2] * gr[2];
+        const float k = (nrm > 0.f) ? dot / (den * den * nrm) : 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) dgr[a] = dgr[a] / den - gr[a] * k;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float dfm = dfeat[(a * 2 + 0) * L + l];
+        float dfp = dfeat[(a * 2 + 1) * L + l];
+        float ix, iy, iz;
+        const float cm = sdf_tap_coords(gs, tc, a, -lay.disp[l], ix, iy, iz);
+        vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, tm);
+        const float cp = sdf_tap_coords(gs, tc, a, lay.disp[l], ix, iy, iz);
+        vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
+        if (dgr[a] != 0.f) {
+          const float d = (dgr[a] / voxel_size) / (cp - cm);
+          dfp += d;
+          dfm -= d;
+        }
+        vx_tap_scatter(sdf_grad, tm, dfm);
+        vx_tap_scatter(sdf_grad, t, dfp);
+      }
+    }
+  }
+}
+
+VX_API int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int C, int k0_channels_last,
+                                 const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
+                                 const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
+                                 const int* n_rows_dev, int capacity, float voxel_size, int use_grad_norm, int P, int Vp,
+                                 int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
+                                 const float* dX2, float* d_sdf_s, float* d_grad_s, float* sdf_grad, float* k0_grad,
+                                 cudaStream_t st) {
+  if (capacity <= 0) return 0;
+  VxRowLayout lay;
+  VX_REQUIRE(fill_layout(lay, P, Vp, P2, V2, L, C, ld1, ld2, displace_host) == 0, "vx_fused_row_backward", "bad layout");
+  VX_REQUIRE(C == 6 || C == 12, "vx_fused_row_backward", "k0 channels must be 6 or 12");
+  const VxGrid gs = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
+  const VxGrid gk = make_grid(X, Y, Z, C, k0_channels_last, xyz_min_host, xyz_max_host);
+  const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
+  const int blocks = min(vx_blocks(capacity, 128), vx_num_sms() * 16);
+  if (C == 6)
+    k_row_backward<6><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, pts, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm, lay,
+                                              dX1, dX2, d_sdf_s, d_grad_s, sdf_grad, k0_grad);
+  else
+    k_row_backward<12><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, pts, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm, lay,
+                                               dX1, dX2, d_sdf_s, d_grad_s, sdf_grad, k0_grad);
+  return vx_check_launch("vx_fused_row_backward");
+}
+
+// ---------------------------------------------------------------------------------------------
+// S13: NeuS-alpha backward + the M2-level scatter into the sdf grid (7 taps per sample).
+// d_alpha comes from vx_alpha2weight_seg_backward (zero for dropped samples and behind the early exit);
+// d_sdf_s / d_grad_s carry the MLP-feature gradients of the rows.  Samples whose gradients are all exactly zero
+// (the vast majority late in training) are skipped before any tap is recomputed.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_alpha_sdf_bwd(VxGrid g, VxPts pts, const int* __restrict__ n_dev, const float* __restrict__ viewdirs,
+                                const float* __restrict__ sdf, const float* __restrict__ grad,
+                                const uint8_t* __restrict__ keep, const float* __restrict__ d_alpha,
+                                const float* __restrict__ d_sdf_s, const float* __restrict__ d_grad_s, float voxel_size,
+                                float dist, float inv_s, float* __restrict__ sdf_grad) {
+  const int64_t n = *n_dev;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    if (!keep[p]) continue;
+    const float ga = d_alpha[p];
+    float ds = d_sdf_s[p];
+    float dg[3] = {d_grad_s[3 * p], d_grad_s[3 * p + 1], d_grad_s[3 * p + 2]};  // x,y,z
+    if (ga != 0.f) {
+      const int r = pts.ray_id[p];
+      const float vx = viewdirs[3 * r], vy = viewdirs[3 * r + 1], vz = viewdirs[3 * r + 2];
+      const float gx = grad[3 * p], gy = grad[3 * p + 1], gz = grad[3 * p + 2];
+      const float s = sdf[p];
+      const float true_cos = __fadd_rn(__fadd_rn(__fmul_rn(vx, gx), __fmul_rn(vy, gy)), __fmul_rn(vz, gz));
+      const float iter_cos = -fmaxf(-true_cos, 0.f);
+      const float h = __fmul_rn(__fmul_rn(iter_cos, dist), 0.5f);
+      const float prev = sigmoidf_(__fmul_rn(__fsub_rn(s, h), inv_s));
+      const float next = sigmoidf_(__fmul_rn(__fadd_rn(s, h), inv_s));
+      const float u = __fadd_rn(__fsub_rn(prev, next), 1e-5f);
+      const float c = __fadd_rn(prev, 1e-5f);
+      const float a = __fdiv_rn(u, c);
+      if (a >= 0.f && a <= 1.f) {
+        const float du = ga / c;
+        const float dc = -ga * u / (c * c);
+        const float dep = (du + dc) * prev * (1.f - prev) * inv_s;
+        const float den = (-du) * next * (1.f - next) * inv_s;
+        ds += dep + den;
+        const float dcos = (true_cos < 0.f) ? (den - dep) * dist * 0.5f : 0.f;
+        dg[0] += dcos * vx; dg[1] += dcos * vy; dg[2] += dcos * vz;
+      }
+    }
+    if (ds == 0.f && dg[0] == 0.f && dg[1] == 0.f && dg[2] == 0.f) continue;
+    float px, py, pz;
+    vx_load_pt(pts, p, px, py, pz);
+    VxTap t;
+    float ix, iy, iz;
+    if (ds != 0.f) {
+      point_to_index(g, px, py, pz, ix, iy, iz);
+      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+      vx_tap_scatter(sdf_grad, t, ds);
+    }
+    SdfTapCoords tc;
+    sdf_tap_setup(g, px, py, pz, tc);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float dga = dg[2 - a];  // reference axis a = z,y,x  <->  xyz component 2 - a
+      if (dga == 0.f) continue;
+      const float cm = sdf_tap_coords(g, tc, a, -1.f, ix, iy, iz);
+      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+      VxTap tp;
+      const float cp = sdf_tap_coords(g, tc, a, 1.f, ix, iy, iz);
+      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, tp);
+      const float d = (dga / voxel_size) / (cp - cm);
+      vx_tap_scatter(sdf_grad, t, -d);
+      vx_tap_scatter(sdf_grad, tp, d);
+    }
+  }
+}
+
+VX_API int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
+                                       const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
+                                       float stepdist, const int* n_dev, const float* viewdirs, const float* sdf,
+                                       const float* grad, const uint8_t* keep, const float* d_alpha, const float* d_sdf_s,
+                                       const float* d_grad_s, float voxel_size, float dist, float inv_s, float* sdf_grad,
+                                       cudaStream_t st) {
+  VX_REQUIRE(n_dev != nullptr, "vx_fused_alpha_sdf_backward", "n_dev required");
+  const VxGrid g = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
+  const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
+  k_alpha_sdf_bwd<<<vx_num_sms() * 8, 256, 0, st>>>(g, pts, n_dev, viewdirs, sdf, grad, keep, d_alpha, d_sdf_s, d_grad_s,
+                                                    voxel_size, dist, inv_s, sdf_grad);
+  return vx_check_launch("vx_fused_alpha_sdf_backward");
+}
+
+// small helpers for the host orchestration ----------------------------------------------------
+__global__ void k_sum_f32(const float* __restrict__ x, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = t;
+  }
+}
+
+VX_API int vx_sum_f32(const float* x, int n, float* out, cudaStream_t st) {
+  k_sum_f32<<<1, 1024, 0, st>>>(x, n, out);
+  return vx_check_launch("vx_sum_f32");
+}

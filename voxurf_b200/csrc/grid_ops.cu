@@ -10,17 +10,11 @@
 // registers, exact zeros are dropped (samples behind the early-termination point have exactly zero
 // gradient), and what is left goes out as fp32 atomics into a persistent, already-zero grad grid.
 #include "common.cuh"
+#include "taps.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // generic C-channel gather:  out[p, c] = trilinear(grid[c], xyz[p])
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void point_to_index(const VxGrid& g, float px, float py, float pz, float& ix, float& iy,
-                                               float& iz) {
-  iz = vx_unnorm_coord(vx_norm_coord(px, g.min[0], g.max[0]), g.X);  // world x -> slowest dim (ATen z / D)
-  iy = vx_unnorm_coord(vx_norm_coord(py, g.min[1], g.max[1]), g.Y);
-  ix = vx_unnorm_coord(vx_norm_coord(pz, g.min[2], g.max[2]), g.Z);  // world z -> fastest dim (ATen x / W)
-}
-
 template <int kC>
 __global__ void k_grid_gather(VxGrid g, const float* __restrict__ grid, VxPts pts, const int* __restrict__ n_dev,
                               int64_t n_host, float* __restrict__ out) {
@@ -128,17 +122,6 @@ __global__ void k_grid_gather_bwd(VxGrid g, VxPts pts, const int* __restrict__ n
   }
 }
 
-static VxGrid make_grid(int X, int Y, int Z, int C, int cl, const float* mn, const float* mx) {
-  VxGrid g;
-  g.X = X; g.Y = Y; g.Z = Z; g.C = C; g.cl = cl;
-  for (int i = 0; i < 3; ++i) { g.min[i] = mn[i]; g.max[i] = mx[i]; }
-  return g;
-}
-
-static int launch_blocks(const int* n_dev, int64_t n_host) {
-  return n_dev ? vx_num_sms() * 8 : (int)min((int64_t)vx_blocks(n_host, 256), (int64_t)vx_num_sms() * 16);
-}
-
 #define VX_DISPATCH_C(C, cl, CALL)                  \
   if ((cl) && (C) == 12) { CALL(12); }              \
   else if ((cl) && (C) == 6) { CALL(6); }           \
@@ -186,50 +169,6 @@ VX_API int vx_grid_gather_backward(int X, int Y, int Z, int C, int channels_last
 // Output order: `xyz_order=0` reference sample_sdfs layout, feat[(a*2+s)*L + l], grad[a*L + l], a = z,y,x;
 // `xyz_order=1` (only L == 1) Voxurf.grid_sampler layout, feat = x-,x+,y-,y+,z-,z+, grad = gx,gy,gz (:525-526).
 // ---------------------------------------------------------------------------------------------
-#define VX_MAX_L 8
-
-struct VxDisp {
-  int L;
-  float d[VX_MAX_L];
-};
-
-__device__ __forceinline__ float roundtrip(float a, int size) {
-  const float sm1 = (float)(size - 1);
-  const float n = __fsub_rn(__fmul_rn(__fdiv_rn(a, sm1), 2.f), 1.f);
-  return vx_unnorm_coord(n, size);
-}
-
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
-
-// axis a in reference order: 0 = z (fastest, ATen x), 1 = y, 2 = x (slowest, ATen z)
-struct SdfTapCoords {
-  float c[3];    // undisplaced clamped+roundtripped coordinate per axis (ATen x,y,z order)
-  float raw[3];  // unclamped index per axis
-};
-
-__device__ __forceinline__ void sdf_tap_setup(const VxGrid& g, float px, float py, float pz, SdfTapCoords& s) {
-  float ix, iy, iz;
-  point_to_index(g, px, py, pz, ix, iy, iz);
-  s.raw[0] = ix; s.raw[1] = iy; s.raw[2] = iz;
-  s.c[0] = roundtrip(clampf(ix, 0.f, (float)(g.Z - 1)), g.Z);
-  s.c[1] = roundtrip(clampf(iy, 0.f, (float)(g.Y - 1)), g.Y);
-  s.c[2] = roundtrip(clampf(iz, 0.f, (float)(g.X - 1)), g.X);
-}
-
-__device__ __forceinline__ int axis_size(const VxGrid& g, int a) { return a == 0 ? g.Z : (a == 1 ? g.Y : g.X); }
-
-// coordinates of tap (axis a, sign s in {-1,+1}, displacement d); returns the clamped raw index on axis a
-__device__ __forceinline__ float sdf_tap_coords(const VxGrid& g, const SdfTapCoords& s, int a, float sd, float& ix,
-                                                float& iy, float& iz) {
-  const int size = axis_size(g, a);
-  const float cl = clampf(__fadd_rn(s.raw[a], sd), 0.f, (float)(size - 1));
-  const float v = roundtrip(cl, size);
-  ix = (a == 0) ? v : s.c[0];
-  iy = (a == 1) ? v : s.c[1];
-  iz = (a == 2) ? v : s.c[2];
-  return cl;
-}
-
 __global__ void k_sdf_taps(VxGrid g, const float* __restrict__ grid, VxPts pts, const int* __restrict__ n_dev,
                            int64_t n_host, VxDisp disp, float voxel_size, int use_grad_norm, int xyz_order,
                            float* __restrict__ out_sdf, float* __restrict__ out_feat, float* __restrict__ out_grad) {
@@ -355,13 +294,6 @@ __global__ void k_sdf_taps_bwd(VxGrid g, const float* __restrict__ grid, VxPts p
   }
 }
 
-static int fill_disp(VxDisp& d, const float* displace_host, int L) {
-  if (L < 0 || L > VX_MAX_L) return -1;
-  d.L = L;
-  for (int i = 0; i < VX_MAX_L; ++i) d.d[i] = i < L ? displace_host[i] : 0.f;
-  return 0;
-}
-
 VX_API int vx_sdf_taps(const float* grid, int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
                        const float* xyz, const int* ray_id, const int* step_id, const float* rays_start,
                        const float* rays_dir, float stepdist, const int* n_dev, int64_t n_host,
@@ -397,8 +329,6 @@ VX_API int vx_sdf_taps_backward(const float* grid, int X, int Y, int Z, const fl
 // ---------------------------------------------------------------------------------------------
 // NeuS alpha (lib/voxurf_fine.py:463-500), forward and backward, one thread per sample.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
 __global__ void k_neus_alpha(const float* __restrict__ viewdirs, const int* __restrict__ ray_id,
                              const int64_t* __restrict__ ray_id64, const float* __restrict__ sdf,
                              const float* __restrict__ gradient, float dist, float inv_s, const int* __restrict__ n_dev,

@@ -408,6 +408,12 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int* __restrict__ in, i
   if (threadIdx.x == 0) out[n] = carry_s;
 }
 
+VX_API int vx_scan_i32(const int* in, int n, int* out /* n+1 */, cudaStream_t st) {
+  if (n < 0) return 0;
+  k_scan_i32<<<1, 1024, 0, st>>>(in, n, out);
+  return vx_check_launch("vx_scan_i32");
+}
+
 // pass 2: expand bit words into the compact list; also (optionally) the legacy M0-sized
 // mask_outbbox = !keep, which is what voxurf_fine.py:636 leaves in ret_dict['mask_outbbox'].
 __global__ void k_march_emit(const int64_t* __restrict__ offsets, int n_rays, const uint32_t* __restrict__ bits_keep,

@@ -1,0 +1,304 @@
+"""Sync-free fused fine-stage step: the B200-first execution of Voxurf.forward + losses + backward + TV +
+per-voxel Adam (lib/voxurf_fine.py:620-802, run.py:600-659) on persistent device buffers.
+
+What this replaces, per training iteration of the reference: ~150 kernel launches, >= 13 host syncs, ~10
+boolean-mask compactions and a dense autograd graph.  Here the iteration is ~45 launches, ZERO host syncs and no
+per-step allocation: every data-dependent count (M2 = samples after bbox + mask cache, M4 = MLP rows) stays in
+device memory and is read by the consuming kernels; threshold compactions are a keep-flag and one index list.
+Results are the same numbers as `voxurf_fine.Voxurf.forward` + autograd (tests/test_gpu_fused.py).
+
+Sequence (kernel -> reference lines):
+  vx_ray_setup            t_min/t_max, N_steps, start/dir, scan          render_utils_kernel.cu:12-79,210-212
+  vx_march_flags/emit     bbox + MaskCache keep bits -> (ray_id, step_id) voxurf_fine.py:593-617,631-636,930-942
+  vx_fused_sdf_alpha      sdf, 6-tap gradient, NeuS alpha, alpha > thres  voxurf_fine.py:640-648
+  vx_alpha2weight_seg     T / weights (bit-exact recurrence), w > thres   voxurf_fine.py:667-669
+  vx_scan_i32, vx_fused_emit_rows   row list                              voxurf_fine.py:670-676
+  vx_fused_row_features   k0 gather, sample_sdfs (L=4), PEs -> X1, X2     voxurf_fine.py:678-739
+  MLP rgbnet / k_rgbnet   (mlp.py)                                        voxurf_fine.py:718,749
+  vx_fused_composite_loss sigmoid, segment sums, losses, their backward   voxurf_fine.py:752-763, run.py:604-636
+  MLP backward            dX1, dX2, weight grads
+  vx_fused_row_backward   k0 scatter, sample_sdfs scatter                 (ATen grid_sampler backward)
+  vx_alpha2weight_seg_backward                                            render_utils_kernel.cu:653-677
+  vx_fused_alpha_sdf_backward  NeuS alpha backward + 7-tap sdf scatter
+  [TV iters] vx_fd_gradient, vx_smooth_grad_tv, vx_fd_gradient_backward, vx_total_variation_add_grad
+  vx_adam_step x4         sdf, k0 (fused grad zero-fill), rgbnet, k_rgbnet lib/utils.py:154-199
+"""
+import math
+
+import numpy as np
+import torch
+
+from ._lib import call
+from .mlp import FlatMLP
+from .optim import _storage
+
+
+class FusedFineStep:
+    def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0):
+        if model.k0_dim not in (6, 12):
+            raise NotImplementedError('fused step: k0 channels must be 6 or 12')
+        if model.k_center_sdf or not model.center_sdf or not model.k_res:
+            raise NotImplementedError('fused step covers the shipped fine configs (center_sdf, k_res, no k_center_sdf)')
+        self.m, self.N = model, int(n_rays)
+        self.cfg = dict(train_cfg) if train_cfg is not None else None
+        self.rk = dict(render_kwargs or {})
+        self.world, self.rank = world, rank
+        dev = model.sdf.grid.device
+        self.dev = dev
+        m = model
+        self.X, self.Y, self.Z = (int(w) for w in m.world_size)
+        self.C = m.k0_dim
+        self.k0_cl = int(m.k0.channels_last)
+        self.disp = sorted(set(m.grad_feat + m.k_grad_feat))
+        assert self.disp == sorted(set(m.sdf_feat + m.k_sdf_feat)) or len(m.k_sdf_feat) == 0
+        self.disp = sorted(set(m.grad_feat))
+        self.L = len(self.disp)
+        self.P, self.Vp = m.posfreq.numel(), m.viewfreq.numel()
+        self.P2, self.V2 = m.k_posfreq.numel(), m.k_viewfreq.numel()
+        self.D1 = 3 + 6 * self.P + 3 + 6 * self.Vp + 1 + 9 * self.L
+        self.D2 = self.C + 3 + 6 * self.P2 + 3 + 6 * self.V2 + 3 + 3
+        self.ld1 = (self.D1 + 15) // 16 * 16
+        self.ld2 = (self.D2 + 15) // 16 * 16
+        self.col_logit = self.D2 - 3
+        stepdist = float(np.float32(float(self.rk.get('stepsize', 0.5)) * m._voxel_size_host))
+        self.stepdist = stepdist
+        self.dist = float(np.float32(float(self.rk.get('stepsize', 0.5)) * m._voxel_size_host))
+        N = self.N
+        cap2 = N * m._max_steps(stepdist)
+        self.cap2 = cap2
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+        u8 = lambda *s: torch.empty(*s, dtype=torch.uint8, device=dev)
+        # per ray
+        self.t_min, self.t_max = f32(N), f32(N)
+        self.n_steps = torch.empty(N, dtype=torch.int64, device=dev)
+        self.start, self.dirs = f32(N, 3), f32(N, 3)
+        self.offsets = torch.empty(N + 1, dtype=torch.int64, device=dev)
+        words = N * (m._max_steps(stepdist) // 32 + 2) + 1
+        self.bits_in, self.bits_keep = i32(words), i32(words)
+        self.keep_count, self.keep_off = i32(N), i32(N + 1)
+        self.w_count, self.off4 = i32(N), i32(N + 1)
+        self.alphainv_last, self.i_end, self.d_last, self.loss_ray = f32(N), i32(N), f32(N), f32(N)
+        self.rgb_marched, self.rgb_marched0 = f32(N, 3), f32(N, 3)
+        self.normal_marched, self.depth = f32(N, 3), f32(N)
+        self.loss = f32(1)
+        # per M2 sample
+        self.ray_id, self.step_id = i32(cap2), i32(cap2)
+        self.sdf_s, self.grad_s, self.alpha = f32(cap2), f32(cap2, 3), f32(cap2)
+        self.keep, self.w_keep = u8(cap2), u8(cap2)
+        self.weight, self.T = f32(cap2), f32(cap2)
+        self.d_w, self.d_alpha, self.d_sdf_s, self.d_grad_s = f32(cap2), f32(cap2), f32(cap2), f32(cap2, 3)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._alloc_rows(int(row_capacity))
+        # MLPs on flat parameter / gradient storage (one Adam launch per network)
+        self.mlp1 = FlatMLP(m.rgbnet, self.ld1, self.D1)
+        self.mlp2 = FlatMLP(m.k_rgbnet, self.ld2, self.D2)
+        # persistent gradient buffers for the grids (zeroed by the Adam kernel itself)
+        self.sdf_grad = torch.zeros_like(m.sdf.grid)
+        self.k0_grad = torch.zeros_like(m.k0.grid, memory_format=torch.preserve_format)
+        m.sdf.grid.grad, m.k0.grid.grad = self.sdf_grad, self.k0_grad
+        self.G = None       # FD gradient grid + its gradient, allocated on the first TV iteration
+        self.smoothed = self.d_smoothed = None
+        if m.smooth_sdf:
+            self.smoothed, self.d_smoothed = torch.empty_like(m.sdf.grid), torch.zeros_like(m.sdf.grid)
+        self.adam_state = {}
+        self.adam_steps = 0
+        self.timings = None   # bench.py: list collecting (start, end) CUDA events around the k0 Adam launch
+        if self.cfg is not None:
+            c = self.cfg
+            self.groups = [('sdf', [m.sdf.grid], c['lrate_sdf']), ('k0', [m.k0.grid], c['lrate_k0']),
+                           ('rgbnet', [self.mlp1.flat], c['lrate_rgbnet']), ('k_rgbnet', [self.mlp2.flat], c['lrate_k_rgbnet'])]
+            self.lr = {name: lr for name, _, lr in self.groups}
+
+    def _alloc_rows(self, cap):
+        dev = self.dev
+        self.cap4 = cap
+        self.idx4 = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.X1 = torch.empty(cap, self.ld1, dtype=torch.float32, device=dev)
+        self.X2 = torch.empty(cap, self.ld2, dtype=torch.float32, device=dev)
+        self.dX1, self.dX2 = torch.empty_like(self.X1), torch.empty_like(self.X2)
+        self.logit1 = torch.empty(cap, 3, dtype=torch.float32, device=dev)
+        self.k_out = torch.empty(cap, 3, dtype=torch.float32, device=dev)
+        self.d_logit1, self.d_kout = torch.zeros_like(self.logit1), torch.zeros_like(self.k_out)
+        if hasattr(self, 'mlp1'):
+            self.mlp1.alloc(cap), self.mlp2.alloc(cap)
+
+    # ------------------------------------------------------------------ forward pieces
+    def _geom(self):
+        m = self.m
+        return (self.X, self.Y, self.Z, m._min_host, m._max_host)
+
+    def _pts(self):
+        return (self.ray_id, self.step_id, self.start, self.dirs, self.stepdist)
+
+    def _forward(self, rays_o, rays_d, viewdirs, global_step, train, target=None):
+        m, N = self.m, self.N
+        assert rays_o.shape[0] == N, 'FusedFineStep is sized for a fixed batch; build another for a different one'
+        rays_o, rays_d, viewdirs = rays_o.contiguous(), rays_d.contiguous(), viewdirs.contiguous()
+        s_val, inv_s = m._update_s_val(global_step)
+        self.inv_s = inv_s
+        X, Y, Z, mn, mx = self._geom()
+        near = self.rk['near']
+        call('vx_ray_setup', rays_o, rays_d, m.xyz_min, m.xyz_max, near, 1e9, self.stepdist, N, self.t_min, self.t_max,
+             self.n_steps, self.start, self.dirs, self.offsets)
+        mc = m.mask_cache.march_args() if m.mask_cache is not None else (None, 1, 1, 1, [0., 0., 0.], [1., 1., 1.], 0., 1., 0.)
+        call('vx_march_flags', self.start, self.dirs, m.xyz_min, m.xyz_max, self.offsets, N, self.stepdist, *mc,
+             self.bits_in, self.bits_keep, self.keep_count, self.keep_off)
+        call('vx_march_emit', self.offsets, N, self.bits_keep, self.keep_off, self.cap2, self.ray_id, self.step_id, None)
+        n2 = self.keep_off[N:]
+        if m.smooth_sdf:
+            call('vx_conv3d_replicate', m.sdf.grid, 1, X, Y, Z, m.smooth_conv.weight_host, m.smooth_conv.ksize, self.smoothed)
+            sdf_grid = self.smoothed
+        else:
+            sdf_grid = m.sdf.grid
+        self._sdf_grid = sdf_grid
+        thres = float(m.fast_color_thres)
+        call('vx_fused_sdf_alpha', sdf_grid, X, Y, Z, mn, mx, *self._pts(), n2, viewdirs, m._voxel_size_host, self.dist,
+             inv_s, thres, self.sdf_s, self.grad_s, self.alpha, self.keep, self.d_w, self.d_sdf_s, self.d_grad_s)
+        call('vx_alpha2weight_seg', self.alpha, self.keep if thres > 0 else None, self.keep_off, N, thres, self.weight, self.T,
+             self.alphainv_last, self.i_end, self.w_keep, self.w_count)
+        call('vx_scan_i32', self.w_count, N, self.off4)
+        call('vx_fused_emit_rows', self.w_keep, self.keep_off, self.off4, N, self.cap4, self.idx4, self.overflow)
+        n4 = self.off4[N:]
+        call('vx_fused_row_features', sdf_grid, _storage(m.k0.grid), X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(),
+             self.idx4, n4, self.cap4, viewdirs, self.sdf_s, self.grad_s, m._voxel_size_host, int(m.use_grad_norm),
+             self.P, self.Vp, self.P2, self.V2, self.disp, self.L, self.ld1, self.ld2, self.X1, self.X2)
+        self.mlp1.forward(self.X1, self.logit1, keep_activations=train)
+        call('vx_fused_fill_logit_cols', self.logit1, 3, n4, self.cap4, self.col_logit, self.ld2, self.X2)
+        self.mlp2.forward(self.X2, self.k_out, keep_activations=train)
+        return s_val, n2, n4
+
+    def _loss_cfg(self):
+        c = self.cfg or {}
+        w_ent = c.get('weight_entropy_last', 0.0)
+        # run.py:607-610 reads the LAST ray of the batch only; with rays sharded over ranks that is the last ray of
+        # the last rank, and gradients are averaged over ranks afterwards, hence the factor `world` there, 0 elsewhere
+        ent_scale = 1.0 if self.world == 1 else (float(self.world) if self.rank == self.world - 1 else 0.0)
+        return c.get('weight_main', 1.0), c.get('weight_rgb0', 0.0), w_ent, ent_scale
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, viewdirs, render_grad=True, render_depth=True):
+        """Inference forward (run.py:123-126 calls model(...) per 8192-ray chunk): -> dict of (N, .) tensors.
+        Buffers are reused by the next call: clone what you keep."""
+        s_val, n2, n4 = self._forward(rays_o, rays_d, viewdirs, None, train=False)
+        call('vx_fused_composite_loss', self.logit1, self.k_out, 3, self.idx4, self.off4, self.cap4, self.weight,
+             self.alphainv_last, None, self.N, 0.0, 0.0, 0.0, 0.0, float(self.rk.get('bg', 0.0)), 0, self.rgb_marched,
+             self.rgb_marched0, None, None, None, None, None)
+        if render_grad or render_depth:
+            call('vx_fused_composite_aux', self.idx4, self.off4, self.cap4, self.weight, self.grad_s, self.step_id, self.dist,
+                 self.N, self.normal_marched if render_grad else None, self.depth if render_depth else None)
+        return {'rgb_marched': self.rgb_marched, 'rgb_marched0': self.rgb_marched0, 'alphainv_cum': self.alphainv_last,
+                'normal_marched': self.normal_marched if render_grad else None, 'depth': self.depth if render_depth else None,
+                'disp': (1 / self.depth) if render_depth else 0, 's_val': s_val}
+
+    @torch.no_grad()
+    def forward_backward(self, rays_o, rays_d, viewdirs, target, global_step):
+        """Forward + losses + backward into the persistent gradient buffers.  Returns the (device) scalar loss."""
+        m, N = self.m, self.N
+        s_val, n2, n4 = self._forward(rays_o, rays_d, viewdirs, global_step, train=True)
+        X, Y, Z, mn, mx = self._geom()
+        w_main, w_rgb0, w_ent, ent_scale = self._loss_cfg()
+        call('vx_fused_composite_loss', self.logit1, self.k_out, 3, self.idx4, self.off4, self.cap4, self.weight,
+             self.alphainv_last, target.contiguous(), N, w_main, w_rgb0, w_ent, ent_scale, float(self.rk.get('bg', 0.0)), 1,
+             self.rgb_marched, self.rgb_marched0, self.d_logit1, self.d_kout, self.d_w, self.d_last, self.loss_ray)
+        call('vx_sum_f32', self.loss_ray, N, self.loss)
+        self.mlp2.backward(self.d_kout, self.dX2)
+        self.mlp1.backward(self.d_logit1, self.dX1)
+        grad_target = self.d_smoothed if m.smooth_sdf else self.sdf_grad
+        call('vx_fused_row_backward', self._sdf_grid, X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(), self.idx4, n4,
+             self.cap4, m._voxel_size_host, int(m.use_grad_norm), self.P, self.Vp, self.P2, self.V2, self.disp, self.L,
+             self.ld1, self.ld2, self.dX1, self.dX2, self.d_sdf_s, self.d_grad_s, grad_target, _storage(self.k0_grad))
+        thres = float(m.fast_color_thres)
+        call('vx_alpha2weight_seg_backward', self.alpha, self.weight, self.T, self.keep if thres > 0 else None,
+             self.alphainv_last, self.keep_off, self.i_end, N, self.d_w, self.d_last, self.d_alpha)
+        call('vx_fused_alpha_sdf_backward', X, Y, Z, mn, mx, *self._pts(), n2, viewdirs.contiguous(), self.sdf_s, self.grad_s,
+             self.keep, self.d_alpha, self.d_sdf_s, self.d_grad_s, m._voxel_size_host, self.dist, self.inv_s, grad_target)
+        if m.smooth_sdf:
+            call('vx_conv3d_replicate_backward', self.d_smoothed, 1, X, Y, Z, m.smooth_conv.weight_host, m.smooth_conv.ksize, 1,
+                 self.sdf_grad)
+            self.d_smoothed.zero_()
+        return self.loss
+
+    def is_tv_iter(self, global_step):
+        c = self.cfg
+        return c['tv_from'] < global_step < c['tv_end'] and global_step % c['tv_every'] == 0
+
+    @torch.no_grad()
+    def regularise(self, global_step, global_batch=None):
+        """run.py:612-625 (smooth-grad TV through the full-grid FD gradient) and run.py:641-655 (TV add-grad)."""
+        c, m = self.cfg, self.m
+        if not self.is_tv_iter(global_step) or c['weight_tv_density'] <= 0 or c.get('ori_tv', False):
+            return
+        X, Y, Z = self.X, self.Y, self.Z
+        tv = c['tv_terms']
+        if tv['smooth_grad_tv'] > 0:
+            if self.G is None:
+                self.G = torch.empty(1, 3, X, Y, Z, dtype=torch.float32, device=self.dev)
+                self.dG = torch.empty_like(self.G)
+                self.tv_loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+                self.tv_scratch = torch.empty(int(call('vx_smooth_grad_tv_scratch_floats')), dtype=torch.float32, device=self.dev)
+            call('vx_fd_gradient', m.sdf.grid, X, Y, Z, m._voxel_size_host, self.G)
+            m.gradient = self.G
+            w = c['weight_tv_density'] * tv['smooth_grad_tv'] / (3.0 * m._n_nonempty)
+            call('vx_smooth_grad_tv', self.G, m.nonempty_mask[0, 0], X, Y, Z, m._tv_smooth_w, w, self.dG, self.tv_scratch, self.tv_loss)
+            self.loss.add_(self.tv_loss)   # run.py:622-625 adds the regulariser to the reported loss
+            call('vx_fd_gradient_backward', self.dG, X, Y, Z, m._voxel_size_host, self.sdf_grad)
+        if tv['sdf_tv'] > 0:
+            n_batch = global_batch or self.N * self.world
+            wt = c['weight_tv_density'] * tv['sdf_tv'] / n_batch * max(X, Y, Z) / 128
+            call('vx_total_variation_add_grad', m.sdf.grid, self.sdf_grad, None, wt, wt, wt,
+                 int(global_step < c['tv_dense_before']), X, Y, Z, m.sdf.grid.numel())
+
+    @torch.no_grad()
+    def optimizer_step(self):
+        """lib/utils.py:83-199 with betas (0.9, 0.99), eps 1e-8 (lib/utils.py:229); grads are zeroed in the same pass."""
+        self.adam_steps += 1
+        step, beta1, beta2, eps = self.adam_steps, 0.9, 0.99, 1e-8
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        for name, params, _ in self.groups:
+            lr = self.lr[name]
+            for p in params:
+                st = self.adam_state.get(id(p))
+                if st is None:
+                    st = (torch.zeros_like(p, memory_format=torch.preserve_format), torch.zeros_like(p, memory_format=torch.preserve_format))
+                    self.adam_state[id(p)] = st
+                timed = self.timings is not None and name == 'k0'
+                if timed:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
+                call('vx_adam_step', _storage(p.data), _storage(p.grad), _storage(st[0]), _storage(st[1]), None, p.numel(),
+                     beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1)
+                if timed:
+                    ev[1].record()
+                    self.timings.append(ev)
+
+    def step(self, rays_o, rays_d, viewdirs, target, global_step, grad_sync=None):
+        """One training iteration (run.py:600-659).  grad_sync: optional callable run between backward and TV/Adam."""
+        loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
+        if grad_sync is not None:
+            grad_sync()
+        self.regularise(global_step)
+        self.optimizer_step()
+        return loss
+
+    def counts(self):
+        """(M0, M2, M4) of the last step -- this syncs; for logging and capacity calibration only."""
+        v = torch.stack([self.offsets[self.N], self.keep_off[self.N].long(), self.off4[self.N].long(), self.overflow[0].long()]).cpu()
+        if int(v[3]) > 0:
+            raise RuntimeError(f'FusedFineStep: {int(v[3])} MLP rows exceed row_capacity={self.cap4}; call calibrate() or raise it')
+        return int(v[0]), int(v[1]), int(v[2])
+
+    def calibrate(self, rays_o, rays_d, viewdirs, global_step=None, headroom=1.3, multiple=4096):
+        """Size the row buffers from one forward of a representative batch (one-off sync).  Pass the global_step the
+        run is at: the NeuS sharpness s_val (and with it the number of MLP rows) depends on it."""
+        self.overflow.zero_()
+        with torch.no_grad():
+            self._forward(rays_o, rays_d, viewdirs, global_step, train=False)
+        v = torch.stack([self.off4[self.N], self.overflow[0]]).cpu()
+        m4 = max(int(v[0]), int(v[1]))
+        cap = max(multiple, int(math.ceil(m4 * headroom / multiple)) * multiple)
+        self.overflow.zero_()
+        if cap != self.cap4:
+            self._alloc_rows(cap)
+        return cap

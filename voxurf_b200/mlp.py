@@ -1,0 +1,81 @@
+"""The two colour MLPs of the fine model (rgbnet 79->192->192->192->3, k_rgbnet 54->...; lib/voxurf_fine.py:132-187)
+run over the fixed-capacity row matrices of the fused step with explicit forward / backward passes and flat
+parameter + gradient storage (one Adam launch per network, no autograd graph).
+
+This is the one dense-contraction stage of the path.  Round-1 implementation: fp32 cuBLAS GEMMs
+(torch.addmm / mm on preallocated buffers, TF32 off) -- "plain library GEMM" per the task rules; the fused
+tensor-core (tcgen05) kernel that keeps the 79/54-wide rows and the hidden activations on chip is the next step
+and plugs in behind the same three methods (alloc / forward / backward).
+"""
+import torch
+import torch.nn as nn
+
+
+class FlatMLP:
+    def __init__(self, seq, ld_in, d_in):
+        """seq: nn.Sequential of Linear / ReLU (possibly nested).  The first layer's weight is stored padded to
+        `ld_in` input columns (zeros) so the padded row matrix is consumed without a strided copy."""
+        self.linears = [m for m in seq.modules() if isinstance(m, nn.Linear)]
+        assert self.linears[0].in_features == d_in
+        dev = self.linears[0].weight.device
+        self.ld_in, self.d_in = ld_in, d_in
+        shapes = []
+        for i, l in enumerate(self.linears):
+            shapes.append((l.out_features, ld_in if i == 0 else l.in_features))
+        n = sum(o * i + o for o, i in shapes)
+        n = (n + 3) // 4 * 4
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat.grad = torch.zeros_like(self.flat)
+        self.W, self.b, self.dW, self.db = [], [], [], []
+        o = 0
+        for (out_f, in_f), l in zip(shapes, self.linears):
+            W = self.flat[o:o + out_f * in_f].view(out_f, in_f)
+            dW = self.flat.grad[o:o + out_f * in_f].view(out_f, in_f)
+            o += out_f * in_f
+            b = self.flat[o:o + out_f]
+            db = self.flat.grad[o:o + out_f]
+            o += out_f
+            W[:, :l.in_features].copy_(l.weight.data)
+            b.copy_(l.bias.data)
+            # the module's parameters become views of the flat storage: state_dict / external code see live values
+            l.weight.data = W[:, :l.in_features]
+            l.bias.data = b
+            l.weight.grad = dW[:, :l.in_features]
+            l.bias.grad = db
+            self.W.append(W); self.b.append(b); self.dW.append(dW); self.db.append(db)
+        self.H = None
+
+    def alloc(self, cap):
+        dev = self.flat.device
+        self.cap = cap
+        self.H = [torch.empty(cap, l.out_features, dtype=torch.float32, device=dev) for l in self.linears[:-1]]
+        self.dH = [torch.empty_like(h) for h in self.H]
+
+    def forward(self, X, out, keep_activations=True):
+        """X (cap, ld_in) -> out (cap, 3).  Hidden activations stay in self.H for the backward pass."""
+        if self.H is None or self.H[0].shape[0] != X.shape[0]:
+            self.alloc(X.shape[0])
+        h = X
+        for i in range(len(self.linears) - 1):
+            torch.addmm(self.b[i], h, self.W[i].t(), out=self.H[i])
+            self.H[i].relu_()
+            h = self.H[i]
+        torch.addmm(self.b[-1], h, self.W[-1].t(), out=out)
+        self._X = X
+        return out
+
+    def backward(self, d_out, dX):
+        """d_out (cap, 3) -> dX (cap, ld_in); accumulates weight / bias gradients into the flat gradient buffer."""
+        n = len(self.linears)
+        dy = d_out
+        for i in range(n - 1, -1, -1):
+            h_in = self.H[i - 1] if i > 0 else self._X
+            self.db[i].add_(dy.sum(0))
+            self.dW[i].addmm_(dy.t(), h_in)
+            if i > 0:
+                torch.mm(dy, self.W[i], out=self.dH[i - 1])
+                self.dH[i - 1].masked_fill_(self.H[i - 1] <= 0, 0.0)
+                dy = self.dH[i - 1]
+            else:
+                torch.mm(dy, self.W[0], out=dX)
+        return dX
