@@ -237,6 +237,15 @@ int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min_host, 
                                 const float* d_grad_s, float voxel_size, float dist, float inv_s, float* sdf_grad,
                                 cudaStream_t stream);
 
+/* ---- tensor-core MLP (tcgen05, TF32x3 split; lib/voxurf_fine.py:132-187,718,749) ---------------------------- */
+/* hi/lo weight images, zero padded to (Np, Kp), optionally transposed (dX chain) */
+int vx_mlp_prep(const float* W, int N, int K, int ldw, int Np, int Kp, int transpose, float* W_hi, float* W_lo,
+                cudaStream_t stream);
+/* Y = chain of up to 4 layers y = act(x W^T + b) [* (mask > 0)] on 128-row tiles; see csrc/mlp_tc.cu for the packed
+ * host arrays: ptrs_host[l*5..] = W_hi, W_lo, bias, H_out, mask device addresses; dims_host[l*5..] = Kp, Np, N, ldh, relu */
+int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, int capacity, int n_layers,
+                 const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,65 @@
+"""Dev check of the tcgen05 MLP chain against float64 torch (run on the GPU box)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from voxurf_b200.mlp import TensorCoreChain
+
+torch.manual_seed(0)
+dev = 'cuda'
+
+
+def run_case(dims, cap, n_rows, k0_valid=None, relu=True):
+    Ws = [torch.randn(dims[i + 1], dims[i], device=dev) / dims[i] ** 0.5 for i in range(len(dims) - 1)]
+    bs = [torch.randn(dims[i + 1], device=dev) * 0.1 for i in range(len(dims) - 1)]
+    layers = [dict(W=W, bias=b, relu=(relu and i + 1 < len(Ws))) for i, (W, b) in enumerate(zip(Ws, bs))]
+    ch = TensorCoreChain(layers)
+    ch.prepare()
+    ldx = (dims[0] + 15) // 16 * 16
+    X = torch.zeros(cap, ldx, device=dev)
+    X[:, :dims[0]] = torch.randn(cap, dims[0], device=dev)
+    Y = torch.full((cap, dims[-1]), float('nan'), device=dev)
+    H = [torch.full((cap, dims[i + 1]), float('nan'), device=dev) for i in range(len(dims) - 2)]
+    n_dev = torch.tensor([n_rows], dtype=torch.int32, device=dev)
+    ch.run(X, dims[0], n_dev, Y, dims[-1], H_out=H)
+    torch.cuda.synchronize()
+    h = X[:n_rows, :dims[0]].double()
+    ok = True
+    for i, (W, b) in enumerate(zip(Ws, bs)):
+        h = h @ W.double().t() + b.double()
+        if i + 1 < len(Ws):
+            if relu:
+                h = h.relu()
+            err = ((H[i][:n_rows].double() - h).abs().max() / h.abs().max()).item()
+            print(f'   hidden {i}: rel err {err:.3e}')
+            ok &= err < 3e-6
+    err = ((Y[:n_rows].double() - h).abs().max() / h.abs().max()).item()
+    untouched = torch.isnan(Y[n_rows:]).all().item() if n_rows < cap else True
+    print(f'dims {dims} cap {cap} rows {n_rows}: out rel err {err:.3e} tail untouched {untouched}')
+    return ok and err < 3e-6 and untouched
+
+
+ok = True
+ok &= run_case([192, 16], 128, 128)                      # one K=192 layer, N=16
+ok &= run_case([64, 192, 3], 256, 200)
+ok &= run_case([80, 192, 192, 192, 3], 1024, 1000)
+ok &= run_case([64, 192, 192, 192, 3], 70000, 61234)
+print('ALL OK' if ok else 'FAILED')
+import time
+# timing of the full-size chain
+dims = [80, 192, 192, 192, 3]
+Ws = [torch.randn(dims[i + 1], dims[i], device=dev) / dims[i] ** 0.5 for i in range(4)]
+bs = [torch.randn(dims[i + 1], device=dev) * 0.1 for i in range(4)]
+ch = TensorCoreChain([dict(W=W, bias=b, relu=i < 3) for i, (W, b) in enumerate(zip(Ws, bs))]); ch.prepare()
+cap = 61440
+X = torch.randn(cap, 80, device=dev); Y = torch.empty(cap, 3, device=dev)
+H = [torch.empty(cap, 192, device=dev) for _ in range(3)]
+n_dev = torch.tensor([43000], dtype=torch.int32, device=dev)
+for _ in range(3):
+    ch.run(X, 80, n_dev, Y, 3, H_out=H)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    ch.run(X, 80, n_dev, Y, 3, H_out=H)
+e1.record(); torch.cuda.synchronize()
+print('chain fwd 43000 rows: %.1f us' % (e0.elapsed_time(e1) / 20 * 1e3))

@@ -118,8 +118,11 @@ def call(name, *args):
             if a is None:
                 cargs.append(ctypes.c_void_p(0))
                 continue
-            vals = [float(v) for v in (a.flatten().tolist() if torch.is_tensor(a) else a)]
-            buf = (ctypes.c_float * max(1, len(vals)))(*vals)
+            seq = a.flatten().tolist() if torch.is_tensor(a) else a
+            if ctype == 'float':
+                buf = (ctypes.c_float * max(1, len(seq)))(*[float(v) for v in seq])
+            else:
+                buf = (_SCALARS[ctype] * max(1, len(seq)))(*[int(v) for v in seq])
             keep.append(buf)
             cargs.append(ctypes.cast(buf, ctypes.c_void_p))
         else:

@@ -34,7 +34,8 @@ from .optim import _storage
 
 
 class FusedFineStep:
-    def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0):
+    def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0,
+                 tensor_core=True):
         if model.k0_dim not in (6, 12):
             raise NotImplementedError('fused step: k0 channels must be 6 or 12')
         if model.k_center_sdf or not model.center_sdf or not model.k_res:
@@ -43,6 +44,7 @@ class FusedFineStep:
         self.cfg = dict(train_cfg) if train_cfg is not None else None
         self.rk = dict(render_kwargs or {})
         self.world, self.rank = world, rank
+        self.tensor_core = tensor_core
         dev = model.sdf.grid.device
         self.dev = dev
         m = model
@@ -91,8 +93,8 @@ class FusedFineStep:
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self._alloc_rows(int(row_capacity))
         # MLPs on flat parameter / gradient storage (one Adam launch per network)
-        self.mlp1 = FlatMLP(m.rgbnet, self.ld1, self.D1)
-        self.mlp2 = FlatMLP(m.k_rgbnet, self.ld2, self.D2)
+        self.mlp1 = FlatMLP(m.rgbnet, self.ld1, self.D1, tensor_core)
+        self.mlp2 = FlatMLP(m.k_rgbnet, self.ld2, self.D2, tensor_core)
         # persistent gradient buffers for the grids (zeroed by the Adam kernel itself)
         self.sdf_grad = torch.zeros_like(m.sdf.grid)
         self.k0_grad = torch.zeros_like(m.k0.grid, memory_format=torch.preserve_format)
@@ -163,9 +165,9 @@ class FusedFineStep:
         call('vx_fused_row_features', sdf_grid, _storage(m.k0.grid), X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(),
              self.idx4, n4, self.cap4, viewdirs, self.sdf_s, self.grad_s, m._voxel_size_host, int(m.use_grad_norm),
              self.P, self.Vp, self.P2, self.V2, self.disp, self.L, self.ld1, self.ld2, self.X1, self.X2)
-        self.mlp1.forward(self.X1, self.logit1, keep_activations=train)
+        self.mlp1.forward(self.X1, self.logit1, keep_activations=train, n_rows_dev=n4 if self.tensor_core else None)
         call('vx_fused_fill_logit_cols', self.logit1, 3, n4, self.cap4, self.col_logit, self.ld2, self.X2)
-        self.mlp2.forward(self.X2, self.k_out, keep_activations=train)
+        self.mlp2.forward(self.X2, self.k_out, keep_activations=train, n_rows_dev=n4 if self.tensor_core else None)
         return s_val, n2, n4
 
     def _loss_cfg(self):

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 
 class FlatMLP:
-    def __init__(self, seq, ld_in, d_in):
+    def __init__(self, seq, ld_in, d_in, tensor_core=True):
         """seq: nn.Sequential of Linear / ReLU (possibly nested).  The first layer's weight is stored padded to
         `ld_in` input columns (zeros) so the padded row matrix is consumed without a strided copy."""
         self.linears = [m for m in seq.modules() if isinstance(m, nn.Linear)]
@@ -44,6 +44,11 @@ class FlatMLP:
             l.bias.grad = db
             self.W.append(W); self.b.append(b); self.dW.append(dW); self.db.append(db)
         self.H = None
+        self.tensor_core = tensor_core
+        self.tc_fwd = None
+        if tensor_core:
+            n = len(self.W)
+            self.tc_fwd = TensorCoreChain([dict(W=self.W[i], bias=self.b[i], relu=(i + 1 < n)) for i in range(n)])
 
     def alloc(self, cap):
         dev = self.flat.device
@@ -51,10 +56,15 @@ class FlatMLP:
         self.H = [torch.empty(cap, l.out_features, dtype=torch.float32, device=dev) for l in self.linears[:-1]]
         self.dH = [torch.empty_like(h) for h in self.H]
 
-    def forward(self, X, out, keep_activations=True):
+    def forward(self, X, out, keep_activations=True, n_rows_dev=None):
         """X (cap, ld_in) -> out (cap, 3).  Hidden activations stay in self.H for the backward pass."""
         if self.H is None or self.H[0].shape[0] != X.shape[0]:
             self.alloc(X.shape[0])
+        self._X = X
+        if self.tensor_core and n_rows_dev is not None:
+            self.tc_fwd.prepare()   # the optimizer changed the weights since the last step
+            self.tc_fwd.run(X, self.ld_in, n_rows_dev, out, out.shape[1], H_out=self.H if keep_activations else None)
+            return out
         h = X
         for i in range(len(self.linears) - 1):
             torch.addmm(self.b[i], h, self.W[i].t(), out=self.H[i])
@@ -79,3 +89,56 @@ class FlatMLP:
             else:
                 torch.mm(dy, self.W[0], out=dX)
         return dX
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core path (tcgen05, TF32x3): csrc/mlp_tc.cu
+# ------------------------------------------------------------------------------------------------
+def _pad(v, m):
+    return (v + m - 1) // m * m
+
+
+class TensorCoreChain:
+    """A chain of up to 4 dense layers executed by one fused tcgen05 kernel launch (vx_mlp_chain).
+
+    layers: list of dicts {W: (N,K) tensor view (row stride ldw), bias: (N,) or None, relu: bool}.  `prepare()` must
+    be called whenever the weights changed (it writes the hi/lo TF32 split images, zero-padded)."""
+
+    def __init__(self, layers, transpose=False):
+        from ._lib import call
+        self._call = call
+        self.layers = layers
+        self.transpose = transpose
+        dev = layers[0]['W'].device
+        self.Kp, self.Np, self.N, self.K = [], [], [], []
+        n = len(layers)
+        for i, L in enumerate(layers):
+            N, K = (L['W'].shape[1], L['W'].shape[0]) if transpose else (L['W'].shape[0], L['W'].shape[1])
+            self.N.append(N); self.K.append(K)
+            self.Kp.append(_pad(K, 8))
+            self.Np.append(_pad(N, 32) if i + 1 < n else _pad(N, 16))
+        for i in range(n - 1):
+            assert self.Np[i] == self.Kp[i + 1], 'hidden widths must be multiples of 32 and chain'
+        self.W_hi = [torch.zeros(self.Np[i], self.Kp[i], dtype=torch.float32, device=dev) for i in range(n)]
+        self.W_lo = [torch.zeros_like(w) for w in self.W_hi]
+
+    def prepare(self):
+        for i, L in enumerate(self.layers):
+            W = L['W']
+            assert W.stride(1) == 1
+            self._call('vx_mlp_prep', W, self.N[i], self.K[i], W.stride(0), self.Np[i], self.Kp[i], int(self.transpose),
+                       self.W_hi[i], self.W_lo[i])
+
+    def run(self, X, k0, n_rows_dev, Y, n_out, H_out=None, masks=None):
+        """X (cap, ldx) with k0 valid columns -> Y (cap, ldy)[:, :n_out].  H_out[l] / masks[l]: optional (cap, ldh) tensors."""
+        n = len(self.layers)
+        ptrs, dims = [], []
+        for i, L in enumerate(self.layers):
+            h = H_out[i] if H_out is not None and i < len(H_out) else None
+            mk = masks[i] if masks is not None and i < len(masks) else None
+            ldh = (h if h is not None else mk).stride(0) if (h is not None or mk is not None) else 0
+            b = L.get('bias')
+            ptrs += [self.W_hi[i].data_ptr(), self.W_lo[i].data_ptr(), b.data_ptr() if b is not None else 0,
+                     h.data_ptr() if h is not None else 0, mk.data_ptr() if mk is not None else 0]
+            dims += [self.Kp[i], self.Np[i], self.N[i], ldh, int(bool(L.get('relu', False)))]
+        self._call('vx_mlp_chain', X, X.stride(0), k0, n_rows_dev, X.shape[0], n, ptrs, dims, Y, Y.stride(0), n_out)
