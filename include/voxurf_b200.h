@@ -241,10 +241,15 @@ int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min_host, 
 /* hi/lo weight images, zero padded to (Np, Kp), optionally transposed (dX chain) */
 int vx_mlp_prep(const float* W, int N, int K, int ldw, int Np, int Kp, int transpose, float* W_hi, float* W_lo,
                 cudaStream_t stream);
-/* Y = chain of up to 4 layers y = act(x W^T + b) [* (mask > 0)] on 128-row tiles; see csrc/mlp_tc.cu for the packed
- * host arrays: ptrs_host[l*5..] = W_hi, W_lo, bias, H_out, mask device addresses; dims_host[l*5..] = Kp, Np, N, ldh, relu */
+/* Y = chain of up to 4 layers y = act(x W^T + b) [* (mask > 0)] on 128-row tiles; packed host arrays (csrc/mlp_tc.cu):
+ * ptrs_host[l*7..] = W_hi, W_lo, bias, H_out, mask, HT_out, maskT device addresses (0 = none); dims_host[l*5..] = Kp, Np, N,
+ * ldh, relu.  XT / HT: feature-major copies (row stride ldt) consumed by vx_mlp_dw. */
 int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, int capacity, int n_layers,
-                 const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, cudaStream_t stream);
+                 const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* XT, int ldt,
+                 cudaStream_t stream);
+/* split-K weight gradient: C[m][n] += sum_r At[m][r] Bt[n][r], c_bias[m] += sum_r At[m][r]  (r < *n_rows_dev) */
+int vx_mlp_dw(const float* At, int M_out, const float* Bt, int N_in, int ldt, const int* n_rows_dev, int capacity,
+              float* C, int ldc, float* c_bias, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

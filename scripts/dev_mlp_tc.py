@@ -63,3 +63,50 @@ for _ in range(20):
     ch.run(X, 80, n_dev, Y, 3, H_out=H)
 e1.record(); torch.cuda.synchronize()
 print('chain fwd 43000 rows: %.1f us' % (e0.elapsed_time(e1) / 20 * 1e3))
+
+
+# ------------------------------------------------------------------ full fwd + bwd through FlatMLP (tensor-core path)
+import torch.nn as nn
+from voxurf_b200.mlp import FlatMLP
+
+
+def mk(d_in, width=192, depth=4):
+    return nn.Sequential(nn.Linear(d_in, width), nn.ReLU(inplace=True),
+                         *[nn.Sequential(nn.Linear(width, width), nn.ReLU(inplace=True)) for _ in range(depth - 2)],
+                         nn.Linear(width, 3)).to(dev)
+
+
+for d_in, ld, cap, n_rows in [(79, 80, 2048, 1999), (54, 64, 61440, 43001)]:
+    torch.manual_seed(1)
+    net = mk(d_in)
+    ref = mk(d_in).double()
+    ref.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    f = FlatMLP(net, ld, d_in, tensor_core=True)
+    f.alloc(cap)
+    X = torch.zeros(cap, ld, device=dev); X[:, :d_in] = torch.randn(cap, d_in, device=dev)
+    out = torch.zeros(cap, 3, device=dev); dX = torch.zeros(cap, ld, device=dev)
+    n_dev = torch.tensor([n_rows], dtype=torch.int32, device=dev)
+    d_out = torch.zeros(cap, 3, device=dev); d_out[:n_rows] = torch.randn(n_rows, 3, device=dev) * 1e-3
+    f.forward(X, out, keep_activations=True, n_rows_dev=n_dev)
+    f.backward(d_out, dX)
+    torch.cuda.synchronize()
+    Xr = X[:n_rows, :d_in].double().requires_grad_(True)
+    yr = ref(Xr)
+    yr.backward(d_out[:n_rows].double())
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+    print(f'net {d_in}: fwd {rel(out[:n_rows], yr):.2e}  dX {rel(dX[:n_rows, :d_in], Xr.grad):.2e}', end='')
+    for l, lr in zip(f.linears, [m for m in ref.modules() if isinstance(m, nn.Linear)]):
+        print(f'  dW {rel(l.weight.grad, lr.weight.grad):.2e} db {rel(l.bias.grad, lr.bias.grad):.2e}', end='')
+    print()
+    for _ in range(3):
+        f.forward(X, out, True, n_dev); f.backward(d_out, dX)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(10):
+        f.forward(X, out, True, n_dev)
+    e1.record()
+    for _ in range(10):
+        f.backward(d_out, dX)
+    e2.record(); torch.cuda.synchronize()
+    print(f'   fwd {e0.elapsed_time(e1) * 100:.0f} us, bwd {e1.elapsed_time(e2) * 100:.0f} us  ({n_rows} rows)')

@@ -171,8 +171,10 @@ struct MlpLayer {
   const float* W_hi;   // [Np][Kp]
   const float* W_lo;
   const float* bias;   // [N] or nullptr
-  float* H;            // [cap][ldh] activation output of this layer in HBM, or nullptr
+  float* H;            // [cap][ldh] activation output of this layer in HBM (row-major), or nullptr
   const float* mask;   // [cap][ldh]: multiply the output by (mask > 0) (ReLU backward), or nullptr
+  float* HT;           // [Np][ldt] the same output TRANSPOSED (feature-major; operand of the split-K weight-gradient GEMM)
+  const float* maskT;  // [Np][ldt] transposed mask
   int Kp, Np, N, ldh, relu;
 };
 struct MlpChain {
@@ -205,7 +207,7 @@ __device__ __forceinline__ void store_a8(MlpSmem& s, uint32_t tmem_a_lane, int r
 
 __global__ void __launch_bounds__(MLP_ROWS, 1)
 k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __restrict__ n_rows_dev, int capacity, MlpChain ch,
-            float* __restrict__ Y, int ldy, int n_out) {
+            float* __restrict__ Y, int ldy, int n_out, float* __restrict__ XT, int ldt) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   MlpSmem& s = *reinterpret_cast<MlpSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -249,6 +251,10 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
             for (int j = 0; j < 8; ++j)
               if (c0 + j < K0) v[j] = __ldg(src + c0 + j);
           }
+        }
+        if (XT && row < ldt) {   // coalesced: consecutive threads = consecutive rows of one feature line
+#pragma unroll
+          for (int j = 0; j < 8; ++j) XT[(int64_t)(c0 + j) * ldt + row] = v[j];
         }
         store_a8(s, lane_addr + MLP_TMEM_A, tid, c0, v);
       }
@@ -334,9 +340,18 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
               if (!(m4.w > 0.f)) v[4 * q + 3] = 0.f;
             }
           }
+          if (L.maskT && row < n_rows) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (!(__ldg(L.maskT + (int64_t)(c0 + j) * ldt + row) > 0.f)) v[j] = 0.f;
+          }
           if (row >= n_rows) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (L.HT && row < ldt) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) L.HT[(int64_t)(c0 + j) * ldt + row] = v[j];
           }
           if (L.H && row < n_rows) {
             float4* dst = reinterpret_cast<float4*>(L.H + (int64_t)row * L.ldh + c0);
@@ -376,22 +391,28 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
 }
 
 // Layers are described by two packed HOST arrays so the C ABI stays plain:
-//   ptrs_host[l*5 + {0..4}] = device addresses of W_hi, W_lo (prepared, [Np][Kp]), bias (or 0), H out (or 0), mask (or 0)
+//   ptrs_host[l*7 + {0..6}] = device addresses of W_hi, W_lo (prepared, [Np][Kp]), bias, H out, mask, HT out, maskT (0 = none)
 //   dims_host[l*5 + {0..4}] = Kp, Np, N, ldh, relu
-// X (capacity, ldx) with K0 valid columns; Y (capacity, ldy) receives the first n_out columns of the last layer.
+// X (capacity, ldx) with K0 valid columns; Y (capacity, ldy) receives the first n_out columns of the last layer;
+// XT (K0p, ldt) optionally receives the transposed input; all transposed buffers share the row stride ldt >= 128*ceil(capacity/128).
 VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, int capacity, int n_layers,
-                        const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, cudaStream_t st) {
+                        const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* XT, int ldt,
+                        cudaStream_t st) {
   VX_REQUIRE(n_layers >= 1 && n_layers <= MLP_MAX_LAYERS, "vx_mlp_chain", "1..4 layers");
   VX_REQUIRE(n_rows_dev != nullptr, "vx_mlp_chain", "n_rows_dev required");
   MlpChain ch;
   ch.n_layers = n_layers;
+  bool any_t = XT != nullptr;
   for (int l = 0; l < n_layers; ++l) {
     MlpLayer& L = ch.L[l];
-    L.W_hi = reinterpret_cast<const float*>(ptrs_host[l * 5 + 0]);
-    L.W_lo = reinterpret_cast<const float*>(ptrs_host[l * 5 + 1]);
-    L.bias = reinterpret_cast<const float*>(ptrs_host[l * 5 + 2]);
-    L.H = reinterpret_cast<float*>(ptrs_host[l * 5 + 3]);
-    L.mask = reinterpret_cast<const float*>(ptrs_host[l * 5 + 4]);
+    L.W_hi = reinterpret_cast<const float*>(ptrs_host[l * 7 + 0]);
+    L.W_lo = reinterpret_cast<const float*>(ptrs_host[l * 7 + 1]);
+    L.bias = reinterpret_cast<const float*>(ptrs_host[l * 7 + 2]);
+    L.H = reinterpret_cast<float*>(ptrs_host[l * 7 + 3]);
+    L.mask = reinterpret_cast<const float*>(ptrs_host[l * 7 + 4]);
+    L.HT = reinterpret_cast<float*>(ptrs_host[l * 7 + 5]);
+    L.maskT = reinterpret_cast<const float*>(ptrs_host[l * 7 + 6]);
+    any_t |= (L.HT != nullptr) || (L.maskT != nullptr);
     L.Kp = dims_host[l * 5 + 0]; L.Np = dims_host[l * 5 + 1]; L.N = dims_host[l * 5 + 2];
     L.ldh = dims_host[l * 5 + 3]; L.relu = dims_host[l * 5 + 4];
     VX_REQUIRE(L.Kp % 8 == 0 && L.Kp >= 8 && L.Kp <= MLP_MAXW && L.Np % 16 == 0 && L.Np >= 16 && L.Np <= MLP_MAXW,
@@ -402,6 +423,8 @@ VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, 
   }
   const int K0p = dims_host[0];
   VX_REQUIRE(K0 <= K0p && K0 <= ldx && n_out <= dims_host[(n_layers - 1) * 5 + 1], "vx_mlp_chain", "K0 / n_out");
+  const int tiles_cap = (capacity + MLP_ROWS - 1) / MLP_ROWS;
+  VX_REQUIRE(!any_t || ldt >= tiles_cap * MLP_ROWS, "vx_mlp_chain", "ldt must cover whole row tiles");
   static bool attr_set = false;
   const int smem = (int)sizeof(MlpSmem) + 1024;
   if (!attr_set) {
@@ -409,9 +432,176 @@ VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, 
     if (e != cudaSuccess) { vx_set_error("vx_mlp_chain", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  const int tiles_cap = (capacity + MLP_ROWS - 1) / MLP_ROWS;
   if (tiles_cap <= 0) return 0;
   const int blocks = min(tiles_cap, vx_num_sms());
-  k_mlp_chain<<<blocks, MLP_ROWS, smem, st>>>(X, ldx, K0, K0p, n_rows_dev, capacity, ch, Y, ldy, n_out);
+  k_mlp_chain<<<blocks, MLP_ROWS, smem, st>>>(X, ldx, K0, K0p, n_rows_dev, capacity, ch, Y, ldy, n_out, XT, ldt);
   return vx_check_launch("vx_mlp_chain");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split-K weight-gradient GEMM:  C[m][n] += sum_r At[m][r] * Bt[n][r]   (dW = dY^T H, db = dY^T 1)
+// At (M_out, ldt) and Bt (N_in, ldt) are the feature-major ("transposed") activations written by the chain
+// kernels; r runs over the MLP rows (K dimension of the MMA, ~43 k), split over the CTAs of blockIdx.x;
+// blockIdx.y selects the 128-row M tile.  Both operands are split hi/lo on the fly while being staged (thread-staged
+// loads: A hi -> TMEM, A lo / B hi / B lo -> K-major smem tiles, double buffered).  An extra virtual B row of
+// ones yields the bias gradient.  Partial results are added to C / c_bias with vector atomics.
+// ---------------------------------------------------------------------------------------------
+#define DW_KC 32                      // rows (K) per chunk
+#define DW_MAXN 208                   // N_in (<= 192) + 1 ones row, padded to 16
+
+struct __align__(16) DwSmem {
+  float A_lo[2][DW_KC / 4 * MLP_ROWS * 4];        // 2 x 16 KB
+  float B_hi[2][DW_KC / 4 * DW_MAXN * 4];         // 2 x 26 KB
+  float B_lo[2][DW_KC / 4 * DW_MAXN * 4];         // 2 x 26 KB
+  uint64_t bar_slot[2];
+  uint64_t bar_acc;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(MLP_ROWS, 1)
+k_mlp_dw(const float* __restrict__ At, int M_out, const float* __restrict__ Bt, int N_in, int ldt,
+         const int* __restrict__ n_rows_dev, int capacity, float* __restrict__ C, int ldc, float* __restrict__ c_bias) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  DwSmem& s = *reinterpret_cast<DwSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_rows = min(*n_rows_dev, capacity);
+  const int n_chunks = (n_rows + DW_KC - 1) / DW_KC;
+  const int m0 = blockIdx.y * MLP_ROWS;
+  const int Np = ((N_in + 1) + 15) / 16 * 16;     // + ones row
+  if (tid == 0) {
+    mbar_init(&s.bar_slot[0], 1); mbar_init(&s.bar_slot[1], 1); mbar_init(&s.bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&s.tmem_base, MLP_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t idesc = make_idesc_tf32(MLP_ROWS, Np);
+  uint32_t phase[2] = {0, 0};
+  uint32_t used = 0;
+  int it = 0;
+  const int m = m0 + tid;                          // this thread's A row (output feature) == TMEM lane
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+    const int slot = it & 1;
+    const int r0 = chunk * DW_KC;
+    // ---- global -> registers (issued before waiting on the slot, to overlap with the in-flight MMAs)
+    float a[DW_KC];
+    if (m < M_out) {
+      const float4* src = reinterpret_cast<const float4*>(At + (int64_t)m * ldt + r0);
+#pragma unroll
+      for (int q = 0; q < DW_KC / 4; ++q) {
+        const float4 x = __ldg(src + q);
+        a[4 * q] = x.x; a[4 * q + 1] = x.y; a[4 * q + 2] = x.z; a[4 * q + 3] = x.w;
+      }
+#pragma unroll
+      for (int j = 0; j < DW_KC; ++j)
+        if (r0 + j >= n_rows) a[j] = 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < DW_KC; ++j) a[j] = 0.f;
+    }
+    if (used & (1u << slot)) { mbar_wait(&s.bar_slot[slot], phase[slot]); phase[slot] ^= 1; used &= ~(1u << slot); }
+    // ---- A: hi -> TMEM columns [256 + slot*32, +32), lo -> smem
+#pragma unroll
+    for (int q = 0; q < DW_KC / 8; ++q) {
+      float hi[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hi[j] = tf32_hi(a[8 * q + j]);
+      tmem_st8(lane_addr + MLP_TMEM_A + slot * DW_KC + 8 * q, hi);
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        float4 lo;
+        lo.x = tf32_hi(a[8 * q + 4 * h2] - hi[4 * h2]); lo.y = tf32_hi(a[8 * q + 4 * h2 + 1] - hi[4 * h2 + 1]);
+        lo.z = tf32_hi(a[8 * q + 4 * h2 + 2] - hi[4 * h2 + 2]); lo.w = tf32_hi(a[8 * q + 4 * h2 + 3] - hi[4 * h2 + 3]);
+        reinterpret_cast<float4*>(s.A_lo[slot])[(2 * q + h2) * MLP_ROWS + tid] = lo;
+      }
+    }
+    // ---- B: rows n = tid, tid + 128 (< Np); row N_in is the virtual ones row (bias gradient)
+    for (int n = tid; n < Np; n += MLP_ROWS) {
+#pragma unroll
+      for (int q = 0; q < DW_KC / 4; ++q) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < N_in) x = __ldg(reinterpret_cast<const float4*>(Bt + (int64_t)n * ldt + r0) + q);
+        else if (n == N_in) x = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (r0 + 4 * q + 0 >= n_rows) x.x = 0.f;
+        if (r0 + 4 * q + 1 >= n_rows) x.y = 0.f;
+        if (r0 + 4 * q + 2 >= n_rows) x.z = 0.f;
+        if (r0 + 4 * q + 3 >= n_rows) x.w = 0.f;
+        const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+        const float4 lo = make_float4(tf32_hi(x.x - hi.x), tf32_hi(x.y - hi.y), tf32_hi(x.z - hi.z), tf32_hi(x.w - hi.w));
+        reinterpret_cast<float4*>(s.B_hi[slot])[q * Np + n] = hi;
+        reinterpret_cast<float4*>(s.B_lo[slot])[q * Np + n] = lo;
+      }
+    }
+    tmem_st_wait();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < DW_KC / 8; ++kk) {
+        const uint32_t a_tm = tmem + MLP_TMEM_A + slot * DW_KC + kk * 8;
+        const uint64_t da_lo = make_desc(smem_u32(s.A_lo[slot]) + (uint32_t)(kk * 2) * MLP_ROWS * 16, MLP_ROWS * 16, 128);
+        const uint32_t b_off = (uint32_t)(kk * 2) * Np * 16;
+        const uint64_t db_hi = make_desc(smem_u32(s.B_hi[slot]) + b_off, Np * 16, 128);
+        const uint64_t db_lo = make_desc(smem_u32(s.B_lo[slot]) + b_off, Np * 16, 128);
+        umma_tf32_ts(tmem, a_tm, db_hi, idesc, (it > 0) || (kk > 0));
+        umma_tf32_ts(tmem, a_tm, db_lo, idesc, 1);
+        umma_tf32_ss(tmem, da_lo, db_hi, idesc, 1);
+      }
+      umma_commit(&s.bar_slot[slot]);
+    }
+    used |= (1u << slot);
+  }
+  if (it > 0) {
+    if (tid == 0) umma_commit(&s.bar_acc);
+    mbar_wait(&s.bar_acc, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < Np; c0 += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + c0, v);   // warp-collective: executed by every thread, only the adds are predicated
+      if (m < M_out) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = c0 + 4 * q;
+          if (n + 3 < N_in && (ldc % 4 == 0)) {
+            atomicAdd(reinterpret_cast<float4*>(C + (int64_t)m * ldc + n), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (n + j < N_in) atomicAdd(C + (int64_t)m * ldc + n + j, v[4 * q + j]);
+              else if (n + j == N_in && c_bias) atomicAdd(c_bias + m, v[4 * q + j]);
+            }
+          }
+        }
+      }
+    }
+    for (int i = 0; i < 2; ++i)
+      if (used & (1u << i)) mbar_wait(&s.bar_slot[i], phase[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, MLP_TMEM_COLS);
+}
+
+VX_API int vx_mlp_dw(const float* At, int M_out, const float* Bt, int N_in, int ldt, const int* n_rows_dev, int capacity,
+                     float* C, int ldc, float* c_bias, cudaStream_t st) {
+  VX_REQUIRE(n_rows_dev != nullptr, "vx_mlp_dw", "n_rows_dev required");
+  VX_REQUIRE(M_out >= 1 && M_out <= 256 && N_in >= 1 && N_in + 1 <= DW_MAXN && ldt % 4 == 0, "vx_mlp_dw", "shape");
+  static bool attr_set = false;
+  const int smem = (int)sizeof(DwSmem) + 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_mlp_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { vx_set_error("vx_mlp_dw", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  const int m_tiles = (M_out + MLP_ROWS - 1) / MLP_ROWS;
+  const int chunks_cap = (capacity + DW_KC - 1) / DW_KC;
+  if (chunks_cap <= 0) return 0;
+  const int gx = max(1, min(vx_num_sms() / m_tiles, (chunks_cap + 7) / 8));
+  k_mlp_dw<<<dim3(gx, m_tiles), MLP_ROWS, smem, st>>>(At, M_out, Bt, N_in, ldt, n_rows_dev, capacity, C, ldc, c_bias);
+  return vx_check_launch("vx_mlp_dw");
 }

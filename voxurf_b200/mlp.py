@@ -45,25 +45,43 @@ class FlatMLP:
             self.W.append(W); self.b.append(b); self.dW.append(dW); self.db.append(db)
         self.H = None
         self.tensor_core = tensor_core
-        self.tc_fwd = None
+        self.tc_fwd = self.tc_bwd = None
         if tensor_core:
             n = len(self.W)
             self.tc_fwd = TensorCoreChain([dict(W=self.W[i], bias=self.b[i], relu=(i + 1 < n)) for i in range(n)])
+            # dX chain: dH_{l-1} = (dH_l W_l) * (H_{l-1} > 0), i.e. the same kernel on the transposed weights, last layer first
+            self.tc_bwd = TensorCoreChain([dict(W=self.W[i], bias=None, relu=False) for i in range(n - 1, -1, -1)], transpose=True)
 
     def alloc(self, cap):
         dev = self.flat.device
         self.cap = cap
+        if self.tensor_core:
+            # feature-major activations / gradients for the split-K weight-gradient GEMM (row stride = whole tiles)
+            self.ldt = (cap + 127) // 128 * 128
+            z = lambda rows: torch.zeros(rows, self.ldt, dtype=torch.float32, device=dev)
+            self.XT = z(self.ld_in)
+            self.HT = [z(l.out_features) for l in self.linears[:-1]]
+            self.dHT = [z(l.out_features) for l in self.linears[:-1]]
+            self.dYT = z(8)
+            self.H = self.dH = []
+            return
         self.H = [torch.empty(cap, l.out_features, dtype=torch.float32, device=dev) for l in self.linears[:-1]]
         self.dH = [torch.empty_like(h) for h in self.H]
 
     def forward(self, X, out, keep_activations=True, n_rows_dev=None):
         """X (cap, ld_in) -> out (cap, 3).  Hidden activations stay in self.H for the backward pass."""
-        if self.H is None or self.H[0].shape[0] != X.shape[0]:
+        if self.H is None or getattr(self, 'cap', None) != X.shape[0]:
             self.alloc(X.shape[0])
         self._X = X
-        if self.tensor_core and n_rows_dev is not None:
+        if self.tensor_core:
+            assert n_rows_dev is not None
+            self._n = n_rows_dev
             self.tc_fwd.prepare()   # the optimizer changed the weights since the last step
-            self.tc_fwd.run(X, self.ld_in, n_rows_dev, out, out.shape[1], H_out=self.H if keep_activations else None)
+            if keep_activations:
+                self.tc_bwd.prepare()
+                self.tc_fwd.run(X, self.ld_in, n_rows_dev, out, out.shape[1], HT_out=self.HT, XT=self.XT, ldt=self.ldt)
+            else:
+                self.tc_fwd.run(X, self.ld_in, n_rows_dev, out, out.shape[1])
             return out
         h = X
         for i in range(len(self.linears) - 1):
@@ -77,6 +95,17 @@ class FlatMLP:
     def backward(self, d_out, dX):
         """d_out (cap, 3) -> dX (cap, ld_in); accumulates weight / bias gradients into the flat gradient buffer."""
         n = len(self.linears)
+        if self.tensor_core:
+            # dX chain (one launch): chain layer j <-> network layer n-1-j; hidden gradients land feature-major in dHT
+            rev = list(range(n - 2, -1, -1))
+            self.tc_bwd.run(d_out, d_out.shape[1], self._n, dX, dX.shape[1], HT_out=[self.dHT[i] for i in rev],
+                            masksT=[self.HT[i] for i in rev], XT=self.dYT, ldt=self.ldt)
+            for i in range(n):   # dW_i = dY_i^T H_{i-1}, db_i = dY_i^T 1
+                At = self.dYT if i == n - 1 else self.dHT[i]
+                Bt = self.XT if i == 0 else self.HT[i - 1]
+                self.tc_fwd._call('vx_mlp_dw', At, self.linears[i].out_features, Bt, self.dW[i].shape[1], self.ldt, self._n,
+                                  self.cap, self.dW[i], self.dW[i].stride(0), self.db[i])
+            return dX
         dy = d_out
         for i in range(n - 1, -1, -1):
             h_in = self.H[i - 1] if i > 0 else self._X
@@ -129,16 +158,17 @@ class TensorCoreChain:
             self._call('vx_mlp_prep', W, self.N[i], self.K[i], W.stride(0), self.Np[i], self.Kp[i], int(self.transpose),
                        self.W_hi[i], self.W_lo[i])
 
-    def run(self, X, k0, n_rows_dev, Y, n_out, H_out=None, masks=None):
-        """X (cap, ldx) with k0 valid columns -> Y (cap, ldy)[:, :n_out].  H_out[l] / masks[l]: optional (cap, ldh) tensors."""
+    def run(self, X, k0, n_rows_dev, Y, n_out, H_out=None, masks=None, HT_out=None, masksT=None, XT=None, ldt=0):
+        """X (cap, ldx) with k0 valid columns -> Y (cap, ldy)[:, :n_out].  Optional per-layer tensors:
+        H_out / masks (cap, ldh) row-major; HT_out / masksT (Np, ldt) feature-major; XT (K0p, ldt)."""
         n = len(self.layers)
         ptrs, dims = [], []
+        pick = lambda lst, i: lst[i] if (lst is not None and i < len(lst)) else None
+        addr = lambda t: t.data_ptr() if t is not None else 0
         for i, L in enumerate(self.layers):
-            h = H_out[i] if H_out is not None and i < len(H_out) else None
-            mk = masks[i] if masks is not None and i < len(masks) else None
+            h, mk = pick(H_out, i), pick(masks, i)
             ldh = (h if h is not None else mk).stride(0) if (h is not None or mk is not None) else 0
-            b = L.get('bias')
-            ptrs += [self.W_hi[i].data_ptr(), self.W_lo[i].data_ptr(), b.data_ptr() if b is not None else 0,
-                     h.data_ptr() if h is not None else 0, mk.data_ptr() if mk is not None else 0]
+            ptrs += [self.W_hi[i].data_ptr(), self.W_lo[i].data_ptr(), addr(L.get('bias')), addr(h), addr(mk),
+                     addr(pick(HT_out, i)), addr(pick(masksT, i))]
             dims += [self.Kp[i], self.Np[i], self.N[i], ldh, int(bool(L.get('relu', False)))]
-        self._call('vx_mlp_chain', X, X.stride(0), k0, n_rows_dev, X.shape[0], n, ptrs, dims, Y, Y.stride(0), n_out)
+        self._call('vx_mlp_chain', X, X.stride(0), k0, n_rows_dev, X.shape[0], n, ptrs, dims, Y, Y.stride(0), n_out, XT, ldt)
