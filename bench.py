@@ -258,7 +258,7 @@ def main():
         fused = FusedFineStep(model, args.rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank)
         fused.calibrate(*dev_pool[0][:3], global_step=START_STEP, headroom=1.35)
         if sync is not None:
-            sync = parallel.GradSync(model, world, extra=[fused.mlp1.flat, fused.mlp2.flat], only_large=True)
+            sync = parallel.GradSync(model, world, tensors=[model.sdf.grid, model.k0.grid, fused.mlp1.flat, fused.mlp2.flat])
 
         class _T:   # same surface as Trainer for the loops below
             optimizer = fused

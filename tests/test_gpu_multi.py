@@ -1,0 +1,88 @@
+"""GPU (needs >= 2 devices; skipped otherwise): ray-sharded data parallelism of the fused step over NCCL.
+N-GPU gradients after the exchange == 1-GPU gradients on the concatenated batch, and so are the parameters after
+the TV + Adam step."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+RK = dict(near=0.3, far=6.0, bg=0.0, stepsize=0.5)
+
+
+def _build(dev):
+    from voxurf_b200 import synthetic as S
+    from tests.helpers import product_fine_model
+    sc = S.make_fine_scene(40, 6, 64, seed=9)
+    return product_fine_model(sc, device=dev, k0_channels_last=True)
+
+
+def _batches(world, n_rays):
+    from voxurf_b200 import synthetic as S
+    from tests.helpers import T
+    out = []
+    for r in range(world):
+        o, d, v = (T(x) for x in S.make_rays(n_rays, seed=50 + r))
+        out.append((o, d, v, T(S.make_target(v.numpy(), seed=r))))
+    return out
+
+
+def _worker(rank, world, port, n_rays, step, ret):
+    import torch.distributed as dist
+    from voxurf_b200.fused import FusedFineStep
+    from voxurf_b200.parallel import GradSync
+    from voxurf_b200.trainer import FINE_TRAIN
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    m = _build(dev)
+    fs = FusedFineStep(m, n_rays, FINE_TRAIN, RK, row_capacity=8192, world=world, rank=rank)
+    sync = GradSync(m, world, tensors=[m.sdf.grid, m.k0.grid, fs.mlp1.flat, fs.mlp2.flat])
+    b = [t.to(dev) for t in _batches(world, n_rays)[rank]]
+    fs.forward_backward(*b, step)
+    sync()
+    grads = {'sdf': m.sdf.grid.grad.clone().cpu(), 'k0': m.k0.grid.grad.contiguous().clone().cpu(),
+             'mlp1': fs.mlp1.flat.grad.clone().cpu(), 'mlp2': fs.mlp2.flat.grad.clone().cpu()}
+    fs.regularise(step)
+    fs.optimizer_step()
+    params = {'sdf': m.sdf.grid.detach().cpu(), 'k0': m.k0.grid.detach().contiguous().cpu(), 'mlp1': fs.mlp1.flat.detach().cpu()}
+    fs.counts()
+    ret[rank] = (grads, params)
+    dist.destroy_process_group()
+
+
+def test_two_gpu_gradients_equal_single_gpu_on_concatenated_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from voxurf_b200.fused import FusedFineStep
+    from voxurf_b200.trainer import FINE_TRAIN
+    world, n_rays, step = 2, 512, 15003
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, n_rays, step, ret), nprocs=world, join=True)
+    # single GPU, concatenated batch
+    dev = torch.device('cuda', 0)
+    m = _build(dev)
+    fs = FusedFineStep(m, n_rays * world, FINE_TRAIN, RK, row_capacity=16384)
+    bs = _batches(world, n_rays)
+    cat = [torch.cat([b[i] for b in bs]).to(dev) for i in range(4)]
+    fs.forward_backward(*cat, step)
+    ref = {'sdf': m.sdf.grid.grad.clone().cpu(), 'k0': m.k0.grid.grad.contiguous().clone().cpu(),
+           'mlp1': fs.mlp1.flat.grad.clone().cpu(), 'mlp2': fs.mlp2.flat.grad.clone().cpu()}
+    fs.regularise(step)
+    fs.optimizer_step()
+    refp = {'sdf': m.sdf.grid.detach().cpu(), 'k0': m.k0.grid.detach().contiguous().cpu(), 'mlp1': fs.mlp1.flat.detach().cpu()}
+    for r in range(world):
+        grads, params = ret[r]
+        for k in ref:
+            scale = float(ref[k].abs().max())
+            np.testing.assert_allclose(grads[k].numpy(), ref[k].numpy(), rtol=1e-4, atol=1e-4 * scale, err_msg=f'rank {r} grad {k}')
+        for k, lr in (('sdf', 5e-3), ('k0', 1e-1), ('mlp1', 3e-3)):
+            np.testing.assert_allclose(params[k].numpy(), refp[k].numpy(), rtol=1e-4, atol=2e-2 * lr, err_msg=f'rank {r} param {k}')
+    # both ranks hold identical replicas after the step
+    for k in ('sdf', 'k0', 'mlp1'):
+        assert torch.equal(ret[0][1][k], ret[1][1][k]), k

@@ -29,13 +29,16 @@ def _dense(t):
 class GradSync:
     """Averages .grad of every trainable parameter across ranks, in place."""
 
-    def __init__(self, model, world, small_numel=1 << 20, group=None, extra=(), only_large=False):
-        """extra: additional tensors with .grad (e.g. the flat MLP buffers of the fused step); only_large: skip the
-        per-module small parameters (they are views of the flat buffers then)."""
+    def __init__(self, model, world, small_numel=1 << 20, group=None, tensors=None):
+        """tensors: explicit list of tensors whose .grad is exchanged one collective each (the fused step passes its
+        grids and its flat per-network MLP buffers); default: every trainable parameter of `model`, small ones bucketed."""
         self.world, self.group = world, group
-        params = [p for p in model.parameters() if p.requires_grad]
-        self.large = [p for p in params if p.numel() >= small_numel] + list(extra)
-        self.small = [] if only_large else [p for p in params if p.numel() < small_numel]
+        if tensors is not None:
+            self.large, self.small = list(tensors), []
+        else:
+            params = [p for p in model.parameters() if p.requires_grad]
+            self.large = [p for p in params if p.numel() >= small_numel]
+            self.small = [p for p in params if p.numel() < small_numel]
         self._flat = None
 
     def __call__(self, model=None):
