@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--cpu-rays', type=int, default=256, help='ray sample of the CPU baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--path', default='fused', choices=['fused', 'dropin'], help='fused = sync-free FusedFineStep; dropin = Voxurf.forward + autograd')
+    ap.add_argument('--dense-k0-allreduce', action='store_true', help='multi-GPU: all-reduce the dense k0 gradient grid instead of exchanging rows')
     ap.add_argument('--phases', action='store_true', help='also print a per-phase CUDA-event breakdown to stderr')
     return ap.parse_args()
 
@@ -257,8 +258,8 @@ def main():
         from voxurf_b200.fused import FusedFineStep
         fused = FusedFineStep(model, args.rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank)
         fused.calibrate(*dev_pool[0][:3], global_step=START_STEP, headroom=1.35)
-        if sync is not None:
-            sync = parallel.GradSync(model, world, tensors=[model.sdf.grid, model.k0.grid, fused.mlp1.flat, fused.mlp2.flat])
+        sync = None   # FusedFineStep.grad_sync(): dense all-reduce for sdf + MLPs, row exchange for k0 (or --dense-k0-allreduce)
+        fused.sparse_k0_exchange = not args.dense_k0_allreduce
 
         class _T:   # same surface as Trainer for the loops below
             optimizer = fused

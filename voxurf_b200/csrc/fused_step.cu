@@ -478,7 +478,7 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
       bool any = false;
 #pragma unroll
       for (int c = 0; c < kC; ++c) { go[c] = g2[c]; any |= go[c] != 0.f; }
-      if (any) {
+      if (any && k0_grad != nullptr) {
         float ix, iy, iz;
         point_to_index(gk, p[0], p[1], p[2], ix, iy, iz);
         VxTap t;
@@ -659,6 +659,34 @@ VX_API int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min
   k_alpha_sdf_bwd<<<vx_num_sms() * 8, 256, 0, st>>>(g, pts, n_dev, viewdirs, sdf, grad, keep, d_alpha, d_sdf_s, d_grad_s,
                                                     voxel_size, dist, inv_s, sdf_grad);
   return vx_check_launch("vx_fused_alpha_sdf_backward");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ray-sharded data parallelism: instead of all-reducing the dense k0 gradient grid (0.8 GB at 256^3 x 12), every
+// rank exports its MLP rows' k0 feature gradients -- (xyz, dk0[C]) per row, ~3 MB -- the ranks all-gather them and each
+// replays the trilinear scatter of ALL ranks' rows into its own gradient grid (vx_grid_gather_backward).
+// `scale` = 1 / world (the global-batch gradient is the mean of the per-rank gradients).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_export_k0_rows(VxPts pts, const int* __restrict__ idx4, const int* __restrict__ n_rows_dev, int capacity,
+                                 const float* __restrict__ dX2, int ld2, int C, float scale, float* __restrict__ xyz_out,
+                                 float* __restrict__ g_out) {
+  const int n = min(*n_rows_dev, capacity);
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < capacity; row += gridDim.x * blockDim.x) {
+    float p[3] = {0.f, 0.f, 0.f};
+    if (row < n) vx_load_pt(pts, idx4[row], p[0], p[1], p[2]);
+    xyz_out[3 * row] = p[0]; xyz_out[3 * row + 1] = p[1]; xyz_out[3 * row + 2] = p[2];
+    for (int c = 0; c < C; ++c) g_out[(int64_t)row * C + c] = (row < n) ? dX2[(int64_t)row * ld2 + c] * scale : 0.f;
+  }
+}
+
+VX_API int vx_fused_export_k0_rows(const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
+                                   float stepdist, const int* idx4, const int* n_rows_dev, int capacity, const float* dX2,
+                                   int ld2, int C, float scale, float* xyz_out, float* g_out, cudaStream_t st) {
+  if (capacity <= 0) return 0;
+  const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
+  k_export_k0_rows<<<min(vx_blocks(capacity, 256), vx_num_sms() * 8), 256, 0, st>>>(pts, idx4, n_rows_dev, capacity, dX2, ld2, C,
+                                                                                    scale, xyz_out, g_out);
+  return vx_check_launch("vx_fused_export_k0_rows");
 }
 
 // small helpers for the host orchestration ----------------------------------------------------

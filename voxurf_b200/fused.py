@@ -35,7 +35,7 @@ from .optim import _storage
 
 class FusedFineStep:
     def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0,
-                 tensor_core=True):
+                 tensor_core=True, sparse_k0_exchange=True):
         if model.k0_dim not in (6, 12):
             raise NotImplementedError('fused step: k0 channels must be 6 or 12')
         if model.k_center_sdf or not model.center_sdf or not model.k_res:
@@ -45,6 +45,7 @@ class FusedFineStep:
         self.rk = dict(render_kwargs or {})
         self.world, self.rank = world, rank
         self.tensor_core = tensor_core
+        self.sparse_k0_exchange = sparse_k0_exchange
         dev = model.sdf.grid.device
         self.dev = dev
         m = model
@@ -208,9 +209,13 @@ class FusedFineStep:
         self.mlp2.backward(self.d_kout, self.dX2)
         self.mlp1.backward(self.d_logit1, self.dX1)
         grad_target = self.d_smoothed if m.smooth_sdf else self.sdf_grad
+        sparse_dp = self.world > 1 and self.sparse_k0_exchange
         call('vx_fused_row_backward', self._sdf_grid, X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(), self.idx4, n4,
              self.cap4, m._voxel_size_host, int(m.use_grad_norm), self.P, self.Vp, self.P2, self.V2, self.disp, self.L,
-             self.ld1, self.ld2, self.dX1, self.dX2, self.d_sdf_s, self.d_grad_s, grad_target, _storage(self.k0_grad))
+             self.ld1, self.ld2, self.dX1, self.dX2, self.d_sdf_s, self.d_grad_s, grad_target,
+             None if sparse_dp else _storage(self.k0_grad))
+        if sparse_dp:
+            self._start_k0_exchange(n4)
         thres = float(m.fast_color_thres)
         call('vx_alpha2weight_seg_backward', self.alpha, self.weight, self.T, self.keep if thres > 0 else None,
              self.alphainv_last, self.keep_off, self.i_end, N, self.d_w, self.d_last, self.d_alpha)
@@ -221,6 +226,38 @@ class FusedFineStep:
                  self.sdf_grad)
             self.d_smoothed.zero_()
         return self.loss
+
+    # ------------------------------------------------------------------ data-parallel exchange
+    def _start_k0_exchange(self, n4):
+        """k0 gradient as rows: export (xyz, dk0 / world) of this rank's MLP rows and all-gather them asynchronously;
+        the scatter of every rank's rows happens in grad_sync()."""
+        import torch.distributed as dist
+        W, cap, C = self.world, self.cap4, self.C
+        if getattr(self, '_k0_send', None) is None or self._k0_send[0].shape[0] != cap:
+            f32 = lambda *s_: torch.empty(*s_, dtype=torch.float32, device=self.dev)
+            self._k0_send = (f32(cap, 3), f32(cap, C))
+            self._k0_recv = (f32(W * cap, 3), f32(W * cap, C))
+        call('vx_fused_export_k0_rows', *self._pts(), self.idx4, n4, cap, self.dX2, self.ld2, C, 1.0 / W, *self._k0_send)
+        self._k0_work = [dist.all_gather_into_tensor(self._k0_recv[i], self._k0_send[i], async_op=True) for i in range(2)]
+
+    def grad_sync(self):
+        """Average gradients over ranks: dense NCCL all-reduce (AVG) for the sdf grid (67 MB at 256^3) and the two flat
+        MLP buffers; the k0 grid (0.8 GB dense) is exchanged as ~3 MB of rows per rank and re-scattered locally."""
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        m = self.m
+        works = [dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True) for t in (self.sdf_grad, self.mlp1.flat.grad, self.mlp2.flat.grad)]
+        if self.sparse_k0_exchange:
+            for w in self._k0_work:
+                w.wait()
+            xyz, g = self._k0_recv
+            call('vx_grid_gather_backward', self.X, self.Y, self.Z, self.C, self.k0_cl, m._min_host, m._max_host, xyz, None, None,
+                 None, None, 0.0, None, xyz.shape[0], g, _storage(self.k0_grad))
+        else:
+            works.append(dist.all_reduce(_storage(self.k0_grad), op=dist.ReduceOp.AVG, async_op=True))
+        for w in works:
+            w.wait()
 
     def is_tv_iter(self, global_step):
         c = self.cfg
@@ -280,6 +317,8 @@ class FusedFineStep:
         loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
         if grad_sync is not None:
             grad_sync()
+        elif self.world > 1:
+            self.grad_sync()
         self.regularise(global_step)
         self.optimizer_step()
         return loss
