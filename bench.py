@@ -328,10 +328,12 @@ def main():
         value = total_rays / (ms * 1e-3)
         V = G ** 3
         peak, peak_src = measured_peak()
-        adam_bytes = 28 * V * C   # read p,g,m,v + write p,m,v (the fused zero-fill of grad is the "1 grad write")
+        # SURVEY.md 8d counts 7 Adam passes (read p,g,m,v; write p,m,v) + 1 gradient zero-fill pass per element; this kernel
+        # does all 8 in one pass -> 32 B/element.  profiles/r01c: dram traffic 6.383 GB per launch vs 6.442 GB algorithmic.
+        adam_bytes = 32 * V * C
         adam_t = float(np.mean(adam_ms)) if adam_ms else None
-        roof = {'bound': 'hbm', 'kernel': 'k_adam (k0 grid, %d x %d^3 fp32)' % (C, G), 'achieved': (adam_bytes / (adam_t * 1e-3) / 1e9) if adam_t else None,
-                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'traffic': None, 'ms_per_launch': adam_t,
+        roof = {'bound': 'hbm', 'kernel': 'k_adam (k0 grid, %d x %d^3 fp32; Adam + fused grad zero-fill, 32 B/element)' % (C, G), 'achieved': (adam_bytes / (adam_t * 1e-3) / 1e9) if adam_t else None,
+                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'traffic': (6.383e9 if (C == 12 and G == 256) else None), 'ms_per_launch': adam_t,
                 'algorithmic_bytes_per_launch': adam_bytes, 'share_of_step': (adam_t / (ms / args.steps)) if adam_t else None}
         roof['frac'] = roof['achieved'] / peak if roof['achieved'] else None
         if fused is not None:

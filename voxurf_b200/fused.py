@@ -240,14 +240,14 @@ class FusedFineStep:
         call('vx_fused_export_k0_rows', *self._pts(), self.idx4, n4, cap, self.dX2, self.ld2, C, 1.0 / W, *self._k0_send)
         self._k0_work = [dist.all_gather_into_tensor(self._k0_recv[i], self._k0_send[i], async_op=True) for i in range(2)]
 
-    def grad_sync(self):
-        """Average gradients over ranks: dense NCCL all-reduce (AVG) for the sdf grid (67 MB at 256^3) and the two flat
-        MLP buffers; the k0 grid (0.8 GB dense) is exchanged as ~3 MB of rows per rank and re-scattered locally."""
-        if self.world <= 1:
-            return
+    def _sync_begin(self):
+        import torch.distributed as dist
+        self._works = [dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True)
+                       for t in (self.sdf_grad, self.mlp1.flat.grad, self.mlp2.flat.grad)]
+
+    def _sync_k0(self):
         import torch.distributed as dist
         m = self.m
-        works = [dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True) for t in (self.sdf_grad, self.mlp1.flat.grad, self.mlp2.flat.grad)]
         if self.sparse_k0_exchange:
             for w in self._k0_work:
                 w.wait()
@@ -255,9 +255,20 @@ class FusedFineStep:
             call('vx_grid_gather_backward', self.X, self.Y, self.Z, self.C, self.k0_cl, m._min_host, m._max_host, xyz, None, None,
                  None, None, 0.0, None, xyz.shape[0], g, _storage(self.k0_grad))
         else:
-            works.append(dist.all_reduce(_storage(self.k0_grad), op=dist.ReduceOp.AVG, async_op=True))
-        for w in works:
+            dist.all_reduce(_storage(self.k0_grad), op=dist.ReduceOp.AVG)
+
+    def _sync_end(self):
+        for w in self._works:
             w.wait()
+
+    def grad_sync(self):
+        """Average gradients over ranks: dense NCCL all-reduce (AVG) for the sdf grid (67 MB at 256^3) and the two flat
+        MLP buffers; the k0 grid (0.8 GB dense) is exchanged as ~3 MB of rows per rank and re-scattered locally."""
+        if self.world <= 1:
+            return
+        self._sync_begin()
+        self._sync_k0()
+        self._sync_end()
 
     def is_tv_iter(self, global_step):
         c = self.cfg
@@ -290,12 +301,16 @@ class FusedFineStep:
                  int(global_step < c['tv_dense_before']), X, Y, Z, m.sdf.grid.numel())
 
     @torch.no_grad()
-    def optimizer_step(self):
-        """lib/utils.py:83-199 with betas (0.9, 0.99), eps 1e-8 (lib/utils.py:229); grads are zeroed in the same pass."""
-        self.adam_steps += 1
+    def optimizer_step(self, only=None, advance=True):
+        """lib/utils.py:83-199 with betas (0.9, 0.99), eps 1e-8 (lib/utils.py:229); grads are zeroed in the same pass.
+        only: restrict to these group names (the multi-GPU step updates k0 while the sdf all-reduce is in flight)."""
+        if advance:
+            self.adam_steps += 1
         step, beta1, beta2, eps = self.adam_steps, 0.9, 0.99, 1e-8
         bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
         for name, params, _ in self.groups:
+            if only is not None and name not in only:
+                continue
             lr = self.lr[name]
             for p in params:
                 st = self.adam_state.get(id(p))
@@ -315,10 +330,17 @@ class FusedFineStep:
     def step(self, rays_o, rays_d, viewdirs, target, global_step, grad_sync=None):
         """One training iteration (run.py:600-659).  grad_sync: optional callable run between backward and TV/Adam."""
         loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
+        if grad_sync is None and self.world > 1:
+            # overlap: the sdf / MLP all-reduces run on the NCCL stream while k0 is re-scattered and updated
+            self._sync_begin()
+            self._sync_k0()
+            self.optimizer_step(only=('k0',))
+            self._sync_end()
+            self.regularise(global_step)
+            self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet'), advance=False)
+            return loss
         if grad_sync is not None:
             grad_sync()
-        elif self.world > 1:
-            self.grad_sync()
         self.regularise(global_step)
         self.optimizer_step()
         return loss
