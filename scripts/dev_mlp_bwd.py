@@ -38,20 +38,10 @@ for d_in, ld, cap, n_rows in [(79, 80, 2048, 1999), (54, 64, 2048, 1999), (79, 8
         acts.append(z)
     acts[-1].backward(d_out[:n_rows].double())
     msg = f'd_in {d_in} cap {cap} rows {n_rows}: fwd {rel(out[:n_rows], acts[-1]):.1e}'
+    un = lambda im, F: (im[0] + im[1]).view(-1, F, 4).permute(0, 2, 1).reshape(-1, F)[:n_rows]
     for i in range(3):
-        msg += f' HT{i} {rel(f.HT[i][:, :n_rows].t(), acts[i + 1]):.1e} dHT{i} {rel(f.dHT[i][:, :n_rows].t(), acts[i + 1].grad * (acts[i + 1] > 0)):.1e}'
+        msg += f' H{i} {rel(un(f.H_img[i], 192), acts[i + 1]):.1e} dH{i} {rel(un(f.dH_img[i], 192), acts[i + 1].grad * (acts[i + 1] > 0)):.1e}'
     msg += f' dX {rel(dX[:n_rows, :d_in], h.grad):.1e}'
     for l, lr in zip(f.linears, lins):
         msg += f' dW {rel(l.weight.grad, lr.weight.grad):.1e}'
     print(msg)
-    if cap == 20000:
-        got = f.dHT[2][:, :n_rows].t().double(); want = acts[3].grad * (acts[3] > 0)
-        bad = ((got - want).abs() > 1e-4 * want.abs().max())
-        rows = bad.any(1).nonzero().flatten()
-        print('  bad rows:', rows.numel(), rows[:5].tolist(), rows[-5:].tolist(), 'bad cols in first bad row:', bad[rows[0]].nonzero().flatten()[:20].tolist() if rows.numel() else None)
-        r = rows[0].item()
-        print('  got', got[r, :6].tolist()); print('  want', want[r, :6].tolist())
-        # is "got" equal to the unmasked product or to another row's values?
-        unmasked = (d_out[:n_rows].double() @ lins[3].weight)
-        print('  unmasked', unmasked[r, :6].tolist())
-        print('  mask row', (acts[3][r, :6] > 0).tolist(), ' HT2 row', f.HT[2][:6, r].tolist())

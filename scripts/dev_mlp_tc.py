@@ -18,10 +18,12 @@ def run_case(dims, cap, n_rows, k0_valid=None, relu=True):
     X = torch.zeros(cap, ldx, device=dev)
     X[:, :dims[0]] = torch.randn(cap, dims[0], device=dev)
     Y = torch.full((cap, dims[-1]), float('nan'), device=dev)
-    H = [torch.full((cap, dims[i + 1]), float('nan'), device=dev) for i in range(len(dims) - 2)]
+    R = (cap + 127) // 128 * 128
+    imgs = [(torch.zeros(R * dims[i + 1], device=dev), torch.zeros(R * dims[i + 1], device=dev)) for i in range(len(dims) - 2)]
     n_dev = torch.tensor([n_rows], dtype=torch.int32, device=dev)
-    ch.run(X, dims[0], n_dev, Y, dims[-1], H_out=H)
+    ch.run(X, dims[0], n_dev, Y, dims[-1], imgs=imgs)
     torch.cuda.synchronize()
+    H = [(a + b).view(R // 4, dims[i + 1], 4).permute(0, 2, 1).reshape(R, dims[i + 1]) for i, (a, b) in enumerate(imgs)]
     h = X[:n_rows, :dims[0]].double()
     ok = True
     for i, (W, b) in enumerate(zip(Ws, bs)):
@@ -52,15 +54,15 @@ bs = [torch.randn(dims[i + 1], device=dev) * 0.1 for i in range(4)]
 ch = TensorCoreChain([dict(W=W, bias=b, relu=i < 3) for i, (W, b) in enumerate(zip(Ws, bs))]); ch.prepare()
 cap = 61440
 X = torch.randn(cap, 80, device=dev); Y = torch.empty(cap, 3, device=dev)
-H = [torch.empty(cap, 192, device=dev) for _ in range(3)]
+H = [(torch.zeros(cap * 192, device=dev), torch.zeros(cap * 192, device=dev)) for _ in range(3)]
 n_dev = torch.tensor([43000], dtype=torch.int32, device=dev)
 for _ in range(3):
-    ch.run(X, 80, n_dev, Y, 3, H_out=H)
+    ch.run(X, 80, n_dev, Y, 3, imgs=H)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(20):
-    ch.run(X, 80, n_dev, Y, 3, H_out=H)
+    ch.run(X, 80, n_dev, Y, 3, imgs=H)
 e1.record(); torch.cuda.synchronize()
 print('chain fwd 43000 rows: %.1f us' % (e0.elapsed_time(e1) / 20 * 1e3))
 
