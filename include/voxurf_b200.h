@@ -250,17 +250,15 @@ int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min_host, 
 int vx_mlp_prep(const float* W, int N, int K, int ldw, int Np, int Kp, int transpose, float* W_hi, float* W_lo,
                 cudaStream_t stream);
 /* Y = chain of up to 4 layers y = act(x W^T + b) [* (mask > 0)] on 128-row tiles.  Packed host arrays (csrc/mlp_tc.cu):
- * ptrs_host[l*6..] = W_hi, W_lo, bias, img_hi out, img_lo out, mask image (device addresses, 0 = none);
- * dims_host[l*4..] = Kp, Np, N, relu.  The images (k = MLP row) are the operands of vx_mlp_dw. */
+ * ptrs_host[l*5..] = W_hi, W_lo, bias, row image out, mask row image (device addresses, 0 = none);
+ * dims_host[l*4..] = Kp, Np, N, relu.  Row images ACT(F) (raw fp32, r = MLP row) feed vx_mlp_dw. */
 int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, int capacity, int n_layers,
-                 const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* x_img_hi,
-                 float* x_img_lo, cudaStream_t stream);
-/* split-K weight gradient on the images: C[m][n] += sum_r A[r][m] B[r][n]  (r < *n_rows_dev, m < M_out, n < N_in) */
-int vx_mlp_dw(const float* A_hi, const float* A_lo, int FA, int M_out, const float* B_hi, const float* B_lo, int FB,
-              int N_in, const int* n_rows_dev, int capacity, float* C, int ldc, cudaStream_t stream);
-/* bias gradient: out[f] += sum_r (hi + lo)[r][f] */
-int vx_mlp_colsum(const float* img_hi, const float* img_lo, int F, int M_out, const int* n_rows_dev, int capacity,
-                  float* out, cudaStream_t stream);
+                 const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* x_img,
+                 cudaStream_t stream);
+/* split-K weight gradient on the row images: C[m][n] += sum_r A[r][m] B[r][n], c_bias[m] += sum_r A[r][m]
+ * (r < *n_rows_dev, m < M_out <= FA, n < N_in <= FB) */
+int vx_mlp_dw(const float* A_img, int FA, int M_out, const float* B_img, int FB, int N_in, const int* n_rows_dev,
+              int capacity, float* C, int ldc, float* c_bias, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

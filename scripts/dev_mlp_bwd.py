@@ -38,7 +38,7 @@ for d_in, ld, cap, n_rows in [(79, 80, 2048, 1999), (54, 64, 2048, 1999), (79, 8
         acts.append(z)
     acts[-1].backward(d_out[:n_rows].double())
     msg = f'd_in {d_in} cap {cap} rows {n_rows}: fwd {rel(out[:n_rows], acts[-1]):.1e}'
-    un = lambda im, F: (im[0] + im[1]).view(-1, F, 4).permute(0, 2, 1).reshape(-1, F)[:n_rows]
+    un = lambda im, F: im.view(-1, F // 4, 8, 4).permute(0, 2, 1, 3).reshape(-1, F)[:n_rows]
     for i in range(3):
         msg += f' H{i} {rel(un(f.H_img[i], 192), acts[i + 1]):.1e} dH{i} {rel(un(f.dH_img[i], 192), acts[i + 1].grad * (acts[i + 1] > 0)):.1e}'
     msg += f' dX {rel(dX[:n_rows, :d_in], h.grad):.1e}'

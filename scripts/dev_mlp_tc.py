@@ -19,11 +19,11 @@ def run_case(dims, cap, n_rows, k0_valid=None, relu=True):
     X[:, :dims[0]] = torch.randn(cap, dims[0], device=dev)
     Y = torch.full((cap, dims[-1]), float('nan'), device=dev)
     R = (cap + 127) // 128 * 128
-    imgs = [(torch.zeros(R * dims[i + 1], device=dev), torch.zeros(R * dims[i + 1], device=dev)) for i in range(len(dims) - 2)]
+    imgs = [torch.zeros(R * dims[i + 1], device=dev) for i in range(len(dims) - 2)]
     n_dev = torch.tensor([n_rows], dtype=torch.int32, device=dev)
     ch.run(X, dims[0], n_dev, Y, dims[-1], imgs=imgs)
     torch.cuda.synchronize()
-    H = [(a + b).view(R // 4, dims[i + 1], 4).permute(0, 2, 1).reshape(R, dims[i + 1]) for i, (a, b) in enumerate(imgs)]
+    H = [a.view(R // 8, dims[i + 1] // 4, 8, 4).permute(0, 2, 1, 3).reshape(R, dims[i + 1]) for i, a in enumerate(imgs)]
     h = X[:n_rows, :dims[0]].double()
     ok = True
     for i, (W, b) in enumerate(zip(Ws, bs)):
@@ -54,7 +54,7 @@ bs = [torch.randn(dims[i + 1], device=dev) * 0.1 for i in range(4)]
 ch = TensorCoreChain([dict(W=W, bias=b, relu=i < 3) for i, (W, b) in enumerate(zip(Ws, bs))]); ch.prepare()
 cap = 61440
 X = torch.randn(cap, 80, device=dev); Y = torch.empty(cap, 3, device=dev)
-H = [(torch.zeros(cap * 192, device=dev), torch.zeros(cap * 192, device=dev)) for _ in range(3)]
+H = [torch.zeros(cap * 192, device=dev) for _ in range(3)]
 n_dev = torch.tensor([43000], dtype=torch.int32, device=dev)
 for _ in range(3):
     ch.run(X, 80, n_dev, Y, 3, imgs=H)

@@ -142,6 +142,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // instruction descriptor: D fp32, A/B TF32, both K-major, M = 128
+// (both operands K-major: measured on B200, tcgen05.mma.kind::tf32 with an MN-major smem operand accumulates nothing)
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -158,7 +159,14 @@ __device__ __forceinline__ float tf32_hi(float x) {
 //     IMG[(k / 4) * F + f][k % 4]
 // i.e. the UMMA K-major no-swizzle operand layout with LBO = F * 16 bytes, SBO = 128 bytes.  A K = 32 slice is a
 // contiguous block of 8 * F * 16 bytes, so one bulk copy brings a whole operand slice into shared memory.
-// Weights: k = input feature, f = output feature.  Activations (for dW): k = MLP row, f = feature.
+// Weights: k = input feature, f = output feature.
+//
+// Activations / activation gradients go to HBM as ONE raw fp32 "row image" per tensor,
+//     ACT[((r / 8) * (F / 4) + f / 4) * 8 + r % 8][f % 4]        (r = MLP row, f = feature)
+// chosen for the writer: the epilogue thread (= one MLP row) stores whole float4s and a warp store covers 4 x 128
+// contiguous bytes; a 32-row slice is one contiguous block of F * 128 bytes (one bulk copy).  The weight-gradient
+// GEMM reduces over r, so its operands must be K-major in r (the tensor core does not take MN-major TF32 operands):
+// k_mlp_dw transposes + hi/lo-splits each slice on chip with its otherwise idle threads.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_mlp_prep(const float* __restrict__ W, int N, int K, int ldw, int Np, int Kp, int transpose,
                            float* __restrict__ W_hi, float* __restrict__ W_lo) {
@@ -189,9 +197,8 @@ struct MlpLayer {
   const float* W_hi;    // CH(Np) image, Kp/4 chunks
   const float* W_lo;
   const float* bias;    // [N] or nullptr
-  float* img_hi;        // CH(Np) image over rows of this layer's output (hi part), or nullptr
-  float* img_lo;
-  const float* mask;    // CH(Np) image (hi part of the forward activation): output *= (mask > 0), or nullptr
+  float* img;           // ACT(Np) row image of this layer's output, or nullptr
+  const float* mask;    // ACT(Np) row image of the forward activation: output *= (mask > 0), or nullptr
   int Kp, Np, N, relu;
 };
 struct MlpChain {
@@ -209,9 +216,9 @@ struct __align__(16) MlpSmem {
   uint32_t tmem_base;
 };
 
-// 8 consecutive features [c0, c0+8) of this thread's row: hi -> TMEM (A operand), lo -> smem tile; optional HBM images
+// 8 consecutive features [c0, c0+8) of this thread's row: hi -> TMEM (A operand), lo -> smem tile; optional HBM row image
 __device__ __forceinline__ void store_a8(MlpSmem& s, uint32_t tmem_a_lane, int row_in_tile, int c0, const float* v,
-                                         float* __restrict__ img_hi, float* __restrict__ img_lo, int F, int64_t row) {
+                                         float* __restrict__ img, int F, int64_t row) {
   float hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { hi[j] = tf32_hi(v[j]); lo[j] = tf32_hi(v[j] - hi[j]); }
@@ -219,16 +226,16 @@ __device__ __forceinline__ void store_a8(MlpSmem& s, uint32_t tmem_a_lane, int r
 #pragma unroll
   for (int q = 0; q < 2; ++q)
     reinterpret_cast<float4*>(s.A_lo)[((c0 >> 2) + q) * MLP_ROWS + row_in_tile] = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-  if (img_hi) {
-    const int64_t base = ((row >> 2) * F + c0) * 4 + (row & 3);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { img_hi[base + 4 * j] = hi[j]; img_lo[base + 4 * j] = lo[j]; }
+  if (img) {
+    const int64_t q0 = ((row >> 3) * (F >> 2) + (c0 >> 2)) * 8 + (row & 7);   // float4 index of feature quad c0/4
+    reinterpret_cast<float4*>(img)[q0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(img)[q0 + 8] = make_float4(v[4], v[5], v[6], v[7]);
   }
 }
 
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __restrict__ n_rows_dev, int capacity, MlpChain ch,
-            float* __restrict__ Y, int ldy, int n_out, float* __restrict__ x_img_hi, float* __restrict__ x_img_lo) {
+            float* __restrict__ Y, int ldy, int n_out, float* __restrict__ x_img) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   MlpSmem& s = *reinterpret_cast<MlpSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -293,7 +300,7 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
                 if (c0 + j < K0) v[j] = __ldg(src + c0 + j);
             }
           }
-          store_a8(s, lane_addr + MLP_TMEM_A, tid, c0, v, x_img_hi, x_img_lo, K0p, row);
+          store_a8(s, lane_addr + MLP_TMEM_A, tid, c0, v, x_img, K0p, row);
         }
         tmem_st_wait();
       }
@@ -346,10 +353,15 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
               v[j] = y;
             }
             if (L.mask && row < n_rows) {
-              const int64_t base = (((int64_t)row >> 2) * Np + c0) * 4 + (row & 3);
+              const float4* mk = reinterpret_cast<const float4*>(L.mask) + (((int64_t)row >> 3) * (Np >> 2) + (c0 >> 2)) * 8 + (row & 7);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (!(__ldg(L.mask + base + 4 * j) > 0.f)) v[j] = 0.f;
+              for (int q = 0; q < 8; ++q) {
+                const float4 m4 = __ldg(mk + 8 * q);
+                if (!(m4.x > 0.f)) v[4 * q] = 0.f;
+                if (!(m4.y > 0.f)) v[4 * q + 1] = 0.f;
+                if (!(m4.z > 0.f)) v[4 * q + 2] = 0.f;
+                if (!(m4.w > 0.f)) v[4 * q + 3] = 0.f;
+              }
             }
             if (row >= n_rows) {
 #pragma unroll
@@ -357,7 +369,7 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              store_a8(s, lane_addr + MLP_TMEM_A, tid, c0 + 8 * q, v + 8 * q, L.img_hi, L.img_lo, Np, row);
+              store_a8(s, lane_addr + MLP_TMEM_A, tid, c0 + 8 * q, v + 8 * q, L.img, Np, row);
           }
           tmem_st_wait();
         } else {
@@ -382,36 +394,33 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
 }
 
 // Layers are described by two packed HOST arrays so the C ABI stays plain:
-//   ptrs_host[l*6 + {0..5}] = device addresses of W_hi, W_lo (CH(Np) images from vx_mlp_prep), bias, img_hi out, img_lo out,
-//                             mask image (0 = none)
+//   ptrs_host[l*5 + {0..4}] = device addresses of W_hi, W_lo (CH(Np) images from vx_mlp_prep), bias, row image out,
+//                             mask row image (0 = none)
 //   dims_host[l*4 + {0..3}] = Kp, Np, N, relu
 // X (capacity, ldx) with K0 valid columns; Y (capacity, ldy) receives the first n_out columns of the last layer;
-// x_img_hi/lo: optional CH(K0p) images of the input.  Every image needs 128 * ceil(capacity / 128) rows.
+// x_img: optional ACT(K0p) row image of the input.  Every row image needs 128 * ceil(capacity / 128) rows.
 VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, int capacity, int n_layers,
-                        const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* x_img_hi,
-                        float* x_img_lo, cudaStream_t st) {
+                        const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* x_img,
+                        cudaStream_t st) {
   VX_REQUIRE(n_layers >= 1 && n_layers <= MLP_MAX_LAYERS, "vx_mlp_chain", "1..4 layers");
   VX_REQUIRE(n_rows_dev != nullptr, "vx_mlp_chain", "n_rows_dev required");
   MlpChain ch;
   ch.n_layers = n_layers;
   for (int l = 0; l < n_layers; ++l) {
     MlpLayer& L = ch.L[l];
-    L.W_hi = reinterpret_cast<const float*>(ptrs_host[l * 6 + 0]);
-    L.W_lo = reinterpret_cast<const float*>(ptrs_host[l * 6 + 1]);
-    L.bias = reinterpret_cast<const float*>(ptrs_host[l * 6 + 2]);
-    L.img_hi = reinterpret_cast<float*>(ptrs_host[l * 6 + 3]);
-    L.img_lo = reinterpret_cast<float*>(ptrs_host[l * 6 + 4]);
-    L.mask = reinterpret_cast<const float*>(ptrs_host[l * 6 + 5]);
+    L.W_hi = reinterpret_cast<const float*>(ptrs_host[l * 5 + 0]);
+    L.W_lo = reinterpret_cast<const float*>(ptrs_host[l * 5 + 1]);
+    L.bias = reinterpret_cast<const float*>(ptrs_host[l * 5 + 2]);
+    L.img = reinterpret_cast<float*>(ptrs_host[l * 5 + 3]);
+    L.mask = reinterpret_cast<const float*>(ptrs_host[l * 5 + 4]);
     L.Kp = dims_host[l * 4 + 0]; L.Np = dims_host[l * 4 + 1]; L.N = dims_host[l * 4 + 2]; L.relu = dims_host[l * 4 + 3];
     VX_REQUIRE(L.Kp % 8 == 0 && L.Kp >= 8 && L.Kp <= MLP_MAXW && L.Np % 16 == 0 && L.Np >= 16 && L.Np <= MLP_MAXW,
                "vx_mlp_chain", "layer shape");
-    VX_REQUIRE((L.img_hi == nullptr) == (L.img_lo == nullptr), "vx_mlp_chain", "img_hi / img_lo come in pairs");
     if (l + 1 < n_layers)
       VX_REQUIRE(L.Np % 32 == 0 && L.Np == dims_host[(l + 1) * 4 + 0], "vx_mlp_chain", "hidden widths must chain and be multiples of 32");
   }
   const int K0p = dims_host[0];
   VX_REQUIRE(K0 <= K0p && K0 <= ldx && n_out <= dims_host[(n_layers - 1) * 4 + 1], "vx_mlp_chain", "K0 / n_out");
-  VX_REQUIRE((x_img_hi == nullptr) == (x_img_lo == nullptr), "vx_mlp_chain", "x_img_hi / x_img_lo come in pairs");
   const int tiles_cap = (capacity + MLP_ROWS - 1) / MLP_ROWS;
   static bool attr_set = false;
   const int smem = (int)sizeof(MlpSmem) + 1024;
@@ -422,32 +431,58 @@ VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, 
   }
   if (tiles_cap <= 0) return 0;
   const int blocks = min(tiles_cap, vx_num_sms());
-  k_mlp_chain<<<blocks, MLP_THREADS, smem, st>>>(X, ldx, K0, K0p, n_rows_dev, capacity, ch, Y, ldy, n_out, x_img_hi, x_img_lo);
+  k_mlp_chain<<<blocks, MLP_THREADS, smem, st>>>(X, ldx, K0, K0p, n_rows_dev, capacity, ch, Y, ldy, n_out, x_img);
   return vx_check_launch("vx_mlp_chain");
 }
 
 // ---------------------------------------------------------------------------------------------
-// Split-K weight-gradient GEMM on the images:  C[m][n] += sum_r A[r][m] * B[r][n]   (dW = dY^T H)
-// A = CH(FA) hi/lo images of dY (m < M_out <= FA), B = CH(FB) hi/lo images of H (n < N_in <= FB): a K = 32-row slice
-// of each of the four operands is one bulk copy; no staging, no split arithmetic in this kernel.  Both 128-row M
-// tiles (output features 0..127 and 128..255) are accumulated by the same CTA in two TMEM accumulators, so every B
-// slice is fetched once.  Slices are dealt round-robin to the CTAs (split-K); partial sums go out as vector atomics.
+// Split-K weight-gradient GEMM on the row images:  C[m][n] += sum_r A[r][m] * B[r][n]   (dW = dY^T H, db = dY^T 1)
+// A = ACT(FA) row image of dY (m < M_out <= FA), B = ACT(FB) row image of H (n < N_in <= FB).  Per 32-row slice:
+//   1. thread 0 bulk-copies the two raw slices (F * 128 bytes each) into shared memory;
+//   2. all 128 threads transpose + hi/lo-split them into four K-major operand tiles (reduction index = MLP row).
+//      Reads are consecutive float4s; the scalar writes are bank-conflict free because the operand tiles are padded
+//      through the descriptor strides (SBO = 144 B between 8-feature groups, LBO = F/8 * 144 + 32 B between 4-row chunks);
+//   3. thread 0 issues the MMAs: both 128-row M tiles (features 0..127 / 128..255) into two TMEM accumulators, plus
+//      two N = 16 MMAs against a constant ones tile whose first column gives the bias gradient.
+// Slices are dealt round-robin to the CTAs (split-K); partial sums leave as vector atomics.
 // ---------------------------------------------------------------------------------------------
 #define DW_KC 32
+#define DW_SBO 144                                              // bytes between 8-feature groups of an operand tile
+#define DW_TILE_BYTES(F) (8 * (((F) >> 3) * DW_SBO + 32))       // 8 four-row chunks
 struct __align__(16) DwSmem {
-  float A[2][2][DW_KC / 4 * MLP_MAXW * 4];   // stage x {hi,lo} x 24 KB
-  float B[2][2][DW_KC / 4 * MLP_MAXW * 4];
-  float pad[DW_KC / 4 * 64 * 4];             // M tile 1 reads up to 64 feature rows past the last chunk of an A slice
-  uint64_t bar_full[2];
-  uint64_t bar_empty[2];
+  float raw[2][DW_KC * MLP_MAXW];                               // bulk-copy landing zone: A slice, B slice (24 KB each)
+  uint8_t op[4][DW_TILE_BYTES(MLP_MAXW) + 2048];                // A_hi, A_lo, B_hi, B_lo operand tiles (+ slack: M tile 1 over-read)
+  float ones[2 * 16 * 4];                                       // K-major [2 chunks][16 features][4 rows]: feature 0 = 1
+  uint64_t bar_full;
+  uint64_t bar_mma;
   uint64_t bar_acc;
   uint32_t tmem_base;
 };
 
+__device__ __forceinline__ void dw_transpose(const float* __restrict__ raw, int F, uint8_t* __restrict__ op_hi,
+                                             uint8_t* __restrict__ op_lo, int tid) {
+  const int quads = F >> 2;                       // feature quads per row
+  const uint32_t lbo = (uint32_t)(F >> 3) * DW_SBO + 32;
+  const int n4 = DW_KC * quads;                   // float4s in the slice
+  for (int idx = tid; idx < n4; idx += MLP_ROWS) {
+    const int r8 = idx & 7, q = (idx >> 3) % quads, g = (idx >> 3) / quads;
+    const float4 x = reinterpret_cast<const float4*>(raw)[idx];
+    const int c = 2 * g + (r8 >> 2), rr = r8 & 3;                 // 4-row chunk, row within the chunk
+    const int f = 4 * q;
+    const uint32_t base = (uint32_t)c * lbo + (uint32_t)(f >> 3) * DW_SBO + (uint32_t)(f & 7) * 16 + (uint32_t)rr * 4;
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float h = tf32_hi(xs[t]);
+      *reinterpret_cast<float*>(op_hi + base + t * 16) = h;
+      *reinterpret_cast<float*>(op_lo + base + t * 16) = tf32_hi(xs[t] - h);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(MLP_ROWS, 1)
-k_mlp_dw(const float* __restrict__ A_hi, const float* __restrict__ A_lo, int FA, int M_out, const float* __restrict__ B_hi,
-         const float* __restrict__ B_lo, int FB, int N_in, const int* __restrict__ n_rows_dev, int capacity,
-         float* __restrict__ C, int ldc) {
+k_mlp_dw(const float* __restrict__ A_img, int FA, int M_out, const float* __restrict__ B_img, int FB, int N_in,
+         const int* __restrict__ n_rows_dev, int capacity, float* __restrict__ C, int ldc, float* __restrict__ c_bias) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   DwSmem& s = *reinterpret_cast<DwSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -455,10 +490,10 @@ k_mlp_dw(const float* __restrict__ A_hi, const float* __restrict__ A_lo, int FA,
   const int n_slices = (n_rows + DW_KC - 1) / DW_KC;
   const int m_tiles = (M_out + MLP_ROWS - 1) / MLP_ROWS;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&s.bar_full[i], 1); mbar_init(&s.bar_empty[i], 1); }
-    mbar_init(&s.bar_acc, 1);
+    mbar_init(&s.bar_full, 1); mbar_init(&s.bar_mma, 1); mbar_init(&s.bar_acc, 1);
     fence_barrier_init();
   }
+  s.ones[tid] = ((tid >> 2) % 16 == 0) ? 1.f : 0.f;   // [chunk][feature][row]: feature 0 of both chunks
   if (warp == 0) tmem_alloc(&s.tmem_base, MLP_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -466,64 +501,72 @@ k_mlp_dw(const float* __restrict__ A_hi, const float* __restrict__ A_lo, int FA,
   const uint32_t tmem = s.tmem_base;
   const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
   const int my_slices = (n_slices > (int)blockIdx.x) ? (n_slices - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const uint32_t a_bytes = DW_KC / 4 * FA * 16, b_bytes = DW_KC / 4 * FB * 16;
-  if (tid == 0 && my_slices > 0) {
-    const uint32_t idesc = make_idesc_tf32(MLP_ROWS, FB);
-    auto issue_load = [&](int i) {
-      const int slot = i & 1;
-      const int64_t sl = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
-      mbar_expect_tx(&s.bar_full[slot], 2 * a_bytes + 2 * b_bytes);
-      bulk_g2s(&s.A[slot][0][0], A_hi + sl * (DW_KC / 4) * FA * 4, a_bytes, &s.bar_full[slot]);
-      bulk_g2s(&s.A[slot][1][0], A_lo + sl * (DW_KC / 4) * FA * 4, a_bytes, &s.bar_full[slot]);
-      bulk_g2s(&s.B[slot][0][0], B_hi + sl * (DW_KC / 4) * FB * 4, b_bytes, &s.bar_full[slot]);
-      bulk_g2s(&s.B[slot][1][0], B_lo + sl * (DW_KC / 4) * FB * 4, b_bytes, &s.bar_full[slot]);
-    };
-    issue_load(0);
-    for (int i = 0; i < my_slices; ++i) {
-      const int slot = i & 1;
-      if (i + 1 < my_slices) {
-        if (i + 1 >= 2) mbar_wait(&s.bar_empty[(i + 1) & 1], (((i + 1) >> 1) - 1) & 1);
-        issue_load(i + 1);
-      }
-      mbar_wait(&s.bar_full[slot], (i >> 1) & 1);
+  const uint32_t a_bytes = DW_KC * FA * 4, b_bytes = DW_KC * FB * 4;
+  const uint32_t a_lbo = (uint32_t)(FA >> 3) * DW_SBO + 32, b_lbo = (uint32_t)(FB >> 3) * DW_SBO + 32;
+  auto issue_load = [&](int i) {
+    const int64_t sl = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+    mbar_expect_tx(&s.bar_full, a_bytes + b_bytes);
+    bulk_g2s(s.raw[0], A_img + sl * DW_KC * FA, a_bytes, &s.bar_full);
+    bulk_g2s(s.raw[1], B_img + sl * DW_KC * FB, b_bytes, &s.bar_full);
+  };
+  if (tid == 0 && my_slices > 0) issue_load(0);
+  for (int i = 0; i < my_slices; ++i) {
+    mbar_wait(&s.bar_full, i & 1);                           // raw slices of step i landed
+    if (i > 0) mbar_wait(&s.bar_mma, (i - 1) & 1);           // MMAs of step i-1 finished reading the operand tiles
+    dw_transpose(s.raw[0], FA, s.op[0], s.op[1], tid);
+    dw_transpose(s.raw[1], FB, s.op[2], s.op[3], tid);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      if (i + 1 < my_slices) issue_load(i + 1);              // raw buffers are free again: overlaps with the MMAs below
       tc_fence_after();
+      const uint32_t idesc = make_idesc_tf32(MLP_ROWS, FB);
+      const uint32_t idesc1 = make_idesc_tf32(MLP_ROWS, 16);
       for (int mt = 0; mt < m_tiles; ++mt) {
 #pragma unroll
-        for (int kk = 0; kk < DW_KC / 8; ++kk) {
-          const uint32_t a_off = (uint32_t)(kk * 2) * FA * 16 + (uint32_t)mt * MLP_ROWS * 16;
-          const uint32_t b_off = (uint32_t)(kk * 2) * FB * 16;
-          const uint64_t da_hi = make_desc(smem_u32(&s.A[slot][0][0]) + a_off, FA * 16, 128);
-          const uint64_t da_lo = make_desc(smem_u32(&s.A[slot][1][0]) + a_off, FA * 16, 128);
-          const uint64_t db_hi = make_desc(smem_u32(&s.B[slot][0][0]) + b_off, FB * 16, 128);
-          const uint64_t db_lo = make_desc(smem_u32(&s.B[slot][1][0]) + b_off, FB * 16, 128);
+        for (int kk = 0; kk < DW_KC / 8; ++kk) {             // one MMA K-step = two 4-row chunks
+          const uint32_t a_off = (uint32_t)(2 * kk) * a_lbo + (uint32_t)mt * (MLP_ROWS / 8) * DW_SBO;
+          const uint32_t b_off = (uint32_t)(2 * kk) * b_lbo;
+          const uint64_t da_hi = make_desc(smem_u32(s.op[0]) + a_off, a_lbo, DW_SBO);
+          const uint64_t da_lo = make_desc(smem_u32(s.op[1]) + a_off, a_lbo, DW_SBO);
+          const uint64_t db_hi = make_desc(smem_u32(s.op[2]) + b_off, b_lbo, DW_SBO);
+          const uint64_t db_lo = make_desc(smem_u32(s.op[3]) + b_off, b_lbo, DW_SBO);
+          const uint64_t d_ones = make_desc(smem_u32(s.ones), 16 * 16, 128);
           const uint32_t d = tmem + mt * 256;
-          umma_tf32_ss(d, da_hi, db_hi, idesc, (i > 0) || (kk > 0));
+          const uint32_t acc = (i > 0) || (kk > 0);
+          umma_tf32_ss(d, da_hi, db_hi, idesc, acc);
           umma_tf32_ss(d, da_hi, db_lo, idesc, 1);
           umma_tf32_ss(d, da_lo, db_hi, idesc, 1);
+          umma_tf32_ss(d + FB, da_hi, d_ones, idesc1, acc);  // bias gradient columns [FB, FB + 16)
+          umma_tf32_ss(d + FB, da_lo, d_ones, idesc1, 1);
         }
       }
-      umma_commit(&s.bar_empty[slot]);
+      umma_commit(&s.bar_mma);
+      if (i == my_slices - 1) umma_commit(&s.bar_acc);
     }
-    umma_commit(&s.bar_acc);
   }
   if (my_slices > 0) {
     mbar_wait(&s.bar_acc, 0);
     tc_fence_after();
     for (int mt = 0; mt < m_tiles; ++mt) {
       const int m = mt * MLP_ROWS + tid;
-      for (int c0 = 0; c0 < FB; c0 += 16) {
+      for (int c0 = 0; c0 < FB + 16; c0 += 16) {
         float v[16];
         tmem_ld16(lane_addr + mt * 256 + c0, v);   // warp-collective: every thread executes it, only the adds are predicated
         if (m < M_out) {
+          if (c0 == FB) {
+            if (c_bias) atomicAdd(c_bias + m, v[0]);
+          } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int n = c0 + 4 * q;
-            if (n + 3 < N_in && (ldc % 4 == 0)) {
-              atomicAdd(reinterpret_cast<float4*>(C + (int64_t)m * ldc + n), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-            } else {
+            for (int q = 0; q < 4; ++q) {
+              const int n = c0 + 4 * q;
+              if (n + 3 < N_in && (ldc % 4 == 0)) {
+                atomicAdd(reinterpret_cast<float4*>(C + (int64_t)m * ldc + n), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+              } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (n + j < N_in) atomicAdd(C + (int64_t)m * ldc + n + j, v[4 * q + j]);
+                for (int j = 0; j < 4; ++j)
+                  if (n + j < N_in) atomicAdd(C + (int64_t)m * ldc + n + j, v[4 * q + j]);
+              }
             }
           }
         }
@@ -535,8 +578,8 @@ k_mlp_dw(const float* __restrict__ A_hi, const float* __restrict__ A_lo, int FA,
   if (warp == 0) tmem_dealloc(tmem, MLP_TMEM_COLS);
 }
 
-VX_API int vx_mlp_dw(const float* A_hi, const float* A_lo, int FA, int M_out, const float* B_hi, const float* B_lo, int FB,
-                     int N_in, const int* n_rows_dev, int capacity, float* C, int ldc, cudaStream_t st) {
+VX_API int vx_mlp_dw(const float* A_img, int FA, int M_out, const float* B_img, int FB, int N_in, const int* n_rows_dev,
+                     int capacity, float* C, int ldc, float* c_bias, cudaStream_t st) {
   VX_REQUIRE(n_rows_dev != nullptr, "vx_mlp_dw", "n_rows_dev required");
   VX_REQUIRE(FA % 8 == 0 && FA >= 8 && FA <= MLP_MAXW && FB % 16 == 0 && FB >= 16 && FB <= MLP_MAXW && M_out >= 1 &&
              M_out <= FA && N_in >= 1 && N_in <= FB, "vx_mlp_dw", "shape");
@@ -550,33 +593,6 @@ VX_API int vx_mlp_dw(const float* A_hi, const float* A_lo, int FA, int M_out, co
   const int slices_cap = (capacity + DW_KC - 1) / DW_KC;
   if (slices_cap <= 0) return 0;
   const int gx = max(1, min(vx_num_sms(), (slices_cap + 3) / 4));
-  k_mlp_dw<<<gx, MLP_ROWS, smem, st>>>(A_hi, A_lo, FA, M_out, B_hi, B_lo, FB, N_in, n_rows_dev, capacity, C, ldc);
+  k_mlp_dw<<<gx, MLP_ROWS, smem, st>>>(A_img, FA, M_out, B_img, FB, N_in, n_rows_dev, capacity, C, ldc, c_bias);
   return vx_check_launch("vx_mlp_dw");
-}
-
-// bias gradient: db[f] += sum_r (hi + lo)[r][f] over a CH(F) image pair (rows < *n_rows_dev)
-__global__ void k_mlp_colsum(const float* __restrict__ img_hi, const float* __restrict__ img_lo, int F, int M_out,
-                             const int* __restrict__ n_rows_dev, int capacity, float* __restrict__ out) {
-  const int n_rows = min(*n_rows_dev, capacity);
-  const int n_chunks = (n_rows + 3) / 4;
-  const int f = threadIdx.x;
-  if (f >= M_out) return;
-  float acc = 0.f;
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-    const float4 h = __ldg(reinterpret_cast<const float4*>(img_hi) + (int64_t)c * F + f);
-    const float4 l = __ldg(reinterpret_cast<const float4*>(img_lo) + (int64_t)c * F + f);
-    const int r = c * 4;
-    if (r + 0 < n_rows) acc += h.x + l.x;
-    if (r + 1 < n_rows) acc += h.y + l.y;
-    if (r + 2 < n_rows) acc += h.z + l.z;
-    if (r + 3 < n_rows) acc += h.w + l.w;
-  }
-  atomicAdd(out + f, acc);
-}
-
-VX_API int vx_mlp_colsum(const float* img_hi, const float* img_lo, int F, int M_out, const int* n_rows_dev, int capacity,
-                         float* out, cudaStream_t st) {
-  VX_REQUIRE(F <= 256 && M_out <= F, "vx_mlp_colsum", "shape");
-  k_mlp_colsum<<<vx_num_sms() * 2, ((F + 31) / 32) * 32, 0, st>>>(img_hi, img_lo, F, M_out, n_rows_dev, capacity, out);
-  return vx_check_launch("vx_mlp_colsum");
 }

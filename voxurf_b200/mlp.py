@@ -59,7 +59,7 @@ class FlatMLP:
             # pre-split hi/lo "chunked K-major images" (k = MLP row) of every activation and activation gradient:
             # written by the chain epilogues, consumed by the split-K weight-gradient GEMM with plain bulk copies
             self.R = (cap + 127) // 128 * 128
-            img = lambda F: (torch.zeros(self.R * F, dtype=torch.float32, device=dev), torch.zeros(self.R * F, dtype=torch.float32, device=dev))
+            img = lambda F: torch.zeros(self.R * F, dtype=torch.float32, device=dev)
             self.F_in = self.tc_fwd.Kp[0]
             self.X_img = img(self.F_in)
             self.H_img = [img(l.out_features) for l in self.linears[:-1]]
@@ -101,15 +101,14 @@ class FlatMLP:
             # dX chain (one launch): chain layer j <-> network layer n-1-j; hidden gradients land feature-major in dHT
             rev = list(range(n - 2, -1, -1))
             self.tc_bwd.run(d_out, d_out.shape[1], self._n, dX, dX.shape[1], imgs=[self.dH_img[i] for i in rev],
-                            masks=[self.H_img[i][0] for i in rev], x_img=self.dY_img)
+                            masks=[self.H_img[i] for i in rev], x_img=self.dY_img)
             call = self.tc_fwd._call
             for i in range(n):   # dW_i = dY_i^T H_{i-1}, db_i = dY_i^T 1
                 A, FA = (self.dY_img, 8) if i == n - 1 else (self.dH_img[i], self.linears[i].out_features)
                 B, FB = (self.X_img, self.F_in) if i == 0 else (self.H_img[i - 1], self.linears[i - 1].out_features)
                 M_out = self.linears[i].out_features
-                call('vx_mlp_dw', A[0], A[1], FA, M_out, B[0], B[1], FB, self.dW[i].shape[1], self._n, self.cap, self.dW[i],
-                     self.dW[i].stride(0))
-                call('vx_mlp_colsum', A[0], A[1], FA, M_out, self._n, self.cap, self.db[i])
+                call('vx_mlp_dw', A, FA, M_out, B, FB, self.dW[i].shape[1], self._n, self.cap, self.dW[i],
+                     self.dW[i].stride(0), self.db[i])
             return dX
         dy = d_out
         for i in range(n - 1, -1, -1):
@@ -165,15 +164,14 @@ class TensorCoreChain:
 
     def run(self, X, k0, n_rows_dev, Y, n_out, imgs=None, masks=None, x_img=None):
         """X (cap, ldx) with k0 valid columns -> Y (cap, ldy)[:, :n_out].  imgs[l] = (hi, lo) CH(Np) images written for
-        layer l's output, masks[l] = hi image gating layer l's output (ReLU backward), x_img = (hi, lo) images of X."""
+        layer l's output (ACT row image), masks[l] = row image gating layer l's output (ReLU backward), x_img = row image of X."""
         n = len(self.layers)
         ptrs, dims = [], []
         pick = lambda lst, i: lst[i] if (lst is not None and i < len(lst)) else None
         addr = lambda t: t.data_ptr() if t is not None else 0
         for i, L in enumerate(self.layers):
-            im = pick(imgs, i)
-            ptrs += [self.W_hi[i].data_ptr(), self.W_lo[i].data_ptr(), addr(L.get('bias')), addr(im[0]) if im else 0,
-                     addr(im[1]) if im else 0, addr(pick(masks, i))]
+            ptrs += [self.W_hi[i].data_ptr(), self.W_lo[i].data_ptr(), addr(L.get('bias')), addr(pick(imgs, i)),
+                     addr(pick(masks, i))]
             dims += [self.Kp[i], self.Np[i], self.N[i], int(bool(L.get('relu', False)))]
         self._call('vx_mlp_chain', X, X.stride(0), k0, n_rows_dev, X.shape[0], n, ptrs, dims, Y, Y.stride(0), n_out,
-                   x_img[0] if x_img else None, x_img[1] if x_img else None)
+                   x_img)
