@@ -128,13 +128,16 @@ __global__ void k_row_features(VxGrid gs, const float* __restrict__ sdf_grid, Vx
                                const float* __restrict__ viewdirs, const float* __restrict__ sdf_s,
                                const float* __restrict__ grad_s, float voxel_size, int use_grad_norm, VxRowLayout lay,
                                float* __restrict__ X1, float* __restrict__ X2) {
+  // four threads per row: sub-thread s evaluates the displacements l = s, s+4, ... (12 taps each); sub-thread 0 also
+  // writes the positional encodings, sub-thread 1 the k0 gather, sub-thread 2 the centre sdf / gradient columns
   const int n = min(*n_rows_dev, capacity);
-  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < capacity; row += gridDim.x * blockDim.x) {
+  for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < capacity * 4; item += gridDim.x * blockDim.x) {
+    const int row = item >> 2, sub = item & 3;
     float* x1 = X1 + (int64_t)row * lay.ld1;
     float* x2 = X2 + (int64_t)row * lay.ld2;
     if (row >= n) {
-      for (int c = 0; c < lay.ld1; ++c) x1[c] = 0.f;
-      for (int c = 0; c < lay.ld2; ++c) x2[c] = 0.f;
+      for (int c = sub; c < lay.ld1; c += 4) x1[c] = 0.f;
+      for (int c = sub; c < lay.ld2; c += 4) x2[c] = 0.f;
       continue;
     }
     const int i = idx4[row];
@@ -146,54 +149,70 @@ __global__ void k_row_features(VxGrid gs, const float* __restrict__ sdf_grid, Vx
 #pragma unroll
     for (int d = 0; d < 3; ++d) xn[d] = __fdiv_rn(__fsub_rn(p[d], gs.min[d]), __fsub_rn(gs.max[d], gs.min[d]));
     int c1 = 0, c2 = kC;
+    if (sub == 0) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) { x1[c1 + d] = xn[d]; x2[c2 + d] = xn[d]; }
+    }
     c1 += 3; c2 += 3;
+    if (sub == 0) {
     for (int d = 0; d < 3; ++d)
       for (int f = 0; f < lay.P; ++f) {
         const float e = __fmul_rn(xn[d], (float)(1 << f));
         x1[c1 + d * lay.P + f] = sinf(e);
         x1[c1 + 3 * lay.P + d * lay.P + f] = cosf(e);
       }
+    }
     c1 += 6 * lay.P;
+    if (sub == 0) {
     for (int d = 0; d < 3; ++d)
       for (int f = 0; f < lay.P2; ++f) {
         const float e = __fmul_rn(xn[d], (float)(1 << f));
         x2[c2 + d * lay.P2 + f] = sinf(e);
         x2[c2 + 3 * lay.P2 + d * lay.P2 + f] = cosf(e);
       }
+    }
     c2 += 6 * lay.P2;
     float vd[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) { vd[d] = viewdirs[3 * r + d]; x1[c1 + d] = vd[d]; x2[c2 + d] = vd[d]; }
+    for (int d = 0; d < 3; ++d) vd[d] = viewdirs[3 * r + d];
+    if (sub == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { x1[c1 + d] = vd[d]; x2[c2 + d] = vd[d]; }
+    }
     c1 += 3; c2 += 3;
+    if (sub == 0) {
     for (int d = 0; d < 3; ++d)
       for (int f = 0; f < lay.Vp; ++f) {
         const float e = __fmul_rn(vd[d], (float)(1 << f));
         x1[c1 + d * lay.Vp + f] = sinf(e);
         x1[c1 + 3 * lay.Vp + d * lay.Vp + f] = cosf(e);
       }
+    }
     c1 += 6 * lay.Vp;
+    if (sub == 0) {
     for (int d = 0; d < 3; ++d)
       for (int f = 0; f < lay.V2; ++f) {
         const float e = __fmul_rn(vd[d], (float)(1 << f));
         x2[c2 + d * lay.V2 + f] = sinf(e);
         x2[c2 + 3 * lay.V2 + d * lay.V2 + f] = cosf(e);
       }
+    }
     c2 += 6 * lay.V2;
     // ---- centre sdf, gradient (values of the M2-level pass)
-    x1[c1] = sdf_s[i];
+    if (sub == 2) x1[c1] = sdf_s[i];
     c1 += 1;
-    x2[c2] = grad_s[3 * i]; x2[c2 + 1] = grad_s[3 * i + 1]; x2[c2 + 2] = grad_s[3 * i + 2];
+    if (sub == 2) { x2[c2] = grad_s[3 * i]; x2[c2 + 1] = grad_s[3 * i + 1]; x2[c2 + 2] = grad_s[3 * i + 2]; }
     c2 += 3;
-    x2[c2] = 0.f; x2[c2 + 1] = 0.f; x2[c2 + 2] = 0.f;   // rgb_logit.detach(), filled after the first MLP
-    for (int c = c2 + 3; c < lay.ld2; ++c) x2[c] = 0.f;
+    if (sub == 2) {
+      x2[c2] = 0.f; x2[c2 + 1] = 0.f; x2[c2 + 2] = 0.f;   // rgb_logit.detach(), filled after the first MLP
+      for (int c = c2 + 3; c < lay.ld2; ++c) x2[c] = 0.f;
+    }
     // ---- sample_sdfs (displacement list, normalised gradients) lib/voxurf_fine.py:688
     const int L = lay.L;
     SdfTapCoords tc;
     sdf_tap_setup(gs, p[0], p[1], p[2], tc);
     VxTap t;
-    for (int l = 0; l < L; ++l) {
+    for (int l = sub; l < L; l += 4) {
       float gr[3];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -215,9 +234,10 @@ __global__ void k_row_features(VxGrid gs, const float* __restrict__ sdf_grid, Vx
 #pragma unroll
       for (int a = 0; a < 3; ++a) x1[c1 + 6 * L + a * L + l] = gr[a];
     }
-    for (int c = c1 + 9 * L; c < lay.ld1; ++c) x1[c] = 0.f;
+    if (sub == 3)
+      for (int c = c1 + 9 * L; c < lay.ld1; ++c) x1[c] = 0.f;
     // ---- k0 trilinear gather (DenseGrid.forward lib/grid.py:47-58) into X2[:, 0:C]
-    {
+    if (sub == 1) {
       float ix, iy, iz;
       point_to_index(gk, p[0], p[1], p[2], ix, iy, iz);
       vx_make_tap(ix, iy, iz, gk.X, gk.Y, gk.Z, t);
@@ -276,7 +296,7 @@ VX_API int vx_fused_row_features(const float* sdf_grid, const float* k0_grid, in
   const VxGrid gs = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
   const VxGrid gk = make_grid(X, Y, Z, C, k0_channels_last, xyz_min_host, xyz_max_host);
   const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
-  const int blocks = min(vx_blocks(capacity, 128), vx_num_sms() * 16);
+  const int blocks = min(vx_blocks((int64_t)capacity * 4, 128), vx_num_sms() * 32);
   if (C == 6)
     k_row_features<6><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, k0_grid, pts, idx4, n_rows_dev, capacity, viewdirs, sdf_s,
                                               grad_s, voxel_size, use_grad_norm, lay, X1, X2);
@@ -464,16 +484,20 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
   const int L = lay.L;
   const int col_sdf = 3 + 6 * lay.P + 3 + 6 * lay.Vp;
   const int col_grad2 = kC + 3 + 6 * lay.P2 + 3 + 6 * lay.V2;
-  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+  // four threads per row: sub-thread s scatters the displacements l = s, s+4, ...; sub-thread 0 also does the k0 scatter
+  for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < n * 4; item += gridDim.x * blockDim.x) {
+    const int row = item >> 2, sub = item & 3;
     const float* g1 = dX1 + (int64_t)row * lay.ld1;
     const float* g2 = dX2 + (int64_t)row * lay.ld2;
     const int i = idx4[row];
     float p[3];
     vx_load_pt(pts, i, p[0], p[1], p[2]);
-    d_sdf_s[i] = g1[col_sdf];
-    d_grad_s[3 * i] = g2[col_grad2]; d_grad_s[3 * i + 1] = g2[col_grad2 + 1]; d_grad_s[3 * i + 2] = g2[col_grad2 + 2];
+    if (sub == 1) {
+      d_sdf_s[i] = g1[col_sdf];
+      d_grad_s[3 * i] = g2[col_grad2]; d_grad_s[3 * i + 1] = g2[col_grad2 + 1]; d_grad_s[3 * i + 2] = g2[col_grad2 + 2];
+    }
     // ---- k0 scatter
-    {
+    if (sub == 0) {
       float go[kC];
       bool any = false;
 #pragma unroll
@@ -512,7 +536,7 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
     SdfTapCoords tc;
     sdf_tap_setup(gs, p[0], p[1], p[2], tc);
     VxTap t, tm;
-    for (int l = 0; l < L; ++l) {
+    for (int l = sub; l < L; l += 4) {
       float dgr[3] = {dgrad[0 * L + l], dgrad[1 * L + l], dgrad[2 * L + l]};
       if (use_grad_norm && (dgr[0] != 0.f || dgr[1] != 0.f || dgr[2] != 0.f)) {
         float gr[3];
@@ -569,7 +593,7 @@ VX_API int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int
   const VxGrid gs = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
   const VxGrid gk = make_grid(X, Y, Z, C, k0_channels_last, xyz_min_host, xyz_max_host);
   const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
-  const int blocks = min(vx_blocks(capacity, 128), vx_num_sms() * 16);
+  const int blocks = min(vx_blocks((int64_t)capacity * 4, 128), vx_num_sms() * 32);
   if (C == 6)
     k_row_backward<6><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, pts, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm, lay,
                                               dX1, dX2, d_sdf_s, d_grad_s, sdf_grad, k0_grad);

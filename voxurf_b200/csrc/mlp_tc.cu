@@ -464,12 +464,15 @@ __device__ __forceinline__ void dw_transpose(const float* __restrict__ raw, int 
   const int quads = F >> 2;                       // feature quads per row
   const uint32_t lbo = (uint32_t)(F >> 3) * DW_SBO + 32;
   const int n4 = DW_KC * quads;                   // float4s in the slice
+  // float4 idx = ((g * quads + q) * 8 + r8): consecutive threads read consecutive float4s; (g, q) advance incrementally
+  const int r8 = tid & 7;
+  int q = tid >> 3, g = 0;
+  while (q >= quads) { q -= quads; ++g; }
+  const uint32_t row_off = (uint32_t)(r8 >> 2) * lbo + (uint32_t)(r8 & 3) * 4;   // chunk parity + row within the 4-row chunk
   for (int idx = tid; idx < n4; idx += MLP_ROWS) {
-    const int r8 = idx & 7, q = (idx >> 3) % quads, g = (idx >> 3) / quads;
     const float4 x = reinterpret_cast<const float4*>(raw)[idx];
-    const int c = 2 * g + (r8 >> 2), rr = r8 & 3;                 // 4-row chunk, row within the chunk
     const int f = 4 * q;
-    const uint32_t base = (uint32_t)c * lbo + (uint32_t)(f >> 3) * DW_SBO + (uint32_t)(f & 7) * 16 + (uint32_t)rr * 4;
+    const uint32_t base = (uint32_t)(2 * g) * lbo + row_off + (uint32_t)(f >> 3) * DW_SBO + (uint32_t)(f & 7) * 16;
     const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -477,6 +480,8 @@ __device__ __forceinline__ void dw_transpose(const float* __restrict__ raw, int 
       *reinterpret_cast<float*>(op_hi + base + t * 16) = h;
       *reinterpret_cast<float*>(op_lo + base + t * 16) = tf32_hi(xs[t] - h);
     }
+    q += MLP_ROWS / 8;
+    while (q >= quads) { q -= quads; ++g; }
   }
 }
 
