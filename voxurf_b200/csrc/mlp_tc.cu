@@ -25,7 +25,8 @@
 #define MLP_MAX_LAYERS 4
 #define MLP_TMEM_COLS 512     // D accumulator at column 0, A (hi) operand at column 256
 #define MLP_TMEM_A 256
-#define MLP_THREADS 160       // warps 0-3: rows / epilogue (thread = row = TMEM lane); warp 4: weight producer
+#define MLP_ROW_THREADS 256   // warps 0-7: thread = row (TMEM lane = tid % 128); warps 0-3 / 4-7 take alternate column blocks
+#define MLP_THREADS 288       // + warp 8: weight producer
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -120,7 +121,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 128 row threads only
+__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 256 row threads only
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -255,7 +256,7 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
 
-  if (warp == 4) {
+  if (warp == MLP_ROW_THREADS / 32) {
     // ===== weight producer: one thread streams every (tile, layer, slice) weight block, two slices ahead at most =====
     if (lane == 0) {
       uint32_t it = 0;
@@ -278,14 +279,16 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
     }
   } else {
     // ===== row threads: stage inputs, (thread 0) issue MMAs, epilogues =====
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes (thread = lane = row)
+    const int rt = tid & (MLP_ROWS - 1);        // row within the tile == TMEM lane
+    const int half = tid >> 7;                  // 0: even column blocks, 1: odd column blocks
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp may only touch TMEM lanes 32*(warp%4)..
     uint32_t acc_phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int row = tile * MLP_ROWS + tid;
+      const int row = tile * MLP_ROWS + rt;
       {
         const bool vec = (ldx % 4 == 0);
         const float* src = X + (int64_t)row * ldx;
-        for (int c0 = 0; c0 < K0p; c0 += 8) {
+        for (int c0 = half * 8; c0 < K0p; c0 += 16) {
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -300,7 +303,7 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
                 if (c0 + j < K0) v[j] = __ldg(src + c0 + j);
             }
           }
-          store_a8(s, lane_addr + MLP_TMEM_A, tid, c0, v, x_img, K0p, row);
+          store_a8(s, lane_addr + MLP_TMEM_A, rt, c0, v, x_img, K0p, row);
         }
         tmem_st_wait();
       }
@@ -343,7 +346,7 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
         tc_fence_after();
         const bool last = (l == ch.n_layers - 1);
         if (!last) {
-          for (int c0 = 0; c0 < Np; c0 += 32) {
+          for (int c0 = half * 32; c0 < Np; c0 += 64) {
             float v[32];
             tmem_ld32(lane_addr + c0, v);
 #pragma unroll
@@ -369,11 +372,11 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              store_a8(s, lane_addr + MLP_TMEM_A, tid, c0 + 8 * q, v + 8 * q, L.img, Np, row);
+              store_a8(s, lane_addr + MLP_TMEM_A, rt, c0 + 8 * q, v + 8 * q, L.img, Np, row);
           }
           tmem_st_wait();
         } else {
-          for (int c0 = 0; c0 < Np; c0 += 16) {
+          for (int c0 = half * 16; c0 < Np; c0 += 32) {
             float v[16];
             tmem_ld16(lane_addr + c0, v);
             if (row < n_rows) {
@@ -447,6 +450,7 @@ VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, 
 // Slices are dealt round-robin to the CTAs (split-K); partial sums leave as vector atomics.
 // ---------------------------------------------------------------------------------------------
 #define DW_KC 32
+#define DW_THREADS 384                                          // 12 warps transpose; warps 0-3 also run the TMEM epilogue
 #define DW_SBO 144                                              // bytes between 8-feature groups of an operand tile
 #define DW_TILE_BYTES(F) (8 * (((F) >> 3) * DW_SBO + 32))       // 8 four-row chunks
 struct __align__(16) DwSmem {
@@ -468,8 +472,9 @@ __device__ __forceinline__ void dw_transpose(const float* __restrict__ raw, int 
   const int r8 = tid & 7;
   int q = tid >> 3, g = 0;
   while (q >= quads) { q -= quads; ++g; }
+  if (g >= DW_KC / 8) return;
   const uint32_t row_off = (uint32_t)(r8 >> 2) * lbo + (uint32_t)(r8 & 3) * 4;   // chunk parity + row within the 4-row chunk
-  for (int idx = tid; idx < n4; idx += MLP_ROWS) {
+  for (int idx = tid; idx < n4; idx += DW_THREADS) {
     const float4 x = reinterpret_cast<const float4*>(raw)[idx];
     const int f = 4 * q;
     const uint32_t base = (uint32_t)(2 * g) * lbo + row_off + (uint32_t)(f >> 3) * DW_SBO + (uint32_t)(f & 7) * 16;
@@ -480,12 +485,12 @@ __device__ __forceinline__ void dw_transpose(const float* __restrict__ raw, int 
       *reinterpret_cast<float*>(op_hi + base + t * 16) = h;
       *reinterpret_cast<float*>(op_lo + base + t * 16) = tf32_hi(xs[t] - h);
     }
-    q += MLP_ROWS / 8;
+    q += DW_THREADS / 8;
     while (q >= quads) { q -= quads; ++g; }
   }
 }
 
-__global__ void __launch_bounds__(MLP_ROWS, 1)
+__global__ void __launch_bounds__(DW_THREADS, 1)
 k_mlp_dw(const float* __restrict__ A_img, int FA, int M_out, const float* __restrict__ B_img, int FB, int N_in,
          const int* __restrict__ n_rows_dev, int capacity, float* __restrict__ C, int ldc, float* __restrict__ c_bias) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -498,7 +503,7 @@ k_mlp_dw(const float* __restrict__ A_img, int FA, int M_out, const float* __rest
     mbar_init(&s.bar_full, 1); mbar_init(&s.bar_mma, 1); mbar_init(&s.bar_acc, 1);
     fence_barrier_init();
   }
-  s.ones[tid] = ((tid >> 2) % 16 == 0) ? 1.f : 0.f;   // [chunk][feature][row]: feature 0 of both chunks
+  if (tid < 128) s.ones[tid] = ((tid >> 2) % 16 == 0) ? 1.f : 0.f;   // [chunk][feature][row]: feature 0 of both chunks
   if (warp == 0) tmem_alloc(&s.tmem_base, MLP_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -550,7 +555,7 @@ k_mlp_dw(const float* __restrict__ A_img, int FA, int M_out, const float* __rest
       if (i == my_slices - 1) umma_commit(&s.bar_acc);
     }
   }
-  if (my_slices > 0) {
+  if (my_slices > 0 && warp < 4) {
     mbar_wait(&s.bar_acc, 0);
     tc_fence_after();
     for (int mt = 0; mt < m_tiles; ++mt) {
@@ -598,6 +603,6 @@ VX_API int vx_mlp_dw(const float* A_img, int FA, int M_out, const float* B_img, 
   const int slices_cap = (capacity + DW_KC - 1) / DW_KC;
   if (slices_cap <= 0) return 0;
   const int gx = max(1, min(vx_num_sms(), (slices_cap + 3) / 4));
-  k_mlp_dw<<<gx, MLP_ROWS, smem, st>>>(A_img, FA, M_out, B_img, FB, N_in, n_rows_dev, capacity, C, ldc, c_bias);
+  k_mlp_dw<<<gx, DW_THREADS, smem, st>>>(A_img, FA, M_out, B_img, FB, N_in, n_rows_dev, capacity, C, ldc, c_bias);
   return vx_check_launch("vx_mlp_dw");
 }
