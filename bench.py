@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--cpu-rays', type=int, default=256, help='ray sample of the CPU baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--path', default='fused', choices=['fused', 'dropin'], help='fused = sync-free FusedFineStep; dropin = Voxurf.forward + autograd')
+    ap.add_argument('--dense-adam', action='store_true', help='k0 Adam over every voxel (no touched/live bitmaps)')
     ap.add_argument('--dense-k0-allreduce', action='store_true', help='multi-GPU: all-reduce the dense k0 gradient grid instead of exchanging rows')
     ap.add_argument('--phases', action='store_true', help='also print a per-phase CUDA-event breakdown to stderr')
     return ap.parse_args()
@@ -256,7 +257,7 @@ def main():
     fused = None
     if args.path == 'fused':
         from voxurf_b200.fused import FusedFineStep
-        fused = FusedFineStep(model, args.rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank)
+        fused = FusedFineStep(model, args.rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank, sparse_adam=not args.dense_adam)
         fused.calibrate(*dev_pool[0][:3], global_step=START_STEP, headroom=1.35)
         sync = None   # FusedFineStep.grad_sync(): dense all-reduce for sdf + MLPs, row exchange for k0 (or --dense-k0-allreduce)
         fused.sparse_k0_exchange = not args.dense_k0_allreduce
@@ -331,11 +332,27 @@ def main():
         # SURVEY.md 8d counts 7 Adam passes (read p,g,m,v; write p,m,v) + 1 gradient zero-fill pass per element; this kernel
         # does all 8 in one pass -> 32 B/element.  profiles/r01c: dram traffic 6.383 GB per launch vs 6.442 GB algorithmic.
         adam_bytes = 32 * V * C
+        adam_kernel = 'k_adam (k0 grid, %d x %d^3 fp32; Adam + fused grad zero-fill, 32 B/element)' % (C, G)
+        sparse = None
+        if fused is not None and fused.k0_touched is not None:
+            # sparse-aware pass: 32 B/element where a gradient landed this step, 24 B/element for voxels that ever had
+            # one (non-zero moments), nothing elsewhere (identity update), plus both bitmaps.  Counted on one extra step.
+            fused.bitmap_probe = []
+            run(1, START_STEP + args.warmup + 2 * args.steps, False)
+            torch.cuda.synchronize()
+            tb, lb = (np.unpackbits(x.cpu().numpy().view(np.uint8)) for x in fused.bitmap_probe[0])
+            fused.bitmap_probe = None
+            n_t, n_l = int(tb.sum()), int((tb | lb).sum())
+            adam_bytes = 4 * C * (8 * n_t + 6 * (n_l - n_t)) + 2 * 4 * fused.k0_touched.numel()
+            adam_kernel = 'k_adam (k0 grid, %d x %d^3 fp32, sparse-aware: %d touched voxels x 32 B/el + %d live x 24 B/el + bitmaps)' % (C, G, n_t, n_l - n_t)
+            sparse = {'voxels': V, 'touched': n_t, 'live': n_l, 'dense_equivalent_bytes': 32 * V * C}
         adam_t = float(np.mean(adam_ms)) if adam_ms else None
-        roof = {'bound': 'hbm', 'kernel': 'k_adam (k0 grid, %d x %d^3 fp32; Adam + fused grad zero-fill, 32 B/element)' % (C, G), 'achieved': (adam_bytes / (adam_t * 1e-3) / 1e9) if adam_t else None,
-                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'traffic': (6.383e9 if (C == 12 and G == 256) else None), 'ms_per_launch': adam_t,
+        roof = {'bound': 'hbm', 'kernel': adam_kernel, 'achieved': (adam_bytes / (adam_t * 1e-3) / 1e9) if adam_t else None,
+                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'traffic': (6.383e9 if (C == 12 and G == 256 and sparse is None) else None), 'ms_per_launch': adam_t,
                 'algorithmic_bytes_per_launch': adam_bytes, 'share_of_step': (adam_t / (ms / args.steps)) if adam_t else None}
         roof['frac'] = roof['achieved'] / peak if roof['achieved'] else None
+        if sparse:
+            roof['sparse'] = sparse
         if fused is not None:
             M0, M2, M4 = fused.counts()
             M3 = int(fused.keep[:M2].sum())

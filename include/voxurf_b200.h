@@ -91,10 +91,16 @@ int vx_adam_upd(float* param, const float* grad, float* exp_avg, float* exp_avg_
                 int64_t numel, int step, float beta1, float beta2, float lr, float eps, int mode,
                 cudaStream_t stream);
 /* the trainer's optimizer: utils.Adam.step / utils.adam, lib/utils.py:83-199 (dense; optional per-voxel lr,
- * optional skip of zero gradients, optional fused zero-fill of grad) */
+ * optional skip of zero gradients, optional fused zero-fill of grad).  `touched` / `live`: optional bitmaps, one bit
+ * per `group` consecutive elements: touched = a gradient was scattered there this step (elsewhere grad == 0 and is
+ * not read), live = a gradient was ever scattered there (elsewhere exp_avg == exp_avg_sq == 0: with grad == 0 the
+ * dense update is the identity and the element is skipped).  Same result as the dense pass, bit for bit. */
 int vx_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const float* perlr, int64_t numel,
                  float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
-                 float sqrt_bias_correction2, float eps, int skip_zero_grad, int zero_grad, cudaStream_t stream);
+                 float sqrt_bias_correction2, float eps, int skip_zero_grad, int zero_grad, const uint32_t* touched,
+                 const uint32_t* live, int group, cudaStream_t stream);
+/* live |= touched; touched = 0 -- after the vx_adam_step that consumed both */
+int vx_bitmap_merge(uint32_t* live, uint32_t* touched, int64_t n_words, cudaStream_t stream);
 
 /* ---- torch_scatter.segment_coo(reduce='sum'), sorted index (lib/voxurf_fine.py:753-777) ----- */
 int vx_segment_coo_sum(const float* src, const int64_t* index, int64_t M, int K, float* out, cudaStream_t stream);
@@ -113,7 +119,8 @@ int vx_grid_gather(const float* grid, int X, int Y, int Z, int C, int channels_l
 int vx_grid_gather_backward(int X, int Y, int Z, int C, int channels_last, const float* xyz_min_host,
                             const float* xyz_max_host, const float* xyz, const int* ray_id, const int* step_id,
                             const float* rays_start, const float* rays_dir, float stepdist, const int* n_dev,
-                            int64_t n_host, const float* grad_out, float* grad_grid, cudaStream_t stream);
+                            int64_t n_host, const float* grad_out, float* grad_grid, uint32_t* touched,
+                            cudaStream_t stream);
 /* Voxurf.grid_sampler (sample_ret + sample_grad)  lib/voxurf_fine.py:502-534  (L=1, xyz_order=1)
  * Voxurf.sample_sdfs                              lib/voxurf_fine.py:537-577  (L<=8, xyz_order=0) */
 int vx_sdf_taps(const float* grid, int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
@@ -142,6 +149,10 @@ int vx_neus_alpha_backward(const float* viewdirs, const int* ray_id, const int64
 int vx_fd_gradient(const float* sdf, int X, int Y, int Z, float voxel_size, float* grad, cudaStream_t stream);
 int vx_fd_gradient_backward(const float* dgrad, int X, int Y, int Z, float voxel_size, float* dsdf,
                             cudaStream_t stream);
+/* vx_fd_gradient_backward then the dense unmasked vx_total_variation_add_grad(param) with one pass over grad
+ * (run.py:612-655: both sdf regularisers of a fine-stage TV iteration); identical result to the two calls */
+int vx_sdf_regularisers_backward(const float* dgrad, const float* param, int X, int Y, int Z, float voxel_size,
+                                 float wx, float wy, float wz, float* grad, cudaStream_t stream);
 /* _gaussian_3dconv / tv_smooth_conv: Conv3d(1,1,k,padding=k//2,'replicate')  lib/voxurf_fine.py:236-258 ;
  * B independent volumes; weight_host is (k,k,k) on the HOST, k in {1,3,5} */
 int vx_conv3d_replicate(const float* in, int B, int X, int Y, int Z, const float* weight_host, int ksize,
@@ -228,7 +239,7 @@ int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int C, int
                           const int* n_rows_dev, int capacity, float voxel_size, int use_grad_norm, int P, int Vp,
                           int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
                           const float* dX2, float* d_sdf_s, float* d_grad_s, float* sdf_grad, float* k0_grad,
-                          cudaStream_t stream);
+                          uint32_t* k0_touched, cudaStream_t stream);
 /* data-parallel exchange of the k0 gradient as rows: (xyz, scale * dX2[:, 0:C]) per MLP row, zeros past *n_rows_dev;
  * the gathered rows of all ranks are scattered with vx_grid_gather_backward.  Pass k0_grad = NULL to
  * vx_fused_row_backward to skip the local scatter. */
@@ -249,6 +260,9 @@ int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min_host, 
  * to (Np, Kp), optionally of the transposed matrix (dX chain). */
 int vx_mlp_prep(const float* W, int N, int K, int ldw, int Np, int Kp, int transpose, float* W_hi, float* W_lo,
                 cudaStream_t stream);
+/* up to 16 vx_mlp_prep jobs in one launch: ptrs_host[j*3..] = W, W_hi, W_lo (device addresses);
+ * dims_host[j*6..] = N, K, ldw, Np, Kp, transpose */
+int vx_mlp_prep_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, cudaStream_t stream);
 /* Y = chain of up to 4 layers y = act(x W^T + b) [* (mask > 0)] on 128-row tiles.  Packed host arrays (csrc/mlp_tc.cu):
  * ptrs_host[l*5..] = W_hi, W_lo, bias, row image out, mask row image (device addresses, 0 = none);
  * dims_host[l*4..] = Kp, Np, N, relu.  Row images ACT(F) (raw fp32, r = MLP row) feed vx_mlp_dw. */

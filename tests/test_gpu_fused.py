@@ -51,6 +51,10 @@ def test_fused_forward_backward_matches_oracle(G, C, cl, n_rays, bg):
     for mlp, ol in ((fs.mlp1, om['rgbnet']), (fs.mlp2, om['k_rgbnet'])):
         for l, (W, b) in zip(mlp.linears, ol):
             grad_close(l.weight.grad, W.grad, 'W'); grad_close(l.bias.grad, b.grad, 'b')
+    if cl:   # every voxel that received a k0 gradient has its `touched` bit set (the sparse-aware Adam relies on it)
+        bits = np.unpackbits(fs.k0_touched.cpu().numpy().view(np.uint8), bitorder='little')[:G ** 3].astype(bool)
+        nz = (m.k0.grid.grad[0].permute(1, 2, 3, 0).reshape(G ** 3, C) != 0).any(1).cpu().numpy()
+        assert (bits | ~nz).all() and bits.sum() <= 8 * M4 and not fs.k0_live.any()
     # regularisers on top (smooth-grad TV through the FD gradient, TV add-grad), then Adam
     fs.regularise(step)
     om['sdf'].grad = None

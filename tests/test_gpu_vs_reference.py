@@ -94,11 +94,12 @@ def test_raw2alpha_vs_reference():
 
 
 @pytest.mark.parametrize('dense', [True, False])
-def test_total_variation_vs_reference(dense):
+@pytest.mark.parametrize('shape', [(1, 2, 40, 33, 47), (1, 1, 40, 33, 48)])   # the second takes the z-vectorised kernel
+def test_total_variation_vs_reference(dense, shape):
     ref = _ref('total_variation_cuda')
     from voxurf_b200 import total_variation_cuda as tv
     rs = np.random.RandomState(5)
-    p = T(rs.standard_normal((1, 2, 40, 33, 47)).astype(np.float32) * 2)
+    p = T(rs.standard_normal(shape).astype(np.float32) * 2)
     g = T(rs.standard_normal(p.shape).astype(np.float32)); g[rs.uniform(0, 1, g.shape) < 0.5] = 0
     mk = T((rs.uniform(0, 1, p.shape) > 0.3).astype(np.float32))
     a, b, c = g.clone().to(DEV), g.clone().to(DEV), g.clone()

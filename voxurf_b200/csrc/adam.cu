@@ -33,10 +33,22 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   }
 }
 
+// Sparse-aware dense Adam.  Two optional bitmaps, one bit per group of `group` consecutive elements (a voxel's
+// channel vector in the channels-last feature grid):
+//   touched : set by the scatter kernels for every voxel that received a gradient THIS step.  Where it is clear the
+//             gradient is exactly zero, so it is neither read nor re-zeroed.
+//   live    : set for every voxel that has EVER received a gradient (the caller ORs `touched` into it after each
+//             step, vx_bitmap_merge).  Where both are clear, exp_avg = exp_avg_sq = 0 and grad = 0, and the dense
+//             update of lib/utils.py:154-199 is the identity (m' = 0, v' = 0, p' = p - step * 0 / eps = p): the voxel
+//             is skipped without touching HBM.
+// The result is bit-identical to the dense pass; only the traffic changes (32 B/element for touched voxels, 24 for
+// live-but-untouched, 0 for the rest -- in the fine stage >90 % of a 256^3 grid lies outside the surface shell).
 template <bool kRef, int kMode, bool kZeroGrad>
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* __restrict__ grad,
                                               float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                                              const float* __restrict__ perlr, int64_t N, AdamCoef c) {
+                                              const float* __restrict__ perlr, int64_t N, AdamCoef c,
+                                              const uint32_t* __restrict__ touched, const uint32_t* __restrict__ live,
+                                              uint32_t group) {
   const int64_t n4 = N >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float4* p4 = reinterpret_cast<float4*>(param);
@@ -45,7 +57,19 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
   float4* v4 = reinterpret_cast<float4*>(exp_avg_sq);
   const float4* l4 = reinterpret_cast<const float4*>(perlr);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 g = g4[i];
+    bool has_grad = true;
+    if (touched) {   // numel < 2^32 checked by the launcher
+      const uint32_t e = (uint32_t)i << 2, v0 = e / group, v1 = (e + 3u) / group;
+      uint32_t t = (__ldg(touched + (v0 >> 5)) >> (v0 & 31)) & 1u;
+      uint32_t l = live ? (__ldg(live + (v0 >> 5)) >> (v0 & 31)) & 1u : 1u;
+      if (v1 != v0) {
+        t |= (__ldg(touched + (v1 >> 5)) >> (v1 & 31)) & 1u;
+        if (live) l |= (__ldg(live + (v1 >> 5)) >> (v1 & 31)) & 1u;
+      }
+      if (!(t | l)) continue;
+      has_grad = t;
+    }
+    const float4 g = has_grad ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     if (kMode == 1 && g.x == 0 && g.y == 0 && g.z == 0 && g.w == 0) continue;
     float4 p = p4[i], m = m4[i], v = v4[i];
     float4 l = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -55,7 +79,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
     if (kMode != 1 || g.z != 0) adam_one<kRef>(p.z, g.z, m.z, v.z, l.z, c);
     if (kMode != 1 || g.w != 0) adam_one<kRef>(p.w, g.w, m.w, v.w, l.w, c);
     p4[i] = p; m4[i] = m; v4[i] = v;
-    if (kZeroGrad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kZeroGrad && has_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   // tail (N % 4)
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
@@ -68,16 +92,64 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
   }
 }
 
+// The sparse-aware pass proper: one warp per bitmap word (32 voxels = 32 * group consecutive floats, a multiple of 4).
+// Words with no live and no touched voxel -- the bulk of the grid -- cost one 8-byte broadcast read; the others are
+// walked float4 by float4 by the warp's lanes (coalesced), each lane testing the bits of the voxel(s) its float4 covers.
+template <bool kZeroGrad>
+__global__ void __launch_bounds__(256) k_adam_sparse(float* __restrict__ param, float* __restrict__ grad,
+                                                     float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                     int64_t n_words, int64_t n_vox, AdamCoef c,
+                                                     const uint32_t* __restrict__ touched,
+                                                     const uint32_t* __restrict__ live, uint32_t group) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4* p4 = reinterpret_cast<float4*>(param);
+  float4* g4 = reinterpret_cast<float4*>(grad);
+  float4* m4 = reinterpret_cast<float4*>(exp_avg);
+  float4* v4 = reinterpret_cast<float4*>(exp_avg_sq);
+  const uint32_t per_word4 = 8u * group;       // float4s per bitmap word
+  // lanes prefetch 32 words at a time, then the warp walks the non-empty ones
+  for (int64_t wbase = warp0 * 32; wbase < n_words; wbase += n_warps * 32) {
+    const int64_t wi = wbase + lane;
+    const uint32_t tw_l = wi < n_words ? __ldg(touched + wi) : 0u;
+    const uint32_t lw_l = (wi < n_words && live) ? __ldg(live + wi) : (wi < n_words && !live ? 0xffffffffu : 0u);
+    uint32_t busy = __ballot_sync(0xffffffffu, (tw_l | lw_l) != 0u);
+    while (busy) {
+      const int src = __ffs(busy) - 1;
+      busy &= busy - 1;
+      const uint32_t tw = __shfl_sync(0xffffffffu, tw_l, src), lw = __shfl_sync(0xffffffffu, lw_l, src);
+      const int64_t w = wbase + src;
+      const int64_t f4_base = w * per_word4;
+      const int64_t f4_end = min(f4_base + per_word4, (n_vox * group) >> 2);
+      for (int64_t i = f4_base + lane; i < f4_end; i += 32) {
+        const uint32_t e = (uint32_t)(i - f4_base) << 2, b0 = e / group, b1 = min((e + 3u) / group, 31u);
+        const uint32_t t = ((tw >> b0) | (tw >> b1)) & 1u, l = ((lw >> b0) | (lw >> b1)) & 1u;
+        if (!(t | l)) continue;
+        const float4 g = t ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 p = p4[i], m = m4[i], v = v4[i];
+        adam_one<false>(p.x, g.x, m.x, v.x, 1.f, c);
+        adam_one<false>(p.y, g.y, m.y, v.y, 1.f, c);
+        adam_one<false>(p.z, g.z, m.z, v.z, 1.f, c);
+        adam_one<false>(p.w, g.w, m.w, v.w, 1.f, c);
+        p4[i] = p; m4[i] = m; v4[i] = v;
+        if (kZeroGrad && t) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+}
+
 template <bool kRef>
 static int launch_adam(float* param, float* grad, float* m, float* v, const float* perlr, int64_t N, const AdamCoef& c,
-                       int mode, int zero_grad, cudaStream_t st) {
+                       int mode, int zero_grad, cudaStream_t st, const uint32_t* touched = nullptr,
+                       const uint32_t* live = nullptr, int group = 1) {
   const bool aligned = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                          reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
                          reinterpret_cast<uintptr_t>(perlr)) & 15) == 0;
   if (!aligned) { vx_set_error("vx_adam", "tensors must be 16-byte aligned"); return -1; }
   const int64_t want = (N / 4 + 255) / 256 + 1;
   const int blocks = (int)min(want, (int64_t)vx_num_sms() * 8);
-#define VX_ADAM(MODE, ZG) k_adam<kRef, MODE, ZG><<<blocks, 256, 0, st>>>(param, grad, m, v, perlr, N, c)
+#define VX_ADAM(MODE, ZG) k_adam<kRef, MODE, ZG><<<blocks, 256, 0, st>>>(param, grad, m, v, perlr, N, c, touched, live, (uint32_t)group)
   if (mode == 0) { if (zero_grad) VX_ADAM(0, true); else VX_ADAM(0, false); }
   else if (mode == 1) { if (zero_grad) VX_ADAM(1, true); else VX_ADAM(1, false); }
   else { if (zero_grad) VX_ADAM(2, true); else VX_ADAM(2, false); }
@@ -99,11 +171,39 @@ VX_API int vx_adam_upd(float* param, const float* grad, float* exp_avg, float* e
 // bias corrections are computed by the caller in Python doubles exactly like lib/utils.py:176-177,192
 VX_API int vx_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const float* perlr, int64_t N,
                         float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
-                        float sqrt_bias_correction2, float eps, int skip_zero_grad, int zero_grad, cudaStream_t st) {
+                        float sqrt_bias_correction2, float eps, int skip_zero_grad, int zero_grad,
+                        const uint32_t* touched, const uint32_t* live, int group, cudaStream_t st) {
   if (N <= 0) return 0;
+  VX_REQUIRE(!touched || (group >= 1 && N % 4 == 0 && N < ((int64_t)1 << 32)), "vx_adam_step",
+             "touched bitmap needs group >= 1, numel % 4 == 0 and numel < 2^32");
+  VX_REQUIRE(!live || touched, "vx_adam_step", "a live bitmap needs a touched bitmap");
   AdamCoef c;
   c.beta1 = beta1; c.beta2 = beta2; c.omb1 = one_minus_beta1; c.omb2 = one_minus_beta2; c.eps = eps;
   c.step_size = step_size; c.sqrt_bc2 = sqrt_bias_correction2;
   const int mode = perlr ? 2 : (skip_zero_grad ? 1 : 0);
-  return launch_adam<false>(param, grad, exp_avg, exp_avg_sq, perlr, N, c, mode, zero_grad, st);
+  if (touched && mode == 0) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+                           reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0;
+    VX_REQUIRE(aligned && N % group == 0, "vx_adam_step", "bitmap pass: 16-byte aligned tensors, numel % group == 0");
+    const int64_t n_vox = N / group, n_words = (n_vox + 31) / 32;
+    const int blocks = (int)min((n_words + 255) / 256, (int64_t)vx_num_sms() * 8);
+    if (zero_grad) k_adam_sparse<true><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_words, n_vox, c, touched, live, (uint32_t)group);
+    else k_adam_sparse<false><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_words, n_vox, c, touched, live, (uint32_t)group);
+    return vx_check_launch("vx_adam_step");
+  }
+  return launch_adam<false>(param, grad, exp_avg, exp_avg_sq, perlr, N, c, mode, zero_grad, st, touched, live, group);
+}
+
+// live |= touched; touched = 0  (after the Adam pass that consumed both)
+__global__ void k_bitmap_merge(uint32_t* __restrict__ live, uint32_t* __restrict__ touched, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t t = touched[i];
+    if (t) { live[i] |= t; touched[i] = 0u; }
+  }
+}
+
+VX_API int vx_bitmap_merge(uint32_t* live, uint32_t* touched, int64_t n_words, cudaStream_t st) {
+  if (n_words <= 0) return 0;
+  k_bitmap_merge<<<(int)min((n_words + 255) / 256, (int64_t)vx_num_sms() * 8), 256, 0, st>>>(live, touched, n_words);
+  return vx_check_launch("vx_bitmap_merge");
 }

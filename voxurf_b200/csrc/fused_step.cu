@@ -479,7 +479,7 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
                                const int* __restrict__ idx4, const int* __restrict__ n_rows_dev, int capacity,
                                float voxel_size, int use_grad_norm, VxRowLayout lay, const float* __restrict__ dX1,
                                const float* __restrict__ dX2, float* __restrict__ d_sdf_s, float* __restrict__ d_grad_s,
-                               float* __restrict__ sdf_grad, float* __restrict__ k0_grad) {
+                               float* __restrict__ sdf_grad, float* __restrict__ k0_grad, uint32_t* __restrict__ k0_touched) {
   const int n = min(*n_rows_dev, capacity);
   const int L = lay.L;
   const int col_sdf = 3 + 6 * lay.P + 3 + 6 * lay.Vp;
@@ -508,6 +508,11 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
         VxTap t;
         vx_make_tap(ix, iy, iz, gk.X, gk.Y, gk.Z, t);
         const int64_t V = (int64_t)gk.X * gk.Y * gk.Z;
+        if (k0_touched) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (t.off[k] >= 0) atomicOr(k0_touched + (t.off[k] >> 5), 1u << (t.off[k] & 31));
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           if (t.off[k] < 0) continue;
@@ -585,7 +590,7 @@ VX_API int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int
                                  const int* n_rows_dev, int capacity, float voxel_size, int use_grad_norm, int P, int Vp,
                                  int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
                                  const float* dX2, float* d_sdf_s, float* d_grad_s, float* sdf_grad, float* k0_grad,
-                                 cudaStream_t st) {
+                                 uint32_t* k0_touched, cudaStream_t st) {
   if (capacity <= 0) return 0;
   VxRowLayout lay;
   VX_REQUIRE(fill_layout(lay, P, Vp, P2, V2, L, C, ld1, ld2, displace_host) == 0, "vx_fused_row_backward", "bad layout");
@@ -596,10 +601,10 @@ VX_API int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int
   const int blocks = min(vx_blocks((int64_t)capacity * 4, 128), vx_num_sms() * 32);
   if (C == 6)
     k_row_backward<6><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, pts, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm, lay,
-                                              dX1, dX2, d_sdf_s, d_grad_s, sdf_grad, k0_grad);
+                                              dX1, dX2, d_sdf_s, d_grad_s, sdf_grad, k0_grad, k0_touched);
   else
     k_row_backward<12><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, pts, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm, lay,
-                                               dX1, dX2, d_sdf_s, d_grad_s, sdf_grad, k0_grad);
+                                               dX1, dX2, d_sdf_s, d_grad_s, sdf_grad, k0_grad, k0_touched);
   return vx_check_launch("vx_fused_row_backward");
 }
 

@@ -72,7 +72,8 @@ __global__ void k_grid_gather(VxGrid g, const float* __restrict__ grid, VxPts pt
 
 template <int kC>
 __global__ void k_grid_gather_bwd(VxGrid g, VxPts pts, const int* __restrict__ n_dev, int64_t n_host,
-                                  const float* __restrict__ grad_out, float* __restrict__ grad_grid) {
+                                  const float* __restrict__ grad_out, float* __restrict__ grad_grid,
+                                  uint32_t* __restrict__ touched) {
   const int64_t n = vx_count(n_dev, n_host);
   const int C = kC > 0 ? kC : g.C;
   const int64_t V = (int64_t)g.X * g.Y * g.Z;
@@ -89,6 +90,11 @@ __global__ void k_grid_gather_bwd(VxGrid g, VxPts pts, const int* __restrict__ n
     point_to_index(g, px, py, pz, ix, iy, iz);
     VxTap t;
     vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+    if (touched) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (t.off[k] >= 0) atomicOr(touched + (t.off[k] >> 5), 1u << (t.off[k] & 31));
+    }
     if (g.cl && kC > 0) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -149,12 +155,13 @@ VX_API int vx_grid_gather(const float* grid, int X, int Y, int Z, int C, int cha
 VX_API int vx_grid_gather_backward(int X, int Y, int Z, int C, int channels_last, const float* xyz_min_host,
                                    const float* xyz_max_host, const float* xyz, const int* ray_id, const int* step_id,
                                    const float* rays_start, const float* rays_dir, float stepdist, const int* n_dev,
-                                   int64_t n_host, const float* grad_out, float* grad_grid, cudaStream_t st) {
+                                   int64_t n_host, const float* grad_out, float* grad_grid, uint32_t* touched,
+                                   cudaStream_t st) {
   if (!n_dev && n_host <= 0) return 0;
   const VxGrid g = make_grid(X, Y, Z, C, channels_last, xyz_min_host, xyz_max_host);
   const VxPts pts{xyz, ray_id, step_id, rays_start, rays_dir, stepdist};
   const int blocks = launch_blocks(n_dev, n_host);
-#define CALL(KC) k_grid_gather_bwd<KC><<<blocks, 256, 0, st>>>(g, pts, n_dev, n_host, grad_out, grad_grid)
+#define CALL(KC) k_grid_gather_bwd<KC><<<blocks, 256, 0, st>>>(g, pts, n_dev, n_host, grad_out, grad_grid, touched)
   VX_DISPATCH_C(C, channels_last, CALL)
 #undef CALL
   return vx_check_launch("vx_grid_gather_backward");

@@ -169,26 +169,56 @@ __device__ __forceinline__ float tf32_hi(float x) {
 // GEMM reduces over r, so its operands must be K-major in r (the tensor core does not take MN-major TF32 operands):
 // k_mlp_dw transposes + hi/lo-splits each slice on chip with its otherwise idle threads.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_mlp_prep(const float* __restrict__ W, int N, int K, int ldw, int Np, int Kp, int transpose,
-                           float* __restrict__ W_hi, float* __restrict__ W_lo) {
+struct MlpPrepJob {
+  const float* W;
+  float *W_hi, *W_lo;
+  int N, K, ldw, Np, Kp, transpose;
+};
+#define MLP_PREP_MAX_JOBS 16
+struct MlpPrepBatch { MlpPrepJob job[MLP_PREP_MAX_JOBS]; };
+
+// one launch for every weight image of a step: blockIdx.y = job (a layer of a forward or of a transposed dX chain)
+__global__ void k_mlp_prep(const __grid_constant__ MlpPrepBatch batch) {
+  const MlpPrepJob& J = batch.job[blockIdx.y];
   // logical operand (n, k) = W[n*ldw + k], or W[k*ldw + n] when transposed; zero outside (N, K)
-  const int total = Np * Kp;
+  const int total = J.Np * J.Kp;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int j = i & 3, n = (i >> 2) % Np, kc = (i >> 2) / Np;
+    const int j = i & 3, n = (i >> 2) % J.Np, kc = (i >> 2) / J.Np;
     const int k = kc * 4 + j;
     float w = 0.f;
-    if (n < N && k < K) w = transpose ? W[(int64_t)k * ldw + n] : W[(int64_t)n * ldw + k];
+    if (n < J.N && k < J.K) w = J.transpose ? J.W[(int64_t)k * J.ldw + n] : J.W[(int64_t)n * J.ldw + k];
     const float h = tf32_hi(w);
-    W_hi[i] = h;
-    W_lo[i] = tf32_hi(w - h);
+    J.W_hi[i] = h;
+    J.W_lo[i] = tf32_hi(w - h);
   }
+}
+
+VX_API int vx_mlp_prep_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, cudaStream_t st) {
+  VX_REQUIRE(n_jobs >= 0 && n_jobs <= MLP_PREP_MAX_JOBS, "vx_mlp_prep_batch", "at most 16 jobs per launch");
+  if (n_jobs == 0) return 0;
+  MlpPrepBatch b;
+  memset(&b, 0, sizeof(b));
+  int max_total = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    MlpPrepJob& J = b.job[j];
+    J.W = reinterpret_cast<const float*>(ptrs_host[3 * j]);
+    J.W_hi = reinterpret_cast<float*>(ptrs_host[3 * j + 1]);
+    J.W_lo = reinterpret_cast<float*>(ptrs_host[3 * j + 2]);
+    J.N = dims_host[6 * j]; J.K = dims_host[6 * j + 1]; J.ldw = dims_host[6 * j + 2];
+    J.Np = dims_host[6 * j + 3]; J.Kp = dims_host[6 * j + 4]; J.transpose = dims_host[6 * j + 5];
+    VX_REQUIRE(J.W && J.W_hi && J.W_lo, "vx_mlp_prep_batch", "null pointer");
+    VX_REQUIRE(J.Np % 16 == 0 && J.Kp % 8 == 0 && J.Np >= J.N && J.Kp >= J.K, "vx_mlp_prep_batch", "bad padding");
+    max_total = max(max_total, J.Np * J.Kp);
+  }
+  k_mlp_prep<<<dim3(vx_blocks(max_total, 256), n_jobs), 256, 0, st>>>(b);
+  return vx_check_launch("vx_mlp_prep_batch");
 }
 
 VX_API int vx_mlp_prep(const float* W, int N, int K, int ldw, int Np, int Kp, int transpose, float* W_hi, float* W_lo,
                        cudaStream_t st) {
-  VX_REQUIRE(Np % 16 == 0 && Kp % 8 == 0 && Np >= N && Kp >= K, "vx_mlp_prep", "bad padding");
-  k_mlp_prep<<<vx_blocks((int64_t)Np * Kp, 256), 256, 0, st>>>(W, N, K, ldw, Np, Kp, transpose, W_hi, W_lo);
-  return vx_check_launch("vx_mlp_prep");
+  const int64_t ptrs[3] = {(int64_t)(uintptr_t)W, (int64_t)(uintptr_t)W_hi, (int64_t)(uintptr_t)W_lo};
+  const int dims[6] = {N, K, ldw, Np, Kp, transpose};
+  return vx_mlp_prep_batch(1, ptrs, dims, st);
 }
 
 // ---------------------------------------------------------------------------------------------

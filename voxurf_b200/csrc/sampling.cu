@@ -91,40 +91,50 @@ VX_API int vx_infer_ray_start_dir(const float* rays_o, const float* rays_d, cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// ray setup: everything per-ray in one launch + an in-kernel exclusive scan of N_steps
-// (n_rays is a batch of ~8192: one 1024-thread CTA scans it with warp shuffles; the reference
-// uses torch cumsum + sum().item(), render_utils_kernel.cu:210-212).
+// ray setup: everything per-ray in one launch spread over the SMs, then a one-CTA exclusive scan of
+// N_steps (n_rays is a batch of ~8192; the reference uses torch cumsum + sum().item(),
+// render_utils_kernel.cu:210-212).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_ray_setup(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                    const float* __restrict__ xyz_min, const float* __restrict__ xyz_max,
-                                                    float near, float far, float stepdist, int n_rays,
-                                                    float* __restrict__ t_min, float* __restrict__ t_max,
-                                                    int64_t* __restrict__ n_steps, float* __restrict__ rays_start,
-                                                    float* __restrict__ rays_dir, int64_t* __restrict__ offsets) {
+__global__ void __launch_bounds__(128) k_ray_setup(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                   const float* __restrict__ xyz_min, const float* __restrict__ xyz_max,
+                                                   float near, float far, float stepdist, int n_rays,
+                                                   float* __restrict__ t_min, float* __restrict__ t_max,
+                                                   int64_t* __restrict__ n_steps, float* __restrict__ rays_start,
+                                                   float* __restrict__ rays_dir) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  const int o = 3 * r;
+  float tmn, tmx;
+  ray_t_minmax(rays_o + o, rays_d + o, xyz_min, xyz_max, near, far, tmn, tmx);
+  const float rnorm = ray_norm(rays_d + o);
+  t_min[r] = tmn; t_max[r] = tmx; n_steps[r] = ray_n_samples(tmn, tmx, rnorm, stepdist);
+  rays_start[o] = rays_o[o] + rays_d[o] * tmn;
+  rays_start[o + 1] = rays_o[o + 1] + rays_d[o + 1] * tmn;
+  rays_start[o + 2] = rays_o[o + 2] + rays_d[o + 2] * tmn;
+  rays_dir[o] = rays_d[o] / rnorm;
+  rays_dir[o + 1] = rays_d[o + 1] / rnorm;
+  rays_dir[o + 2] = rays_d[o + 2] / rnorm;
+}
+
+// exclusive scan of n_steps[0..n) -> offsets[0..n], one CTA: every thread owns 8 consecutive entries per pass
+constexpr int kScanPerThread = 8;
+__global__ void __launch_bounds__(1024) k_ray_offsets(const int64_t* __restrict__ n_steps, int n_rays,
+                                                      int64_t* __restrict__ offsets) {
   __shared__ int64_t warp_sum[32];
   __shared__ int64_t carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (int base = 0; base < n_rays; base += blockDim.x) {
-    const int r = base + threadIdx.x;
-    int64_t n = 0;
-    if (r < n_rays) {
-      const int o = 3 * r;
-      float tmn, tmx;
-      ray_t_minmax(rays_o + o, rays_d + o, xyz_min, xyz_max, near, far, tmn, tmx);
-      const float rnorm = ray_norm(rays_d + o);
-      n = ray_n_samples(tmn, tmx, rnorm, stepdist);
-      t_min[r] = tmn; t_max[r] = tmx; n_steps[r] = n;
-      rays_start[o] = rays_o[o] + rays_d[o] * tmn;
-      rays_start[o + 1] = rays_o[o + 1] + rays_d[o + 1] * tmn;
-      rays_start[o + 2] = rays_o[o + 2] + rays_d[o + 2] * tmn;
-      rays_dir[o] = rays_d[o] / rnorm;
-      rays_dir[o + 1] = rays_d[o + 1] / rnorm;
-      rays_dir[o + 2] = rays_d[o + 2] / rnorm;
+  for (int base = 0; base < n_rays; base += blockDim.x * kScanPerThread) {
+    const int r0 = base + threadIdx.x * kScanPerThread;
+    int64_t n[kScanPerThread];
+    int64_t tot = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+      n[j] = (r0 + j < n_rays) ? n_steps[r0 + j] : 0;
+      tot += n[j];
     }
-    // block-wide inclusive scan of n
-    int64_t x = n;
+    int64_t x = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int64_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -142,9 +152,13 @@ __global__ void __launch_bounds__(1024) k_ray_setup(const float* __restrict__ ra
       warp_sum[lane] = w;
     }
     __syncthreads();
-    const int64_t carry = carry_s;
-    const int64_t incl = x + (warp > 0 ? warp_sum[warp - 1] : 0) + carry;
-    if (r < n_rays) offsets[r] = incl - n;
+    const int64_t incl = x + (warp > 0 ? warp_sum[warp - 1] : 0) + carry_s;
+    int64_t run = incl - tot;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+      if (r0 + j < n_rays) offsets[r0 + j] = run;
+      run += n[j];
+    }
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry_s = incl;
     __syncthreads();
@@ -156,8 +170,10 @@ VX_API int vx_ray_setup(const float* rays_o, const float* rays_d, const float* x
                         float far, float stepdist, int n_rays, float* t_min, float* t_max, int64_t* n_steps,
                         float* rays_start, float* rays_dir, int64_t* offsets, cudaStream_t st) {
   VX_REQUIRE(n_rays >= 0, "vx_ray_setup", "n_rays < 0");
-  k_ray_setup<<<1, 1024, 0, st>>>(rays_o, rays_d, xyz_min, xyz_max, near, far, stepdist, n_rays, t_min, t_max, n_steps,
-                                  rays_start, rays_dir, offsets);
+  if (n_rays > 0)
+    k_ray_setup<<<vx_blocks(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, xyz_min, xyz_max, near, far, stepdist, n_rays, t_min,
+                                                       t_max, n_steps, rays_start, rays_dir);
+  k_ray_offsets<<<1, 1024, 0, st>>>(n_steps, n_rays, offsets);
   return vx_check_launch("vx_ray_setup");
 }
 

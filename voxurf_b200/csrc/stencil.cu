@@ -44,11 +44,106 @@ __global__ void k_fd_gradient_bwd(const float* __restrict__ dgrad, int X, int Y,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vectorised forms (Z % 4 == 0, numel < 2^31, 16-byte aligned): one thread = 4 consecutive z, 32-bit index
+// arithmetic, 128-bit loads / stores.  Every output element is produced by exactly the scalar kernels' sequence of
+// rounded operations, so the two forms agree bit for bit (x / 2 == x * 0.5 exactly).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float fd1(float hi, float lo, float vs) { return __fdiv_rn(__fmul_rn(__fsub_rn(hi, lo), 0.5f), vs); }
+__device__ __forceinline__ float4 fd4(const float4& a, const float4& b, float vs) {
+  return make_float4(fd1(a.x, b.x, vs), fd1(a.y, b.y, vs), fd1(a.z, b.z, vs), fd1(a.w, b.w, vs));
+}
+static bool vec4_ok(int X, int Y, int Z, int64_t planes, const void* a, const void* b, const void* c = nullptr) {
+  const int64_t n = (int64_t)X * Y * Z * planes;
+  return Z % 4 == 0 && n < ((int64_t)1 << 31) &&
+         ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
+__global__ void __launch_bounds__(256) k_fd_gradient_v4(const float* __restrict__ sdf, uint32_t X, uint32_t Y, uint32_t Z,
+                                                        float vs, float* __restrict__ grad) {
+  const uint32_t Z4 = Z >> 2, n4 = X * Y * Z4, V = X * Y * Z, sX = Y * Z;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
+    const uint32_t k4 = t % Z4, ij = t / Z4, j = ij % Y, i = ij / Y, v = t << 2;
+    const float4 c = ld4(sdf + v);
+    float4 gx = make_float4(0.f, 0.f, 0.f, 0.f), gy = gx, gz;
+    if (i > 0 && i < X - 1) gx = fd4(ld4(sdf + v + sX), ld4(sdf + v - sX), vs);
+    if (j > 0 && j < Y - 1) gy = fd4(ld4(sdf + v + Z), ld4(sdf + v - Z), vs);
+    gz.x = k4 > 0 ? fd1(c.y, __ldg(sdf + v - 1), vs) : 0.f;
+    gz.y = fd1(c.z, c.x, vs);
+    gz.z = fd1(c.w, c.y, vs);
+    gz.w = k4 < Z4 - 1 ? fd1(__ldg(sdf + v + 4), c.z, vs) : 0.f;
+    *reinterpret_cast<float4*>(grad + v) = gx;
+    *reinterpret_cast<float4*>(grad + V + v) = gy;
+    *reinterpret_cast<float4*>(grad + 2 * V + v) = gz;
+  }
+}
+
+// grad += FD^T(dgrad) (vx_fd_gradient_backward), then, when kTv, grad += the dense unmasked total_variation_add_grad
+// of `param` (total_variation_kernel.cu:14-35) -- one read-modify-write of grad for both regularisers.
+template <bool kFd, bool kTv>
+__global__ void __launch_bounds__(256) k_sdf_reg_backward_v4(const float* __restrict__ dgrad, const float* __restrict__ param,
+                                                             uint32_t X, uint32_t Y, uint32_t Z, float vs, float w_fast,
+                                                             float w_mid, float w_slow, float* __restrict__ grad) {
+  const uint32_t Z4 = Z >> 2, n4 = X * Y * Z4, V = X * Y * Z, sX = Y * Z;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
+    const uint32_t k4 = t % Z4, ij = t / Z4, j = ij % Y, i = ij / Y, v = t << 2, k = k4 << 2;
+    float4 g = *reinterpret_cast<const float4*>(grad + v);
+    float* gp = reinterpret_cast<float*>(&g);
+    if (kFd) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      // same order as k_fd_gradient_bwd: x-, x+, y-, y+, z-, z+ ; a source contributes iff it is interior on its axis
+      if (i >= 2 && i - 1 < X - 1) { const float4 a = ld4(dgrad + v - sX); acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; }
+      if (i + 1 < X - 1) { const float4 a = ld4(dgrad + v + sX); acc[0] -= a.x; acc[1] -= a.y; acc[2] -= a.z; acc[3] -= a.w; }
+      if (j >= 2 && j - 1 < Y - 1) { const float4 a = ld4(dgrad + V + v - Z); acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; }
+      if (j + 1 < Y - 1) { const float4 a = ld4(dgrad + V + v + Z); acc[0] -= a.x; acc[1] -= a.y; acc[2] -= a.z; acc[3] -= a.w; }
+      const float4 cz = ld4(dgrad + 2 * V + v);
+      const float zl = k4 > 0 ? __ldg(dgrad + 2 * V + v - 1) : 0.f, zr = k4 < Z4 - 1 ? __ldg(dgrad + 2 * V + v + 4) : 0.f;
+      const float zv[6] = {zl, cz.x, cz.y, cz.z, cz.w, zr};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t kk = k + q;
+        if (kk >= 2 && kk - 1 < Z - 1) acc[q] += zv[q];
+        if (kk + 1 < Z - 1) acc[q] -= zv[q + 2];
+        gp[q] += (acc[q] / vs) * 0.5f;
+      }
+    }
+    if (kTv) {
+      const float4 c = ld4(param + v);
+      const float pl = k4 > 0 ? __ldg(param + v - 1) : 0.f, pr = k4 < Z4 - 1 ? __ldg(param + v + 4) : 0.f;
+      const float pv[6] = {pl, c.x, c.y, c.z, c.w, pr};
+      float ym[4] = {0.f, 0.f, 0.f, 0.f}, yp[4] = {0.f, 0.f, 0.f, 0.f}, xm[4] = {0.f, 0.f, 0.f, 0.f}, xp[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j > 0) { const float4 a = ld4(param + v - Z); ym[0] = a.x; ym[1] = a.y; ym[2] = a.z; ym[3] = a.w; }
+      if (j < Y - 1) { const float4 a = ld4(param + v + Z); yp[0] = a.x; yp[1] = a.y; yp[2] = a.z; yp[3] = a.w; }
+      if (i > 0) { const float4 a = ld4(param + v - sX); xm[0] = a.x; xm[1] = a.y; xm[2] = a.z; xm[3] = a.w; }
+      if (i < X - 1) { const float4 a = ld4(param + v + sX); xp[0] = a.x; xp[1] = a.y; xp[2] = a.z; xp[3] = a.w; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t kk = k + q;
+        const float p0 = pv[q + 1];
+        float add = 0;
+        if (kk != 0) add += w_fast * fminf(fmaxf(p0 - pv[q], -1.f), 1.f);
+        if (kk != Z - 1) add += w_fast * fminf(fmaxf(p0 - pv[q + 2], -1.f), 1.f);
+        if (j != 0) add += w_mid * fminf(fmaxf(p0 - ym[q], -1.f), 1.f);
+        if (j != Y - 1) add += w_mid * fminf(fmaxf(p0 - yp[q], -1.f), 1.f);
+        if (i != 0) add += w_slow * fminf(fmaxf(p0 - xm[q], -1.f), 1.f);
+        if (i != X - 1) add += w_slow * fminf(fmaxf(p0 - xp[q], -1.f), 1.f);
+        gp[q] += add;
+      }
+    }
+    *reinterpret_cast<float4*>(grad + v) = g;
+  }
+}
+
 static int grid_blocks(int64_t V) { return (int)min((int64_t)vx_blocks(V, 256), (int64_t)vx_num_sms() * 16); }
 
 VX_API int vx_fd_gradient(const float* sdf, int X, int Y, int Z, float voxel_size, float* grad, cudaStream_t st) {
   const int64_t V = (int64_t)X * Y * Z;
   if (V <= 0) return 0;
+  if (vec4_ok(X, Y, Z, 3, sdf, grad) && V % 4 == 0) {   // (the y/z component planes start at multiples of V floats)
+    k_fd_gradient_v4<<<grid_blocks(V / 4), 256, 0, st>>>(sdf, X, Y, Z, voxel_size, grad);
+    return vx_check_launch("vx_fd_gradient");
+  }
   k_fd_gradient<<<grid_blocks(V), 256, 0, st>>>(sdf, X, Y, Z, voxel_size, grad);
   return vx_check_launch("vx_fd_gradient");
 }
@@ -57,6 +152,10 @@ VX_API int vx_fd_gradient_backward(const float* dgrad, int X, int Y, int Z, floa
                                    cudaStream_t st) {
   const int64_t V = (int64_t)X * Y * Z;
   if (V <= 0) return 0;
+  if (vec4_ok(X, Y, Z, 3, dgrad, dsdf)) {
+    k_sdf_reg_backward_v4<true, false><<<grid_blocks(V / 4), 256, 0, st>>>(dgrad, nullptr, X, Y, Z, voxel_size, 0.f, 0.f, 0.f, dsdf);
+    return vx_check_launch("vx_fd_gradient_backward");
+  }
   k_fd_gradient_bwd<<<grid_blocks(V), 256, 0, st>>>(dgrad, X, Y, Z, voxel_size, dsdf);
   return vx_check_launch("vx_fd_gradient_backward");
 }
@@ -209,6 +308,63 @@ __global__ void k_smooth_grad_tv(const float* __restrict__ G, const bool* __rest
   }
 }
 
+__global__ void __launch_bounds__(256) k_smooth_grad_tv_v4(const float* __restrict__ G, const bool* __restrict__ mask,
+                                                          uint32_t X, uint32_t Y, uint32_t Z, VxKernel3 ker, float scale,
+                                                          float* __restrict__ dG, float* __restrict__ partial) {
+  __shared__ float red[32];
+  const uint32_t Z4 = Z >> 2, V = X * Y * Z, V4 = V >> 2;
+  float local = 0.f;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < 3 * V4; t += gridDim.x * blockDim.x) {
+    const uint32_t comp = t / V4, u4 = t - comp * V4, v = u4 << 2;
+    const uint32_t k4 = u4 % Z4, ij = u4 / Z4, y = ij % Y, x = ij / Y;
+    const uchar4 mk = __ldg(reinterpret_cast<const uchar4*>(mask) + u4);
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mk.x | mk.y | mk.z | mk.w) {
+      const float* src = G + comp * V;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float ctr[4];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const uint32_t xx = min(max((int)x + a - 1, 0), (int)X - 1);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const uint32_t yy = min(max((int)y + b - 1, 0), (int)Y - 1);
+          const float* row = src + (xx * Y + yy) * Z + (k4 << 2);
+          const float4 m = ld4(row);
+          const float l = k4 > 0 ? __ldg(row - 1) : m.x, r = k4 < Z4 - 1 ? __ldg(row + 4) : m.w;   // replicate clamp
+          const float vals[6] = {l, m.x, m.y, m.z, m.w, r};
+          if (a == 1 && b == 1) { ctr[0] = m.x; ctr[1] = m.y; ctr[2] = m.z; ctr[3] = m.w; }
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += vals[q + c] * ker.w[(a * 3 + b) * 3 + c];
+        }
+      }
+      const unsigned char mq[4] = {mk.x, mk.y, mk.z, mk.w};
+      float dq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dq[q] = 0.f;
+        if (mq[q]) {
+          const float e = acc[q] - ctr[q];
+          local += e * e;
+          dq[q] = -2.f * scale * e;
+        }
+      }
+      d = make_float4(dq[0], dq[1], dq[2], dq[3]);
+    }
+    *reinterpret_cast<float4*>(dG + comp * V + v) = d;
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+
 __global__ void k_sum_partials(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
   __shared__ float red[32];
   float s = 0.f;
@@ -232,8 +388,10 @@ VX_API int vx_smooth_grad_tv(const float* G, const bool* mask, int X, int Y, int
   VX_REQUIRE(fill_kernel(ker, weight3_host, 3) == 0, "vx_smooth_grad_tv", "bad kernel");
   const int64_t n = (int64_t)X * Y * Z * 3;
   if (n <= 0) return 0;
-  const int blocks = grid_blocks(n);
-  k_smooth_grad_tv<<<blocks, 256, 0, st>>>(G, mask, X, Y, Z, ker, w_over_3n, dG, scratch);
+  const bool v4 = vec4_ok(X, Y, Z, 3, G, dG) && (reinterpret_cast<uintptr_t>(mask) & 3) == 0 && (n / 3) % 4 == 0;
+  const int blocks = grid_blocks(v4 ? n / 4 : n);
+  if (v4) k_smooth_grad_tv_v4<<<blocks, 256, 0, st>>>(G, mask, X, Y, Z, ker, w_over_3n, dG, scratch);
+  else k_smooth_grad_tv<<<blocks, 256, 0, st>>>(G, mask, X, Y, Z, ker, w_over_3n, dG, scratch);
   int rc = vx_check_launch("vx_smooth_grad_tv");
   if (rc) return rc;
   if (loss_out) {
@@ -289,11 +447,33 @@ VX_API int vx_total_variation_add_grad(const float* param, float* grad, const fl
   const int blocks = (int)((N + threads - 1) / threads);
   wx /= 6; wy /= 6; wz /= 6;  // :76-78
   const float w_fast = mask ? wx : wz, w_mid = wy, w_slow = wz;
+  if (!mask && dense_mode && N == sz_i * sz_j * sz_k && vec4_ok((int)sz_i, (int)sz_j, (int)sz_k, 1, param, grad)) {
+    k_sdf_reg_backward_v4<false, true><<<grid_blocks(N / 4), 256, 0, st>>>(nullptr, param, (uint32_t)sz_i, (uint32_t)sz_j,
+                                                                         (uint32_t)sz_k, 1.f, w_fast, w_mid, w_slow, grad);
+    return vx_check_launch("vx_total_variation_add_grad");
+  }
 #define VX_TV(D, M) k_total_variation_add_grad<D, M><<<blocks, threads, 0, st>>>(param, grad, mask, w_fast, w_mid, w_slow, (size_t)sz_i, (size_t)sz_j, (size_t)sz_k, (size_t)N)
   if (mask) { if (dense_mode) VX_TV(true, true); else VX_TV(false, true); }
   else { if (dense_mode) VX_TV(true, false); else VX_TV(false, false); }
 #undef VX_TV
   return vx_check_launch("vx_total_variation_add_grad");
+}
+
+// vx_fd_gradient_backward followed by the dense, unmasked vx_total_variation_add_grad of a single-channel grid, with one
+// read-modify-write of grad (the fine stage's two sdf regularisers, run.py:612-655).  Same result, bit for bit, as the
+// two separate calls.
+VX_API int vx_sdf_regularisers_backward(const float* dgrad, const float* param, int X, int Y, int Z, float voxel_size,
+                                        float wx, float wy, float wz, float* grad, cudaStream_t st) {
+  const int64_t V = (int64_t)X * Y * Z;
+  if (V <= 0) return 0;
+  if (vec4_ok(X, Y, Z, 3, dgrad, grad, param)) {
+    (void)wx;  // the reference's unmasked kernel routes wz to the fastest and the slowest axis (total_variation_kernel.cu:27-32)
+    k_sdf_reg_backward_v4<true, true><<<grid_blocks(V / 4), 256, 0, st>>>(dgrad, param, X, Y, Z, voxel_size, wz / 6, wy / 6, wz / 6, grad);
+    return vx_check_launch("vx_sdf_regularisers_backward");
+  }
+  int rc = vx_fd_gradient_backward(dgrad, X, Y, Z, voxel_size, grad, st);
+  if (rc) return rc;
+  return vx_total_variation_add_grad(param, grad, nullptr, wx, wy, wz, 1, X, Y, Z, V, st);
 }
 
 // ---------------------------------------------------------------------------------------------

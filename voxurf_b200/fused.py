@@ -29,13 +29,13 @@ import numpy as np
 import torch
 
 from ._lib import call
-from .mlp import FlatMLP
+from .mlp import FlatMLP, prepare_chains
 from .optim import _storage
 
 
 class FusedFineStep:
     def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0,
-                 tensor_core=True, sparse_k0_exchange=True):
+                 tensor_core=True, sparse_k0_exchange=True, sparse_adam=True):
         if model.k0_dim not in (6, 12):
             raise NotImplementedError('fused step: k0 channels must be 6 or 12')
         if model.k_center_sdf or not model.center_sdf or not model.k_res:
@@ -100,12 +100,23 @@ class FusedFineStep:
         self.sdf_grad = torch.zeros_like(m.sdf.grid)
         self.k0_grad = torch.zeros_like(m.k0.grid, memory_format=torch.preserve_format)
         m.sdf.grid.grad, m.k0.grid.grad = self.sdf_grad, self.k0_grad
+        # k0 bitmaps, one bit per voxel (channels-last: a voxel's C channels are contiguous).  touched: a gradient was
+        # scattered there this step; live: one ever was.  The k0 Adam pass skips the gradient read where untouched and
+        # the whole voxel where not live (m = v = g = 0: the dense update is the identity) -- same result, bit for bit,
+        # as utils.Adam over the dense grid (lib/utils.py:154-199), far less traffic.  Only the scatter kernels write
+        # k0 gradients in the fine stage (weight_tv_k0 = 0, configs/default_fine_s.py).
+        self.k0_touched = self.k0_live = None
+        if self.k0_cl and sparse_adam:
+            n_words = (self.X * self.Y * self.Z + 31) // 32
+            self.k0_touched = torch.zeros(n_words, dtype=torch.int32, device=dev)
+            self.k0_live = torch.zeros(n_words, dtype=torch.int32, device=dev)
         self.G = None       # FD gradient grid + its gradient, allocated on the first TV iteration
         self.smoothed = self.d_smoothed = None
         if m.smooth_sdf:
             self.smoothed, self.d_smoothed = torch.empty_like(m.sdf.grid), torch.zeros_like(m.sdf.grid)
         self.adam_state = {}
         self.adam_steps = 0
+        self.bitmap_probe = None   # bench.py: list collecting copies of (touched, live) as the k0 Adam launch sees them
         self.timings = None   # bench.py: list collecting (start, end) CUDA events around the k0 Adam launch
         if self.cfg is not None:
             c = self.cfg
@@ -166,9 +177,11 @@ class FusedFineStep:
         call('vx_fused_row_features', sdf_grid, _storage(m.k0.grid), X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(),
              self.idx4, n4, self.cap4, viewdirs, self.sdf_s, self.grad_s, m._voxel_size_host, int(m.use_grad_norm),
              self.P, self.Vp, self.P2, self.V2, self.disp, self.L, self.ld1, self.ld2, self.X1, self.X2)
-        self.mlp1.forward(self.X1, self.logit1, keep_activations=train, n_rows_dev=n4 if self.tensor_core else None)
+        if self.tensor_core:   # all weight images of both networks (forward + transposed dX chains) in one launch
+            prepare_chains(self.mlp1.chains(train) + self.mlp2.chains(train))
+        self.mlp1.forward(self.X1, self.logit1, keep_activations=train, n_rows_dev=n4 if self.tensor_core else None, prepared=True)
         call('vx_fused_fill_logit_cols', self.logit1, 3, n4, self.cap4, self.col_logit, self.ld2, self.X2)
-        self.mlp2.forward(self.X2, self.k_out, keep_activations=train, n_rows_dev=n4 if self.tensor_core else None)
+        self.mlp2.forward(self.X2, self.k_out, keep_activations=train, n_rows_dev=n4 if self.tensor_core else None, prepared=True)
         return s_val, n2, n4
 
     def _loss_cfg(self):
@@ -213,7 +226,7 @@ class FusedFineStep:
         call('vx_fused_row_backward', self._sdf_grid, X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(), self.idx4, n4,
              self.cap4, m._voxel_size_host, int(m.use_grad_norm), self.P, self.Vp, self.P2, self.V2, self.disp, self.L,
              self.ld1, self.ld2, self.dX1, self.dX2, self.d_sdf_s, self.d_grad_s, grad_target,
-             None if sparse_dp else _storage(self.k0_grad))
+             None if sparse_dp else _storage(self.k0_grad), None if sparse_dp else self.k0_touched)
         if sparse_dp:
             self._start_k0_exchange(n4)
         thres = float(m.fast_color_thres)
@@ -253,9 +266,11 @@ class FusedFineStep:
                 w.wait()
             xyz, g = self._k0_recv
             call('vx_grid_gather_backward', self.X, self.Y, self.Z, self.C, self.k0_cl, m._min_host, m._max_host, xyz, None, None,
-                 None, None, 0.0, None, xyz.shape[0], g, _storage(self.k0_grad))
+                 None, None, 0.0, None, xyz.shape[0], g, _storage(self.k0_grad), self.k0_touched)
         else:
             dist.all_reduce(_storage(self.k0_grad), op=dist.ReduceOp.AVG)
+            if self.k0_touched is not None:
+                self.k0_touched.fill_(-1)   # dense exchange: every voxel may carry a gradient
 
     def _sync_end(self):
         for w in self._works:
@@ -293,10 +308,16 @@ class FusedFineStep:
             w = c['weight_tv_density'] * tv['smooth_grad_tv'] / (3.0 * m._n_nonempty)
             call('vx_smooth_grad_tv', self.G, m.nonempty_mask[0, 0], X, Y, Z, m._tv_smooth_w, w, self.dG, self.tv_scratch, self.tv_loss)
             self.loss.add_(self.tv_loss)   # run.py:622-625 adds the regulariser to the reported loss
+        dense = global_step < c['tv_dense_before']
+        n_batch = global_batch or self.N * self.world
+        wt = c['weight_tv_density'] * tv['sdf_tv'] / n_batch * max(X, Y, Z) / 128
+        if tv['smooth_grad_tv'] > 0 and tv['sdf_tv'] > 0 and dense:
+            # both regularisers land in the sdf gradient with one read-modify-write
+            call('vx_sdf_regularisers_backward', self.dG, m.sdf.grid, X, Y, Z, m._voxel_size_host, wt, wt, wt, self.sdf_grad)
+            return
+        if tv['smooth_grad_tv'] > 0:
             call('vx_fd_gradient_backward', self.dG, X, Y, Z, m._voxel_size_host, self.sdf_grad)
         if tv['sdf_tv'] > 0:
-            n_batch = global_batch or self.N * self.world
-            wt = c['weight_tv_density'] * tv['sdf_tv'] / n_batch * max(X, Y, Z) / 128
             call('vx_total_variation_add_grad', m.sdf.grid, self.sdf_grad, None, wt, wt, wt,
                  int(global_step < c['tv_dense_before']), X, Y, Z, m.sdf.grid.numel())
 
@@ -321,11 +342,21 @@ class FusedFineStep:
                 if timed:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                     ev[0].record()
+                touched, live = (self.k0_touched, self.k0_live) if name == 'k0' else (None, None)
+                if touched is not None and self.bitmap_probe is not None:
+                    self.bitmap_probe.append((touched.clone(), live.clone()))
                 call('vx_adam_step', _storage(p.data), _storage(p.grad), _storage(st[0]), _storage(st[1]), None, p.numel(),
-                     beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1)
+                     beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1, touched, live, self.C)
+                if touched is not None:
+                    call('vx_bitmap_merge', live, touched, touched.numel())
                 if timed:
                     ev[1].record()
                     self.timings.append(ev)
+
+    def mark_all_live(self):
+        """Call after loading optimizer moments from elsewhere: every voxel may then hold non-zero exp_avg / exp_avg_sq."""
+        if self.k0_live is not None:
+            self.k0_live.fill_(-1)
 
     def step(self, rays_o, rays_d, viewdirs, target, global_step, grad_sync=None):
         """One training iteration (run.py:600-659).  grad_sync: optional callable run between backward and TV/Adam."""

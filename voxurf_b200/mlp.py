@@ -70,17 +70,21 @@ class FlatMLP:
         self.H = [torch.empty(cap, l.out_features, dtype=torch.float32, device=dev) for l in self.linears[:-1]]
         self.dH = [torch.empty_like(h) for h in self.H]
 
-    def forward(self, X, out, keep_activations=True, n_rows_dev=None):
-        """X (cap, ld_in) -> out (cap, 3).  Hidden activations stay in self.H for the backward pass."""
+    def chains(self, train=True):
+        return [self.tc_fwd, self.tc_bwd] if train else [self.tc_fwd]
+
+    def forward(self, X, out, keep_activations=True, n_rows_dev=None, prepared=False):
+        """X (cap, ld_in) -> out (cap, 3).  Hidden activations stay in self.H for the backward pass.
+        prepared: the caller already refreshed the weight images of self.chains(keep_activations) (prepare_chains)."""
         if self.H is None or getattr(self, 'cap', None) != X.shape[0]:
             self.alloc(X.shape[0])
         self._X = X
         if self.tensor_core:
             assert n_rows_dev is not None
             self._n = n_rows_dev
-            self.tc_fwd.prepare()   # the optimizer changed the weights since the last step
+            if not prepared:   # the optimizer changed the weights since the last step
+                prepare_chains(self.chains(keep_activations))
             if keep_activations:
-                self.tc_bwd.prepare()
                 self.tc_fwd.run(X, self.ld_in, n_rows_dev, out, out.shape[1], imgs=self.H_img, x_img=self.X_img)
             else:
                 self.tc_fwd.run(X, self.ld_in, n_rows_dev, out, out.shape[1])
@@ -131,6 +135,18 @@ def _pad(v, m):
     return (v + m - 1) // m * m
 
 
+def prepare_chains(chains):
+    """(Re)write the hi/lo TF32 weight images of several chains with one launch per 16 layers (vx_mlp_prep_batch)."""
+    from ._lib import call
+    ptrs, dims = [], []
+    for c in chains:
+        p, d = c.prep_jobs()
+        ptrs += p; dims += d
+    for j in range(0, len(ptrs) // 3, 16):
+        n = min(16, len(ptrs) // 3 - j)
+        call('vx_mlp_prep_batch', n, ptrs[3 * j:3 * (j + n)], dims[6 * j:6 * (j + n)])
+
+
 class TensorCoreChain:
     """A chain of up to 4 dense layers executed by one fused tcgen05 kernel launch (vx_mlp_chain).
 
@@ -155,12 +171,17 @@ class TensorCoreChain:
         self.W_hi = [torch.zeros(self.Np[i], self.Kp[i], dtype=torch.float32, device=dev) for i in range(n)]
         self.W_lo = [torch.zeros_like(w) for w in self.W_hi]
 
-    def prepare(self):
+    def prep_jobs(self):
+        ptrs, dims = [], []
         for i, L in enumerate(self.layers):
             W = L['W']
             assert W.stride(1) == 1
-            self._call('vx_mlp_prep', W, self.N[i], self.K[i], W.stride(0), self.Np[i], self.Kp[i], int(self.transpose),
-                       self.W_hi[i], self.W_lo[i])
+            ptrs += [W.data_ptr(), self.W_hi[i].data_ptr(), self.W_lo[i].data_ptr()]
+            dims += [self.N[i], self.K[i], W.stride(0), self.Np[i], self.Kp[i], int(self.transpose)]
+        return ptrs, dims
+
+    def prepare(self):
+        prepare_chains([self])
 
     def run(self, X, k0, n_rows_dev, Y, n_out, imgs=None, masks=None, x_img=None):
         """X (cap, ldx) with k0 valid columns -> Y (cap, ldy)[:, :n_out].  imgs[l] = (hi, lo) CH(Np) images written for

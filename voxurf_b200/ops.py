@@ -51,7 +51,7 @@ class _GridGather(torch.autograd.Function):
         gg = torch.empty(shape, dtype=torch.float32, device=xyz.device,
                          memory_format=torch.channels_last_3d if cl else torch.contiguous_format).zero_()
         call('vx_grid_gather_backward', X, Y, Z, C, cl, xyz_min, xyz_max, xyz, None, None, None, None, 0.0, None,
-             xyz.shape[0], grad_out.contiguous(), _dense_storage(gg))
+             xyz.shape[0], grad_out.contiguous(), _dense_storage(gg), None)
         return gg, None, None, None
 
 
