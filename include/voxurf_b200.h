@@ -265,14 +265,26 @@ int vx_mlp_prep(const float* W, int N, int K, int ldw, int Np, int Kp, int trans
 int vx_mlp_prep_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, cudaStream_t stream);
 /* Y = chain of up to 4 layers y = act(x W^T + b) [* (mask > 0)] on 128-row tiles.  Packed host arrays (csrc/mlp_tc.cu):
  * ptrs_host[l*5..] = W_hi, W_lo, bias, row image out, mask row image (device addresses, 0 = none);
- * dims_host[l*4..] = Kp, Np, N, relu.  Row images ACT(F) (raw fp32, r = MLP row) feed vx_mlp_dw. */
+ * dims_host[l*4..] = Kp, Np, N, relu.  Row images ACT(F) (raw fp32, r = MLP row, F = feature count padded to 32; byte offset
+ * (r/4)*16F + (f/32)*512 + (r%4)*128 + (((f%32)/8) ^ (r%4))*32 + (f%8)*4 -- the MN-major TF32 UMMA operand layout) feed
+ * vx_mlp_dw; x_img is the ACT(pad32(Kp[0])) image of the input. */
 int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, int capacity, int n_layers,
                  const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* x_img,
                  cudaStream_t stream);
 /* split-K weight gradient on the row images: C[m][n] += sum_r A[r][m] B[r][n], c_bias[m] += sum_r A[r][m]
- * (r < *n_rows_dev, m < M_out <= FA, n < N_in <= FB) */
+ * (r < *n_rows_dev, m < M_out <= FA, n < N_in <= FB; FA, FB multiples of 32; image rows past *n_rows_dev up to the next
+ * multiple of 16 must hold zeros) */
 int vx_mlp_dw(const float* A_img, int FA, int M_out, const float* B_img, int FB, int N_in, const int* n_rows_dev,
               int capacity, float* C, int ldc, float* c_bias, cudaStream_t stream);
+/* up to 8 vx_mlp_dw GEMMs (same row count) in one launch, the SMs dealt in proportion to each job's cost:
+ * ptrs_host[j*4..] = A_img, B_img, C, c_bias (device addresses, c_bias may be 0); dims_host[j*5..] = FA, M_out, FB, N_in, ldc */
+int vx_mlp_dw_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
+                    cudaStream_t stream);
+
+/* development probe: one M = 128, K = 8 TF32 tcgen05.mma on caller-laid-out shared-memory operand images (<= 32 KB each)
+ * with caller-chosen descriptor fields; used by tests/test_gpu_mlp.py to pin the operand layouts the kernels rely on */
+int vx_umma_probe(const float* A_img, int a_floats, const float* B_img, int b_floats, int64_t desc_a_fields,
+                  int64_t desc_b_fields, int64_t idesc, int N, float* D, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

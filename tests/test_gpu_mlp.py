@@ -25,14 +25,24 @@ def rel(a, b):
     return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-300))
 
 
+def act_index(R, F, device=DEV):
+    """float index of element (r, f) in the ACT(F) row image (csrc/mlp_tc.cu act_offset): 4-row x 32-feature atoms,
+    every row a 128-byte line whose 32-byte pieces are XOR-permuted with r % 4"""
+    r = torch.arange(R, device=device).view(R, 1)
+    f = torch.arange(F, device=device).view(1, F)
+    return ((r // 4) * (F // 32) + f // 32) * 128 + (r % 4) * 32 + ((((f % 32) // 8) ^ (r % 4)) * 8) + f % 8
+
+
 def unpack(img, F, n_rows):
-    """ACT row image [r/8][f/4][r%8][f%4] -> (n_rows, F)"""
-    return img.view(-1, F // 4, 8, 4).permute(0, 2, 1, 3).reshape(-1, F)[:n_rows]
+    R = img.numel() // F
+    return img[act_index(R, F, img.device).reshape(-1)].view(R, F)[:n_rows]
 
 
 def pack(V):
     R, F = V.shape
-    return V.view(R // 8, 8, F // 4, 4).permute(0, 2, 1, 3).contiguous().view(-1)
+    img = torch.empty(R * F, device=V.device)
+    img[act_index(R, F, V.device).reshape(-1)] = V.reshape(-1)
+    return img
 
 
 @pytest.mark.parametrize('d_in,ld,cap,n_rows', [(79, 80, 2048, 1999), (54, 64, 2048, 1), (60, 64, 640, 640),
@@ -119,8 +129,8 @@ def test_flat_mlp_eval_forward_matches_cublas_path():
     assert rel(o[0], o[1].double()) < 5e-6
 
 
-@pytest.mark.parametrize('R,FA,M_out,FB,N_in', [(64, 16, 16, 16, 16), (256, 192, 192, 192, 192), (1024, 8, 3, 192, 192),
-                                                 (4096, 192, 192, 80, 80), (43008, 192, 192, 192, 192), (4096, 192, 192, 64, 54)])
+@pytest.mark.parametrize('R,FA,M_out,FB,N_in', [(64, 32, 16, 32, 16), (256, 192, 192, 192, 192), (1024, 32, 3, 192, 192),
+                                                 (4096, 192, 192, 96, 80), (43008, 192, 192, 192, 192), (4096, 192, 192, 64, 54)])
 def test_mlp_dw_direct(R, FA, M_out, FB, N_in):
     """vx_mlp_dw on packed row images: C += A^T B, c_bias += A^T 1 over the first *n_rows rows."""
     from voxurf_b200._lib import call
@@ -154,3 +164,43 @@ def test_mlp_prep_images():
         assert (h[N:] == 0).all() and (h[:, K:] == 0).all() and (l[N:] == 0).all() and (l[:, K:] == 0).all()
         assert ((h[:N, :K].view(torch.int32) & 0x1fff) == 0).all()
         assert ((h + l)[:N, :K] - L).abs().max() <= 2.0 ** -21 * L.abs().max()
+
+
+def test_mlp_dw_batch_matches_single_jobs():
+    """vx_mlp_dw_batch (8 GEMMs of different shapes in one launch, SMs dealt by cost) == the GEMMs one by one."""
+    from voxurf_b200._lib import call
+    torch.manual_seed(11)
+    R, n_rows = 6144, 6001
+    shapes = [(32, 3, 192, 192), (192, 192, 192, 192), (192, 192, 192, 192), (192, 192, 96, 79),
+              (32, 3, 192, 192), (192, 192, 192, 192), (192, 192, 192, 192), (192, 192, 64, 54)]
+    n = torch.tensor([n_rows], dtype=torch.int32, device=DEV)
+    ptrs, dims, keep, refs = [], [], [], []
+    for FA, M_out, FB, N_in in shapes:
+        dY = torch.randn(R, FA, device=DEV); H = torch.randn(R, FB, device=DEV)
+        dY[:, M_out:] = 0; H[:, N_in:] = 0; dY[n_rows:] = 0; H[n_rows:] = 0
+        A, B = pack(dY), pack(H)
+        C = torch.zeros(M_out, N_in, device=DEV); cb = torch.zeros(M_out, device=DEV)
+        keep.append((A, B, C, cb))
+        ptrs += [A.data_ptr(), B.data_ptr(), C.data_ptr(), cb.data_ptr()]
+        dims += [FA, M_out, FB, N_in, C.stride(0)]
+        refs.append((dY[:, :M_out].double().t() @ H[:, :N_in].double(), dY[:, :M_out].double().sum(0)))
+    call('vx_mlp_dw_batch', len(shapes), ptrs, dims, n, R)
+    for (A, B, C, cb), (rC, rb) in zip(keep, refs):
+        assert rel(C, rC) < 2e-5 and rel(cb, rb) < 2e-5
+
+
+def test_umma_mn_major_tf32_operand_layout():
+    """Pins the operand layout the row images rely on: one M = 128, K = 8 TF32 MMA (vx_umma_probe) with A and B read
+    MN-major through layout type 1 from images built with act_index()."""
+    from voxurf_b200._lib import call
+    torch.manual_seed(2)
+    N = 64
+    A = torch.randint(-8, 9, (8, 128)).float()     # [k][m]: exactly representable in TF32
+    B = torch.randint(-8, 9, (8, N)).float()       # [k][n]
+    a_img = torch.zeros(8192, device=DEV); b_img = torch.zeros(8192, device=DEV)
+    a_img[:8 * 128] = pack(A.to(DEV)); b_img[:8 * N] = pack(B.to(DEV))
+    desc = lambda lbo, sbo: ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1 << 46) | (1 << 61)
+    idesc = (1 << 4) | (2 << 7) | (2 << 10) | (1 << 15) | (1 << 16) | ((N >> 3) << 17) | ((128 >> 4) << 24)
+    D = torch.zeros(128, N, device=DEV)
+    call('vx_umma_probe', a_img, 8192, b_img, 8192, desc(512, 16 * 128), desc(512, 16 * N), idesc, N, D)
+    assert torch.equal(D.cpu(), A.t() @ B)

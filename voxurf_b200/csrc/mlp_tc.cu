@@ -13,15 +13,16 @@
 //   * weights (hi/lo images prepared once per optimizer step by k_mlp_prep) are streamed from L2 in K=32 slices by
 //     ONE producer thread with bulk async copies (cp.async.bulk + mbarrier complete_tx) into a double-buffered ring that
 //     runs ahead across layers and tiles; one thread issues the MMAs and frees ring slots with tcgen05.commit;
-//   * the hidden activations are also written to HBM as pre-split hi/lo "chunked K-major images" [row/4][feature][row%4]
-//     -- exactly the operand layout of the split-K weight-gradient GEMM (k_mlp_dw), which then needs no staging at all.
+//   * the activations (and, in the dX chain, their gradients) are also written to HBM as raw fp32 "row images" in the
+//     MN-major 32-byte-swizzled UMMA operand layout, which the split-K weight-gradient GEMM (k_mlp_dw) reads with plain
+//     bulk copies: no transposition anywhere.
 // The row count is read from device memory (sync-free pipeline); rows past it are computed as zeros.
 #include "common.cuh"
 
 #define MLP_ROWS 128
 #define MLP_MAXW 192          // max layer width (N and K)
 #define MLP_STAGES 2
-#define MLP_SLICE_K 32        // K extent of one weight slice in the cp.async ring (4 MMA K-steps)
+#define MLP_SLICE_K 32        // K extent of one weight slice in the bulk-copy ring (4 MMA K-steps); a 5 x K=16 ring measured 10 % slower
 #define MLP_MAX_LAYERS 4
 #define MLP_TMEM_COLS 512     // D accumulator at column 0, A (hi) operand at column 256
 #define MLP_TMEM_A 256
@@ -142,8 +143,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
 
+// MN-major TF32 operand: layout type 1 (128-byte swizzle, 32-byte base) -- with any other layout type an MN-major TF32
+// MMA accumulates nothing (measured).  LBO = bytes between 32-element MN groups, SBO = bytes between 4-element K groups.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);
+}
+
 // instruction descriptor: D fp32, A/B TF32, both K-major, M = 128
-// (both operands K-major: measured on B200, tcgen05.mma.kind::tf32 with an MN-major smem operand accumulates nothing)
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -155,6 +161,12 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(r);
 }
 
+// the same rounding (nearest, ties away from zero) in two integer instructions, for finite inputs: the cvt above is
+// expanded by ptxas into add + mask + an Inf/NaN guard, which the hot loops below do not need
+__device__ __forceinline__ float tf32_rn(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 // ---------------------------------------------------------------------------------------------
 // "Chunked K-major image" CH(F) of a matrix V[k][f] (k = reduction index, f = feature / row of the operand):
 //     IMG[(k / 4) * F + f][k % 4]
@@ -162,13 +174,21 @@ __device__ __forceinline__ float tf32_hi(float x) {
 // contiguous block of 8 * F * 16 bytes, so one bulk copy brings a whole operand slice into shared memory.
 // Weights: k = input feature, f = output feature.
 //
-// Activations / activation gradients go to HBM as ONE raw fp32 "row image" per tensor,
-//     ACT[((r / 8) * (F / 4) + f / 4) * 8 + r % 8][f % 4]        (r = MLP row, f = feature)
-// chosen for the writer: the epilogue thread (= one MLP row) stores whole float4s and a warp store covers 4 x 128
-// contiguous bytes; a 32-row slice is one contiguous block of F * 128 bytes (one bulk copy).  The weight-gradient
-// GEMM reduces over r, so its operands must be K-major in r (the tensor core does not take MN-major TF32 operands):
-// k_mlp_dw transposes + hi/lo-splits each slice on chip with its otherwise idle threads.
+// Activations / activation gradients go to HBM as ONE raw fp32 "row image" ACT(F) per tensor (r = MLP row, f = feature,
+// F a multiple of 32), byte offset
+//     (r / 4) * 16 F  +  (f / 32) * 512  +  (r % 4) * 128  +  (((f % 32) / 8) ^ (r % 4)) * 32  +  (f % 8) * 4
+// i.e. 4-row x 32-feature atoms of 512 bytes; inside an atom every row is one 128-byte line whose four 32-byte
+// pieces are XOR-permuted with the row number.  This is exactly what tcgen05.mma.kind::tf32 reads as an MN-major
+// operand (shared-memory descriptor layout type 1, "128B swizzle with 32B base", the only MN-major layout TF32 has;
+// LBO = 512 between 32-feature groups, SBO = 16 F between 4-row groups; measured with vx_umma_probe,
+// scripts/probe_umma.py): the weight-gradient GEMM reduces over r, so for it a slice of 16 rows (one contiguous block
+// of 64 F bytes, one bulk copy) is a ready-made operand.  It also suits the writer: an epilogue thread (= one MLP
+// row) stores 8 consecutive features as one aligned 32-byte piece.
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int64_t act_offset(int64_t r, int f, int F) {   // in floats
+  return ((r >> 2) * (F >> 5) + (f >> 5)) * 128 + (r & 3) * 32 + ((((f & 31) >> 3) ^ (int)(r & 3)) << 3) + (f & 7);
+}
+
 struct MlpPrepJob {
   const float* W;
   float *W_hi, *W_lo;
@@ -252,15 +272,14 @@ __device__ __forceinline__ void store_a8(MlpSmem& s, uint32_t tmem_a_lane, int r
                                          float* __restrict__ img, int F, int64_t row) {
   float hi[8], lo[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { hi[j] = tf32_hi(v[j]); lo[j] = tf32_hi(v[j] - hi[j]); }
+  for (int j = 0; j < 8; ++j) { hi[j] = tf32_rn(v[j]); lo[j] = tf32_rn(v[j] - hi[j]); }
   tmem_st8(tmem_a_lane + c0, hi);
 #pragma unroll
   for (int q = 0; q < 2; ++q)
     reinterpret_cast<float4*>(s.A_lo)[((c0 >> 2) + q) * MLP_ROWS + row_in_tile] = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-  if (img) {
-    const int64_t q0 = ((row >> 3) * (F >> 2) + (c0 >> 2)) * 8 + (row & 7);   // float4 index of feature quad c0/4
-    reinterpret_cast<float4*>(img)[q0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(img)[q0 + 8] = make_float4(v[4], v[5], v[6], v[7]);
+  if (img) {   // one aligned 32-byte piece, one 256-bit store
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(img + act_offset(row, c0, F)), "f"(v[0]),
+                 "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
   }
 }
 
@@ -318,22 +337,33 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
       {
         const bool vec = (ldx % 4 == 0);
         const float* src = X + (int64_t)row * ldx;
-        for (int c0 = half * 8; c0 < K0p; c0 += 16) {
-          float v[8];
+        // this thread's share of the row, six 8-float pieces at a time: all loads are issued before the first use, so
+        // the tile pays one memory latency instead of one per piece
+        for (int cbase = half * 8; cbase < K0p; cbase += 16 * 6) {
+          float v[6][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          if (row < n_rows) {
-            if (vec && c0 + 8 <= K0) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(src + c0));
-              const float4 b2 = __ldg(reinterpret_cast<const float4*>(src + c0 + 4));
-              v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b2.x; v[5] = b2.y; v[6] = b2.z; v[7] = b2.w;
-            } else {
+          for (int u = 0; u < 6; ++u) {
+            const int c0 = cbase + 16 * u;
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (c0 + j < K0) v[j] = __ldg(src + c0 + j);
+            for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+            if (c0 < K0p && row < n_rows) {
+              if (vec && c0 + 8 <= K0) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src + c0));
+                const float4 b2 = __ldg(reinterpret_cast<const float4*>(src + c0 + 4));
+                v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+                v[u][4] = b2.x; v[u][5] = b2.y; v[u][6] = b2.z; v[u][7] = b2.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (c0 + j < K0) v[u][j] = __ldg(src + c0 + j);
+              }
             }
           }
-          store_a8(s, lane_addr + MLP_TMEM_A, rt, c0, v, x_img, K0p, row);
+#pragma unroll
+          for (int u = 0; u < 6; ++u) {
+            const int c0 = cbase + 16 * u;
+            if (c0 < K0p) store_a8(s, lane_addr + MLP_TMEM_A, rt, c0, v[u], x_img, (K0p + 31) & ~31, row);
+          }
         }
         tmem_st_wait();
       }
@@ -377,7 +407,19 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
         const bool last = (l == ch.n_layers - 1);
         if (!last) {
           for (int c0 = half * 32; c0 < Np; c0 += 64) {
-            float v[32];
+            float v[32], mk[32];
+            const bool gate = L.mask && row < n_rows;
+            if (gate) {
+              // ReLU gates of the 32 features [c0, c0 + 32) of this row: one 128-byte line of the forward row image
+              // (32-byte pieces permuted), four 256-bit loads issued ahead of the TMEM load they are applied to
+              const float* line = L.mask + act_offset(row, c0, Np) - ((((c0 & 31) >> 3) ^ (row & 3)) << 3);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=f"(mk[8 * q]), "=f"(mk[8 * q + 1]), "=f"(mk[8 * q + 2]), "=f"(mk[8 * q + 3]), "=f"(mk[8 * q + 4]),
+                               "=f"(mk[8 * q + 5]), "=f"(mk[8 * q + 6]), "=f"(mk[8 * q + 7])
+                             : "l"(line + ((q ^ (row & 3)) << 3)));
+            }
             tmem_ld32(lane_addr + c0, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -385,16 +427,10 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
               if (L.relu) y = fmaxf(y, 0.f);
               v[j] = y;
             }
-            if (L.mask && row < n_rows) {
-              const float4* mk = reinterpret_cast<const float4*>(L.mask) + (((int64_t)row >> 3) * (Np >> 2) + (c0 >> 2)) * 8 + (row & 7);
+            if (gate) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 m4 = __ldg(mk + 8 * q);
-                if (!(m4.x > 0.f)) v[4 * q] = 0.f;
-                if (!(m4.y > 0.f)) v[4 * q + 1] = 0.f;
-                if (!(m4.z > 0.f)) v[4 * q + 2] = 0.f;
-                if (!(m4.w > 0.f)) v[4 * q + 3] = 0.f;
-              }
+              for (int j = 0; j < 32; ++j)
+                if (!(mk[j] > 0.f)) v[j] = 0.f;
             }
             if (row >= n_rows) {
 #pragma unroll
@@ -469,143 +505,191 @@ VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Split-K weight-gradient GEMM on the row images:  C[m][n] += sum_r A[r][m] * B[r][n]   (dW = dY^T H, db = dY^T 1)
-// A = ACT(FA) row image of dY (m < M_out <= FA), B = ACT(FB) row image of H (n < N_in <= FB).  Per 32-row slice:
-//   1. thread 0 bulk-copies the two raw slices (F * 128 bytes each) into shared memory;
-//   2. all 128 threads transpose + hi/lo-split them into four K-major operand tiles (reduction index = MLP row).
-//      Reads are consecutive float4s; the scalar writes are bank-conflict free because the operand tiles are padded
-//      through the descriptor strides (SBO = 144 B between 8-feature groups, LBO = F/8 * 144 + 32 B between 4-row chunks);
-//   3. thread 0 issues the MMAs: both 128-row M tiles (features 0..127 / 128..255) into two TMEM accumulators, plus
-//      two N = 16 MMAs against a constant ones tile whose first column gives the bias gradient.
-// Slices are dealt round-robin to the CTAs (split-K); partial sums leave as vector atomics.
+// Split-K weight-gradient GEMMs on the row images:  C[m][n] += sum_r A[r][m] * B[r][n]   (dW = dY^T H, db = dY^T 1)
+// A = ACT(FA) row image of dY (m < M_out <= FA), B = ACT(FB) row image of H (n < N_in <= FB).
+// One launch runs up to 8 such GEMMs (all layers of both colour networks): the CTAs are dealt to the jobs in
+// proportion to their cost and every CTA walks its job's 16-row slices round-robin through a three-role pipeline
+//   warp 13 lane 0  producer : bulk-copies the raw A / B slices (64 F bytes each) into a 6-deep ring;
+//   warps 0-11      split a slice element-wise (hi in place, lo into a twin buffer; 128-bit loads / stores) -- the row
+//                   image already is the MN-major operand layout, nothing is transposed;
+//   warp 12 lane 0  issues the MMAs of a slice, both operands MN-major (instruction-descriptor bits 15 / 16): both
+//                   128-row M tiles (features 0..127 / 128..255) into two TMEM accumulators, plus N = 16 MMAs against
+//                   a constant K-major ones tile whose first column is the bias gradient; tcgen05.commit hands the
+//                   stage back to the producer.
+// Partial sums leave as vector atomics (warps 0-3).
 // ---------------------------------------------------------------------------------------------
-#define DW_KC 32
-#define DW_THREADS 384                                          // 12 warps transpose; warps 0-3 also run the TMEM epilogue
-#define DW_SBO 144                                              // bytes between 8-feature groups of an operand tile
-#define DW_TILE_BYTES(F) (8 * (((F) >> 3) * DW_SBO + 32))       // 8 four-row chunks
-struct __align__(16) DwSmem {
-  float raw[2][DW_KC * MLP_MAXW];                               // bulk-copy landing zone: A slice, B slice (24 KB each)
-  uint8_t op[4][DW_TILE_BYTES(MLP_MAXW) + 2048];                // A_hi, A_lo, B_hi, B_lo operand tiles (+ slack: M tile 1 over-read)
-  float ones[2 * 16 * 4];                                       // K-major [2 chunks][16 features][4 rows]: feature 0 = 1
-  uint64_t bar_full;
-  uint64_t bar_mma;
+#define DW_KC 16
+#define DW_T_THREADS 384                                        // 12 splitting warps; warps 0-3 also run the TMEM epilogue
+#define DW_THREADS (DW_T_THREADS + 64)                          // + MMA warp + producer warp
+#define DW_MAX_JOBS 8
+struct DwJob {
+  const float* A;
+  const float* B;
+  float* C;
+  float* c_bias;
+  int FA, M_out, FB, N_in, ldc;
+  int cta_begin, cta_count;
+};
+struct DwBatch {
+  int n_jobs;
+  DwJob job[DW_MAX_JOBS];
+};
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+#define DW_RAW_STAGES 6      // raw slices in flight (hi parts are produced in place): covers the HBM latency
+#define DW_LO_STAGES 2       // lo twins only live from the split to the MMAs of a slice
+struct __align__(16) DwmSmem {
+  float raw[DW_RAW_STAGES][2][DW_KC * MLP_MAXW];                // A slice, B slice (raw -> hi), 12 KB each
+  float lo[DW_LO_STAGES][2][DW_KC * MLP_MAXW];                  // A_lo, B_lo
+  float slack[1024];                                            // M tile 1 over-reads up to 2 KB past the last slice
+  float ones[2 * 16 * 4];
+  uint64_t full[DW_RAW_STAGES], empty[DW_RAW_STAGES];
+  uint64_t split[DW_LO_STAGES], lo_empty[DW_LO_STAGES];
   uint64_t bar_acc;
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void dw_transpose(const float* __restrict__ raw, int F, uint8_t* __restrict__ op_hi,
-                                             uint8_t* __restrict__ op_lo, int tid) {
-  const int quads = F >> 2;                       // feature quads per row
-  const uint32_t lbo = (uint32_t)(F >> 3) * DW_SBO + 32;
-  const int n4 = DW_KC * quads;                   // float4s in the slice
-  // float4 idx = ((g * quads + q) * 8 + r8): consecutive threads read consecutive float4s; (g, q) advance incrementally
-  const int r8 = tid & 7;
-  int q = tid >> 3, g = 0;
-  while (q >= quads) { q -= quads; ++g; }
-  if (g >= DW_KC / 8) return;
-  const uint32_t row_off = (uint32_t)(r8 >> 2) * lbo + (uint32_t)(r8 & 3) * 4;   // chunk parity + row within the 4-row chunk
-  for (int idx = tid; idx < n4; idx += DW_THREADS) {
-    const float4 x = reinterpret_cast<const float4*>(raw)[idx];
-    const int f = 4 * q;
-    const uint32_t base = (uint32_t)(2 * g) * lbo + row_off + (uint32_t)(f >> 3) * DW_SBO + (uint32_t)(f & 7) * 16;
-    const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float h = tf32_hi(xs[t]);
-      *reinterpret_cast<float*>(op_hi + base + t * 16) = h;
-      *reinterpret_cast<float*>(op_lo + base + t * 16) = tf32_hi(xs[t] - h);
-    }
-    q += DW_THREADS / 8;
-    while (q >= quads) { q -= quads; ++g; }
-  }
+__device__ __forceinline__ uint32_t make_idesc_tf32_major(int M, int N, int a_mn, int b_mn) {
+  return make_idesc_tf32(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+
+__device__ __forceinline__ void dw_split4(float4* __restrict__ hi, float4* __restrict__ lo, int idx, const float4 x) {
+  const float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+  hi[idx] = h;
+  lo[idx] = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
 }
 
 __global__ void __launch_bounds__(DW_THREADS, 1)
-k_mlp_dw(const float* __restrict__ A_img, int FA, int M_out, const float* __restrict__ B_img, int FB, int N_in,
-         const int* __restrict__ n_rows_dev, int capacity, float* __restrict__ C, int ldc, float* __restrict__ c_bias) {
+k_mlp_dw(const __grid_constant__ DwBatch batch, const int* __restrict__ n_rows_dev, int capacity) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  DwSmem& s = *reinterpret_cast<DwSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  DwmSmem& s = *reinterpret_cast<DwmSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int ji = 0;
+  while (ji + 1 < batch.n_jobs && (int)blockIdx.x >= batch.job[ji].cta_begin + batch.job[ji].cta_count) ++ji;
+  const DwJob& J = batch.job[ji];
+  const int cta = (int)blockIdx.x - J.cta_begin, n_cta = J.cta_count;
+  const int FA = J.FA, FB = J.FB;
   const int n_rows = min(*n_rows_dev, capacity);
   const int n_slices = (n_rows + DW_KC - 1) / DW_KC;
-  const int m_tiles = (M_out + MLP_ROWS - 1) / MLP_ROWS;
+  const int m_tiles = (J.M_out + MLP_ROWS - 1) / MLP_ROWS;
   if (tid == 0) {
-    mbar_init(&s.bar_full, 1); mbar_init(&s.bar_mma, 1); mbar_init(&s.bar_acc, 1);
+    for (int i = 0; i < DW_RAW_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < DW_LO_STAGES; ++i) { mbar_init(&s.split[i], DW_T_THREADS); mbar_init(&s.lo_empty[i], 1); }
+    mbar_init(&s.bar_acc, 1);
     fence_barrier_init();
   }
-  if (tid < 128) s.ones[tid] = ((tid >> 2) % 16 == 0) ? 1.f : 0.f;   // [chunk][feature][row]: feature 0 of both chunks
+  if (tid < 128) s.ones[tid] = ((tid >> 2) % 16 == 0) ? 1.f : 0.f;   // K-major [chunk][feature][row]: feature 0 of both chunks
   if (warp == 0) tmem_alloc(&s.tmem_base, MLP_TMEM_COLS);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-  const int my_slices = (n_slices > (int)blockIdx.x) ? (n_slices - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int my_slices = (n_slices > cta) ? (n_slices - 1 - cta) / n_cta + 1 : 0;
   const uint32_t a_bytes = DW_KC * FA * 4, b_bytes = DW_KC * FB * 4;
-  const uint32_t a_lbo = (uint32_t)(FA >> 3) * DW_SBO + 32, b_lbo = (uint32_t)(FB >> 3) * DW_SBO + 32;
-  auto issue_load = [&](int i) {
-    const int64_t sl = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
-    mbar_expect_tx(&s.bar_full, a_bytes + b_bytes);
-    bulk_g2s(s.raw[0], A_img + sl * DW_KC * FA, a_bytes, &s.bar_full);
-    bulk_g2s(s.raw[1], B_img + sl * DW_KC * FB, b_bytes, &s.bar_full);
-  };
-  if (tid == 0 && my_slices > 0) issue_load(0);
-  for (int i = 0; i < my_slices; ++i) {
-    mbar_wait(&s.bar_full, i & 1);                           // raw slices of step i landed
-    if (i > 0) mbar_wait(&s.bar_mma, (i - 1) & 1);           // MMAs of step i-1 finished reading the operand tiles
-    dw_transpose(s.raw[0], FA, s.op[0], s.op[1], tid);
-    dw_transpose(s.raw[1], FB, s.op[2], s.op[3], tid);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      if (i + 1 < my_slices) issue_load(i + 1);              // raw buffers are free again: overlaps with the MMAs below
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_tf32(MLP_ROWS, FB);
-      const uint32_t idesc1 = make_idesc_tf32(MLP_ROWS, 16);
-      for (int mt = 0; mt < m_tiles; ++mt) {
+
+  if (warp == DW_T_THREADS / 32 + 1) {
+    // ===== producer =====
+    if (lane == 0)
+      for (int i = 0; i < my_slices; ++i) {
+        const int st = i % DW_RAW_STAGES;
+        if (i >= DW_RAW_STAGES) mbar_wait(&s.empty[st], (i / DW_RAW_STAGES - 1) & 1);
+        const int64_t sl = (int64_t)cta + (int64_t)i * n_cta;
+        mbar_expect_tx(&s.full[st], a_bytes + b_bytes);
+        bulk_g2s(s.raw[st][0], J.A + sl * DW_KC * FA, a_bytes, &s.full[st]);
+        bulk_g2s(s.raw[st][1], J.B + sl * DW_KC * FB, b_bytes, &s.full[st]);
+      }
+  } else if (warp == DW_T_THREADS / 32) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_major(MLP_ROWS, FB, 1, 1);
+      const uint32_t idesc1 = make_idesc_tf32_major(MLP_ROWS, 16, 1, 0);
+      const uint64_t d_ones = make_desc(smem_u32(s.ones), 16 * 16, 128);
+      const uint32_t a_sbo = 16u * FA, b_sbo = 16u * FB;          // bytes between 4-row groups; 512 between 32-feature groups
+      // descriptors of stage 0 / K-step 0 / M tile 0; the others differ only in the start-address field (bytes >> 4)
+      const uint64_t da_hi0 = make_desc_mn(smem_u32(s.raw[0][0]), 512, a_sbo), db_hi0 = make_desc_mn(smem_u32(s.raw[0][1]), 512, b_sbo);
+      const uint64_t da_lo0 = make_desc_mn(smem_u32(s.lo[0][0]), 512, a_sbo), db_lo0 = make_desc_mn(smem_u32(s.lo[0][1]), 512, b_sbo);
+      constexpr uint32_t kRawStage = 2 * DW_KC * MLP_MAXW * 4 >> 4, kLoStage = kRawStage;
+      for (int i = 0; i < my_slices; ++i) {
+        const int rs = i % DW_RAW_STAGES, ls = i % DW_LO_STAGES;
+        mbar_wait(&s.split[ls], (i / DW_LO_STAGES) & 1);
+        tc_fence_after();
+        for (int mt = 0; mt < m_tiles; ++mt) {
 #pragma unroll
-        for (int kk = 0; kk < DW_KC / 8; ++kk) {             // one MMA K-step = two 4-row chunks
-          const uint32_t a_off = (uint32_t)(2 * kk) * a_lbo + (uint32_t)mt * (MLP_ROWS / 8) * DW_SBO;
-          const uint32_t b_off = (uint32_t)(2 * kk) * b_lbo;
-          const uint64_t da_hi = make_desc(smem_u32(s.op[0]) + a_off, a_lbo, DW_SBO);
-          const uint64_t da_lo = make_desc(smem_u32(s.op[1]) + a_off, a_lbo, DW_SBO);
-          const uint64_t db_hi = make_desc(smem_u32(s.op[2]) + b_off, b_lbo, DW_SBO);
-          const uint64_t db_lo = make_desc(smem_u32(s.op[3]) + b_off, b_lbo, DW_SBO);
-          const uint64_t d_ones = make_desc(smem_u32(s.ones), 16 * 16, 128);
-          const uint32_t d = tmem + mt * 256;
-          const uint32_t acc = (i > 0) || (kk > 0);
-          umma_tf32_ss(d, da_hi, db_hi, idesc, acc);
-          umma_tf32_ss(d, da_hi, db_lo, idesc, 1);
-          umma_tf32_ss(d, da_lo, db_hi, idesc, 1);
-          umma_tf32_ss(d + FB, da_hi, d_ones, idesc1, acc);  // bias gradient columns [FB, FB + 16)
-          umma_tf32_ss(d + FB, da_lo, d_ones, idesc1, 1);
+          for (int kk = 0; kk < DW_KC / 8; ++kk) {             // one MMA K-step = two 4-row groups
+            const uint32_t a_off = ((uint32_t)(2 * kk) * a_sbo + (uint32_t)mt * (MLP_ROWS / 32) * 512) >> 4;
+            const uint32_t b_off = ((uint32_t)(2 * kk) * b_sbo) >> 4;
+            const uint64_t da_hi = da_hi0 + rs * kRawStage + a_off, da_lo = da_lo0 + ls * kLoStage + a_off;
+            const uint64_t db_hi = db_hi0 + rs * kRawStage + b_off, db_lo = db_lo0 + ls * kLoStage + b_off;
+            const uint32_t d = tmem + mt * 256;
+            const uint32_t acc = (i > 0) || (kk > 0);
+            umma_tf32_ss(d, da_hi, db_hi, idesc, acc);
+            umma_tf32_ss(d, da_hi, db_lo, idesc, 1);
+            umma_tf32_ss(d, da_lo, db_hi, idesc, 1);
+            umma_tf32_ss(d + FB, da_hi, d_ones, idesc1, acc);  // bias gradient columns [FB, FB + 16)
+            umma_tf32_ss(d + FB, da_lo, d_ones, idesc1, 1);
+          }
+        }
+        umma_commit(&s.empty[rs]);
+        umma_commit(&s.lo_empty[ls]);
+      }
+      if (my_slices > 0) umma_commit(&s.bar_acc);
+    }
+  } else {
+    // ===== splitters =====
+    const int na4 = DW_KC * FA / 4, nb4 = DW_KC * FB / 4;
+    for (int i = 0; i < my_slices; ++i) {
+      const int rs = i % DW_RAW_STAGES, ls = i % DW_LO_STAGES;
+      mbar_wait(&s.full[rs], (i / DW_RAW_STAGES) & 1);
+      if (i >= DW_LO_STAGES) mbar_wait(&s.lo_empty[ls], (i / DW_LO_STAGES - 1) & 1);
+      float4* hiA = reinterpret_cast<float4*>(s.raw[rs][0]);
+      float4* hiB = reinterpret_cast<float4*>(s.raw[rs][1]);
+      float4* loA = reinterpret_cast<float4*>(s.lo[ls][0]);
+      float4* loB = reinterpret_cast<float4*>(s.lo[ls][1]);
+      if (na4 == 2 * DW_T_THREADS && nb4 == 2 * DW_T_THREADS) {   // 192 x 192: four independent 128-bit loads per thread
+        const float4 a0 = hiA[tid], a1 = hiA[tid + DW_T_THREADS], b0 = hiB[tid], b1 = hiB[tid + DW_T_THREADS];
+        dw_split4(hiA, loA, tid, a0);
+        dw_split4(hiA, loA, tid + DW_T_THREADS, a1);
+        dw_split4(hiB, loB, tid, b0);
+        dw_split4(hiB, loB, tid + DW_T_THREADS, b1);
+      } else {
+        for (int idx = tid; idx < max(na4, nb4); idx += DW_T_THREADS) {
+          const bool va = idx < na4, vb = idx < nb4;
+          float4 xa, xb;
+          if (va) xa = hiA[idx];
+          if (vb) xb = hiB[idx];
+          if (va) dw_split4(hiA, loA, idx, xa);
+          if (vb) dw_split4(hiB, loB, idx, xb);
         }
       }
-      umma_commit(&s.bar_mma);
-      if (i == my_slices - 1) umma_commit(&s.bar_acc);
+      fence_proxy_async();
+      mbar_arrive(&s.split[ls]);
     }
-  }
-  if (my_slices > 0 && warp < 4) {
-    mbar_wait(&s.bar_acc, 0);
-    tc_fence_after();
-    for (int mt = 0; mt < m_tiles; ++mt) {
-      const int m = mt * MLP_ROWS + tid;
-      for (int c0 = 0; c0 < FB + 16; c0 += 16) {
-        float v[16];
-        tmem_ld16(lane_addr + mt * 256 + c0, v);   // warp-collective: every thread executes it, only the adds are predicated
-        if (m < M_out) {
-          if (c0 == FB) {
-            if (c_bias) atomicAdd(c_bias + m, v[0]);
-          } else {
+    if (my_slices > 0 && warp < 4) {
+      const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+      mbar_wait(&s.bar_acc, 0);
+      tc_fence_after();
+      for (int mt = 0; mt < m_tiles; ++mt) {
+        const int m = mt * MLP_ROWS + tid;
+        for (int c0 = 0; c0 < FB + 16; c0 += 16) {
+          float v[16];
+          tmem_ld16(lane_addr + mt * 256 + c0, v);   // warp-collective: every thread executes it, only the adds are predicated
+          if (m < J.M_out) {
+            if (c0 == FB) {
+              if (J.c_bias) atomicAdd(J.c_bias + m, v[0]);
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int n = c0 + 4 * q;
-              if (n + 3 < N_in && (ldc % 4 == 0)) {
-                atomicAdd(reinterpret_cast<float4*>(C + (int64_t)m * ldc + n), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-              } else {
+              for (int q = 0; q < 4; ++q) {
+                const int n = c0 + 4 * q;
+                if (n + 3 < J.N_in && (J.ldc % 4 == 0)) {
+                  atomicAdd(reinterpret_cast<float4*>(J.C + (int64_t)m * J.ldc + n), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (n + j < N_in) atomicAdd(C + (int64_t)m * ldc + n + j, v[4 * q + j]);
+                  for (int j = 0; j < 4; ++j)
+                    if (n + j < J.N_in) atomicAdd(J.C + (int64_t)m * J.ldc + n + j, v[4 * q + j]);
+                }
               }
             }
           }
@@ -618,21 +702,118 @@ k_mlp_dw(const float* __restrict__ A_img, int FA, int M_out, const float* __rest
   if (warp == 0) tmem_dealloc(tmem, MLP_TMEM_COLS);
 }
 
-VX_API int vx_mlp_dw(const float* A_img, int FA, int M_out, const float* B_img, int FB, int N_in, const int* n_rows_dev,
-                     int capacity, float* C, int ldc, float* c_bias, cudaStream_t st) {
-  VX_REQUIRE(n_rows_dev != nullptr, "vx_mlp_dw", "n_rows_dev required");
-  VX_REQUIRE(FA % 8 == 0 && FA >= 8 && FA <= MLP_MAXW && FB % 16 == 0 && FB >= 16 && FB <= MLP_MAXW && M_out >= 1 &&
-             M_out <= FA && N_in >= 1 && N_in <= FB, "vx_mlp_dw", "shape");
+// ptrs_host[j*4..] = A_img, B_img, C, c_bias (device addresses; c_bias may be 0); dims_host[j*5..] = FA, M_out, FB, N_in, ldc
+VX_API int vx_mlp_dw_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
+                           cudaStream_t st) {
+  VX_REQUIRE(n_rows_dev != nullptr, "vx_mlp_dw_batch", "n_rows_dev required");
+  VX_REQUIRE(n_jobs >= 0 && n_jobs <= DW_MAX_JOBS, "vx_mlp_dw_batch", "at most 8 jobs per launch");
+  const int slices_cap = (capacity + DW_KC - 1) / DW_KC;
+  if (n_jobs == 0 || slices_cap <= 0) return 0;
+  DwBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n_jobs = n_jobs;
+  double cost[DW_MAX_JOBS], total = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    DwJob& J = b.job[j];
+    J.A = reinterpret_cast<const float*>(ptrs_host[4 * j]);
+    J.B = reinterpret_cast<const float*>(ptrs_host[4 * j + 1]);
+    J.C = reinterpret_cast<float*>(ptrs_host[4 * j + 2]);
+    J.c_bias = reinterpret_cast<float*>(ptrs_host[4 * j + 3]);
+    J.FA = dims_host[5 * j]; J.M_out = dims_host[5 * j + 1]; J.FB = dims_host[5 * j + 2]; J.N_in = dims_host[5 * j + 3];
+    J.ldc = dims_host[5 * j + 4];
+    VX_REQUIRE(J.A && J.B && J.C, "vx_mlp_dw_batch", "null pointer");
+    VX_REQUIRE(J.FA % 32 == 0 && J.FA >= 32 && J.FA <= MLP_MAXW && J.FB % 32 == 0 && J.FB >= 32 && J.FB <= MLP_MAXW &&
+               J.M_out >= 1 && J.M_out <= J.FA && J.N_in >= 1 && J.N_in <= J.FB, "vx_mlp_dw_batch", "shape");
+    // per-slice cost: MMA columns of both M tiles, or the transposition when that is longer
+    const int m_tiles = (J.M_out + MLP_ROWS - 1) / MLP_ROWS;
+    cost[j] = m_tiles * (3.0 * J.FB + 32) + 0.3 * (J.FA + J.FB) + 60;
+    total += cost[j];
+  }
+  // deal the SMs to the jobs in proportion to their cost (largest remainder), at most one CTA per 4 slices
+  const int sms = vx_num_sms();
+  const int cap_per_job = max(1, (slices_cap + 3) / 4);
+  int given = 0, n_cta[DW_MAX_JOBS];
+  for (int j = 0; j < n_jobs; ++j) {
+    n_cta[j] = max(1, (int)(sms * cost[j] / total));
+    given += n_cta[j];
+  }
+  for (int j = 0; given < sms; j = (j + 1) % n_jobs) { ++n_cta[j]; ++given; }   // (given may exceed sms by < n_jobs: harmless)
+  int begin = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    b.job[j].cta_begin = begin;
+    b.job[j].cta_count = min(n_cta[j], cap_per_job);
+    begin += b.job[j].cta_count;
+  }
   static bool attr_set = false;
-  const int smem = (int)sizeof(DwSmem) + 1024;
+  const int smem = (int)sizeof(DwmSmem) + 1024;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_mlp_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { vx_set_error("vx_mlp_dw", cudaGetErrorString(e)); return (int)e; }
+    if (e != cudaSuccess) { vx_set_error("vx_mlp_dw_batch", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  const int slices_cap = (capacity + DW_KC - 1) / DW_KC;
-  if (slices_cap <= 0) return 0;
-  const int gx = max(1, min(vx_num_sms(), (slices_cap + 3) / 4));
-  k_mlp_dw<<<gx, DW_THREADS, smem, st>>>(A_img, FA, M_out, B_img, FB, N_in, n_rows_dev, capacity, C, ldc, c_bias);
-  return vx_check_launch("vx_mlp_dw");
+  k_mlp_dw<<<begin, DW_THREADS, smem, st>>>(b, n_rows_dev, capacity);
+  return vx_check_launch("vx_mlp_dw_batch");
+}
+
+VX_API int vx_mlp_dw(const float* A_img, int FA, int M_out, const float* B_img, int FB, int N_in, const int* n_rows_dev,
+                     int capacity, float* C, int ldc, float* c_bias, cudaStream_t st) {
+  const int64_t ptrs[4] = {(int64_t)(uintptr_t)A_img, (int64_t)(uintptr_t)B_img, (int64_t)(uintptr_t)C, (int64_t)(uintptr_t)c_bias};
+  const int dims[5] = {FA, M_out, FB, N_in, ldc};
+  return vx_mlp_dw_batch(1, ptrs, dims, n_rows_dev, capacity, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layout probe (tests / development): one M = 128, K = 8 TF32 MMA on caller-provided shared-memory images and
+// descriptor fields, D returned as (128, N).  desc_*_fields = the 64-bit smem descriptor without its start address.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+k_umma_probe(const float* __restrict__ A_img, int a_floats, const float* __restrict__ B_img, int b_floats,
+             uint64_t desc_a, uint64_t desc_b, uint32_t idesc, int N, float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  float* sA = reinterpret_cast<float*>(smem_raw);
+  float* sB = reinterpret_cast<float*>(smem_raw + 32768);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < a_floats; i += 128) sA[i] = A_img[i];
+  for (int i = tid; i < b_floats; i += 128) sB[i] = B_img[i];
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const uint64_t da = desc_a | (uint64_t)((smem_u32(sA) >> 4) & 0x3FFF);
+    const uint64_t db = desc_b | (uint64_t)((smem_u32(sB) >> 4) & 0x3FFF);
+    umma_tf32_ss(tmem, da, db, idesc, 0);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < N) D[tid * N + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+VX_API int vx_umma_probe(const float* A_img, int a_floats, const float* B_img, int b_floats, int64_t desc_a_fields,
+                         int64_t desc_b_fields, int64_t idesc, int N, float* D, cudaStream_t st) {
+  VX_REQUIRE(a_floats <= 8192 && b_floats <= 8192 && N % 16 == 0 && N >= 16 && N <= 256, "vx_umma_probe", "sizes");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
+    attr_set = true;
+  }
+  k_umma_probe<<<1, 128, 65536 + 1024, st>>>(A_img, a_floats, B_img, b_floats, (uint64_t)desc_a_fields, (uint64_t)desc_b_fields,
+                                            (uint32_t)idesc, N, D);
+  return vx_check_launch("vx_umma_probe");
 }

@@ -29,7 +29,7 @@ import numpy as np
 import torch
 
 from ._lib import call
-from .mlp import FlatMLP, prepare_chains
+from .mlp import FlatMLP, prepare_chains, run_dw_batch
 from .optim import _storage
 
 
@@ -219,8 +219,13 @@ class FusedFineStep:
              self.alphainv_last, target.contiguous(), N, w_main, w_rgb0, w_ent, ent_scale, float(self.rk.get('bg', 0.0)), 1,
              self.rgb_marched, self.rgb_marched0, self.d_logit1, self.d_kout, self.d_w, self.d_last, self.loss_ray)
         call('vx_sum_f32', self.loss_ray, N, self.loss)
-        self.mlp2.backward(self.d_kout, self.dX2)
-        self.mlp1.backward(self.d_logit1, self.dX1)
+        if self.tensor_core:   # both dX chains, then the 8 weight-gradient GEMMs of both networks in one launch
+            self.mlp2.backward(self.d_kout, self.dX2, defer_dw=True)
+            self.mlp1.backward(self.d_logit1, self.dX1, defer_dw=True)
+            run_dw_batch([self.mlp2, self.mlp1])
+        else:
+            self.mlp2.backward(self.d_kout, self.dX2)
+            self.mlp1.backward(self.d_logit1, self.dX1)
         grad_target = self.d_smoothed if m.smooth_sdf else self.sdf_grad
         sparse_dp = self.world > 1 and self.sparse_k0_exchange
         call('vx_fused_row_backward', self._sdf_grid, X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(), self.idx4, n4,

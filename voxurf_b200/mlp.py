@@ -56,15 +56,18 @@ class FlatMLP:
         dev = self.flat.device
         self.cap = cap
         if self.tensor_core:
-            # pre-split hi/lo "chunked K-major images" (k = MLP row) of every activation and activation gradient:
-            # written by the chain epilogues, consumed by the split-K weight-gradient GEMM with plain bulk copies
+            # raw fp32 "row images" of every activation and activation gradient in the MN-major UMMA operand layout
+            # (csrc/mlp_tc.cu, act_offset; feature count padded to 32): written by the chain epilogues, consumed by the
+            # split-K weight-gradient GEMM with plain bulk copies
             self.R = (cap + 127) // 128 * 128
             img = lambda F: torch.zeros(self.R * F, dtype=torch.float32, device=dev)
-            self.F_in = self.tc_fwd.Kp[0]
+            assert all(l.out_features % 32 == 0 for l in self.linears[:-1]), 'hidden widths must be multiples of 32'
+            self.F_in = _pad(self.tc_fwd.Kp[0], 32)
+            self.F_out = _pad(self.tc_bwd.Kp[0], 32)
             self.X_img = img(self.F_in)
             self.H_img = [img(l.out_features) for l in self.linears[:-1]]
             self.dH_img = [img(l.out_features) for l in self.linears[:-1]]
-            self.dY_img = img(8)
+            self.dY_img = img(self.F_out)
             self.H = self.dH = []
             return
         self.H = [torch.empty(cap, l.out_features, dtype=torch.float32, device=dev) for l in self.linears[:-1]]
@@ -98,21 +101,30 @@ class FlatMLP:
         self._X = X
         return out
 
-    def backward(self, d_out, dX):
-        """d_out (cap, 3) -> dX (cap, ld_in); accumulates weight / bias gradients into the flat gradient buffer."""
+    def dw_jobs(self):
+        """(ptrs, dims) of this network's weight-gradient GEMMs for vx_mlp_dw_batch: dW_i = dY_i^T H_{i-1}, db_i = dY_i^T 1
+        on the row images left by forward() / backward()."""
+        n = len(self.linears)
+        ptrs, dims = [], []
+        for i in range(n):
+            A, FA = (self.dY_img, self.F_out) if i == n - 1 else (self.dH_img[i], self.linears[i].out_features)
+            B, FB = (self.X_img, self.F_in) if i == 0 else (self.H_img[i - 1], self.linears[i - 1].out_features)
+            ptrs += [A.data_ptr(), B.data_ptr(), self.dW[i].data_ptr(), self.db[i].data_ptr()]
+            dims += [FA, self.linears[i].out_features, FB, self.dW[i].shape[1], self.dW[i].stride(0)]
+        return ptrs, dims
+
+    def backward(self, d_out, dX, defer_dw=False):
+        """d_out (cap, 3) -> dX (cap, ld_in); accumulates weight / bias gradients into the flat gradient buffer.
+        defer_dw: only run the dX chain; the caller batches the weight-gradient GEMMs of several networks into one
+        launch with run_dw_batch()."""
         n = len(self.linears)
         if self.tensor_core:
             # dX chain (one launch): chain layer j <-> network layer n-1-j; hidden gradients land feature-major in dHT
             rev = list(range(n - 2, -1, -1))
             self.tc_bwd.run(d_out, d_out.shape[1], self._n, dX, dX.shape[1], imgs=[self.dH_img[i] for i in rev],
                             masks=[self.H_img[i] for i in rev], x_img=self.dY_img)
-            call = self.tc_fwd._call
-            for i in range(n):   # dW_i = dY_i^T H_{i-1}, db_i = dY_i^T 1
-                A, FA = (self.dY_img, 8) if i == n - 1 else (self.dH_img[i], self.linears[i].out_features)
-                B, FB = (self.X_img, self.F_in) if i == 0 else (self.H_img[i - 1], self.linears[i - 1].out_features)
-                M_out = self.linears[i].out_features
-                call('vx_mlp_dw', A, FA, M_out, B, FB, self.dW[i].shape[1], self._n, self.cap, self.dW[i],
-                     self.dW[i].stride(0), self.db[i])
+            if not defer_dw:
+                run_dw_batch([self])
             return dX
         dy = d_out
         for i in range(n - 1, -1, -1):
@@ -133,6 +145,19 @@ class FlatMLP:
 # ------------------------------------------------------------------------------------------------
 def _pad(v, m):
     return (v + m - 1) // m * m
+
+
+def run_dw_batch(mlps):
+    """Weight / bias gradients of several FlatMLPs (same row count and capacity) with one launch per 8 layers."""
+    from ._lib import call
+    ptrs, dims = [], []
+    for m in mlps:
+        assert m._n is mlps[0]._n and m.cap == mlps[0].cap
+        p, d = m.dw_jobs()
+        ptrs += p; dims += d
+    for j in range(0, len(ptrs) // 4, 8):
+        n = min(8, len(ptrs) // 4 - j)
+        call('vx_mlp_dw_batch', n, ptrs[4 * j:4 * (j + n)], dims[5 * j:5 * (j + n)], mlps[0]._n, mlps[0].cap)
 
 
 def prepare_chains(chains):
