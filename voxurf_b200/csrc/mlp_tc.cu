@@ -576,7 +576,7 @@ k_mlp_dw(const __grid_constant__ DwBatch batch, const int* __restrict__ n_rows_d
   const int m_tiles = (J.M_out + MLP_ROWS - 1) / MLP_ROWS;
   if (tid == 0) {
     for (int i = 0; i < DW_RAW_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    for (int i = 0; i < DW_LO_STAGES; ++i) { mbar_init(&s.split[i], DW_T_THREADS); mbar_init(&s.lo_empty[i], 1); }
+    for (int i = 0; i < DW_LO_STAGES; ++i) { mbar_init(&s.split[i], DW_T_THREADS / 32); mbar_init(&s.lo_empty[i], 1); }
     mbar_init(&s.bar_acc, 1);
     fence_barrier_init();
   }
@@ -664,8 +664,9 @@ k_mlp_dw(const __grid_constant__ DwBatch batch, const int* __restrict__ n_rows_d
           if (vb) dw_split4(hiB, loB, idx, xb);
         }
       }
-      fence_proxy_async();
-      mbar_arrive(&s.split[ls]);
+      fence_proxy_async();           // every thread: its own stores -> async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.split[ls]);   // one arrival per warp (384 single arrivals on one word serialise)
     }
     if (my_slices > 0 && warp < 4) {
       const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
