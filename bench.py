@@ -143,6 +143,16 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_tensor_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['bf16_tflops_sustained']), 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+        except Exception:
+            pass
+    return 1590.0, 'fallback (B200_PROFILING.md, 1.59 PFLOP/s bf16)'
+
+
 def algorithmic_bytes(V, C, tv, M2, M3, M4, N, fd):
     """B = 4V[9(1+C) + 3 tv + 4 fd] + (16 M2 + 8 M3 + 20 M4) + 60 N"""
     return 4 * V * (9 * (1 + C) + 3 * tv + 4 * fd) + (16 * M2 + 8 * M3 + 20 * M4) + 60 * N
@@ -299,6 +309,9 @@ def main():
     if fused is None:
         trainer.optimizer.timed_param = model.k0.grid
     trainer.optimizer.timings = []
+    from voxurf_b200 import mlp as _mlp
+    if fused is not None:
+        _mlp.CHAIN_TIMINGS = []
     with ClockSampler(local_rank) as clk:
         ev0.record()
         ret = run(args.steps, START_STEP + args.warmup, False)
@@ -306,7 +319,14 @@ def main():
         barrier()
     launches = _lib.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
-    adam_ms = [a.elapsed_time(b) for a, b in trainer.optimizer.timings]
+    tm = trainer.optimizer.timings
+    if fused is not None:
+        adam_ms = [ev[0].elapsed_time(ev[1]) for name, ev in tm if name == 'k0']
+        sdf_adam_ms = [ev[0].elapsed_time(ev[1]) for name, ev in tm if name == 'sdf']
+    else:
+        adam_ms, sdf_adam_ms = [a.elapsed_time(b) for a, b in tm], []
+    chain = [((a.elapsed_time(b)), fl) for (a, b), fl in (_mlp.CHAIN_TIMINGS or [])]
+    _mlp.CHAIN_TIMINGS = None
     if fused is None:
         trainer.optimizer.timed_param = None
     else:
@@ -324,6 +344,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
+    probe = None
+    if fused is not None and fused.k0_touched is not None:
+        # one extra (untimed) step on every rank to count the voxels the sparse-aware k0 Adam pass touches
+        fused.bitmap_probe = []
+        run(1, START_STEP + args.warmup + 2 * args.steps, False)
+        torch.cuda.synchronize()
+        probe, fused.bitmap_probe = fused.bitmap_probe, None
     if rank == 0:
         total_rays = args.rays * world * args.steps
         value = total_rays / (ms * 1e-3)
@@ -337,28 +364,48 @@ def main():
         if fused is not None and fused.k0_touched is not None:
             # sparse-aware pass: 32 B/element where a gradient landed this step, 24 B/element for voxels that ever had
             # one (non-zero moments), nothing elsewhere (identity update), plus both bitmaps.  Counted on one extra step.
-            fused.bitmap_probe = []
-            run(1, START_STEP + args.warmup + 2 * args.steps, False)
-            torch.cuda.synchronize()
-            tb, lb = (np.unpackbits(x.cpu().numpy().view(np.uint8)) for x in fused.bitmap_probe[0])
-            fused.bitmap_probe = None
+            tb, lb = (np.unpackbits(x.cpu().numpy().view(np.uint8)) for x in probe[0])
             n_t, n_l = int(tb.sum()), int((tb | lb).sum())
             adam_bytes = 4 * C * (8 * n_t + 6 * (n_l - n_t)) + 2 * 4 * fused.k0_touched.numel()
             adam_kernel = 'k_adam (k0 grid, %d x %d^3 fp32, sparse-aware: %d touched voxels x 32 B/el + %d live x 24 B/el + bitmaps)' % (C, G, n_t, n_l - n_t)
             sparse = {'voxels': V, 'touched': n_t, 'live': n_l, 'dense_equivalent_bytes': 32 * V * C}
         adam_t = float(np.mean(adam_ms)) if adam_ms else None
-        roof = {'bound': 'hbm', 'kernel': adam_kernel, 'achieved': (adam_bytes / (adam_t * 1e-3) / 1e9) if adam_t else None,
-                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'traffic': (6.383e9 if (C == 12 and G == 256 and sparse is None) else None), 'ms_per_launch': adam_t,
-                'algorithmic_bytes_per_launch': adam_bytes, 'share_of_step': (adam_t / (ms / args.steps)) if adam_t else None}
-        roof['frac'] = roof['achieved'] / peak if roof['achieved'] else None
+        step_ms = ms / args.steps
+        roof_k0 = {'bound': 'hbm', 'kernel': adam_kernel, 'achieved': (adam_bytes / (adam_t * 1e-3) / 1e9) if adam_t else None,
+                   'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'traffic': (6.383e9 if (C == 12 and G == 256 and sparse is None) else None),
+                   'ms_per_launch': adam_t, 'algorithmic_bytes_per_launch': adam_bytes, 'share_of_step': (adam_t / step_ms) if adam_t else None}
+        roof_k0['frac'] = roof_k0['achieved'] / peak if roof_k0['achieved'] else None
         if sparse:
-            roof['sparse'] = sparse
+            roof_k0['sparse'] = sparse
         if fused is not None:
             M0, M2, M4 = fused.counts()
             M3 = int(fused.keep[:M2].sum())
         else:
             M4 = int(ret['weights'].shape[0]); M3 = int(ret['mask'].shape[0]); M0 = int(ret['mask_outbbox'].shape[0])
             M2 = int((~ret['mask_outbbox']).sum())
+        roof, extra = roof_k0, {}
+        if chain and sum(t for t, _ in chain) / args.steps > (adam_t or 0):
+            # the dominant kernel of the fused step is the tcgen05 layer-chain kernel (4 launches per step: two forward
+            # chains, two dX chains).  Algorithmic flops = 2 * rows * sum_l K_l N_l in fp32 terms; the kernel issues
+            # three TF32 MMAs per product term (TF32x3 split), and TF32 runs at half the bf16 rate, so the ceiling of
+            # this formulation is peak / 6.  peak = the driver-measured dense bf16 cuBLAS throughput (sustained figure:
+            # the kernel is timed inside a long step).
+            tf_peak, tf_src = measured_tensor_peak()
+            t_chain = float(np.mean([t for t, _ in chain]))
+            fl = float(np.mean([f for _, f in chain])) * M4
+            roof = {'bound': 'tensor', 'kernel': 'k_mlp_chain (fused 4-layer MLP chain on tcgen05, TF32x3; %d rows, 4 launches/step)' % M4,
+                    'achieved': fl / (t_chain * 1e-3) / 1e12, 'peak': tf_peak, 'peak_source': tf_src, 'unit': 'TFLOP/s',
+                    'traffic': None, 'ms_per_launch': t_chain, 'algorithmic_flops_per_launch': fl,
+                    'issued_tf32_flops_per_launch': 3 * fl, 'formulation_ceiling_frac': 1.0 / 6.0,
+                    'share_of_step': sum(t for t, _ in chain) / args.steps / step_ms}
+            roof['frac'] = roof['achieved'] / tf_peak
+            extra['roofline_k0_adam'] = roof_k0
+            if sdf_adam_ms:
+                t_sdf = float(np.mean(sdf_adam_ms))
+                extra['roofline_sdf_adam'] = {'bound': 'hbm', 'kernel': 'k_adam (sdf grid, %d^3 fp32, dense, 32 B/element)' % G,
+                                              'achieved': 32 * V / (t_sdf * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                              'frac': 32 * V / (t_sdf * 1e-3) / 1e9 / peak, 'ms_per_launch': t_sdf,
+                                              'algorithmic_bytes_per_launch': 32 * V, 'share_of_step': t_sdf / step_ms}
         B = algorithmic_bytes(V, C, 1 / 3, M2, M3, M4, args.rays, 1 / 3)
         step_roof = {'algorithmic_bytes_per_step': B, 'achieved_gbs': B / (ms / args.steps * 1e-3) / 1e9,
                      'frac_of_hbm': B / (ms / args.steps * 1e-3) / 1e9 / peak, 'M0': M0, 'M2': M2, 'M3': M3, 'M4': M4}
@@ -370,6 +417,7 @@ def main():
                 'e2e': {'value': total_rays / (ms_e2e * 1e-3), 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                         'ms_per_step': ms_e2e / args.steps},
                 'roofline': roof, 'step_roofline': step_roof}
+        line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_reference_arm(args, 1, 1, args.cpu_rays)
         print(json.dumps(line))

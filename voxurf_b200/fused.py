@@ -117,7 +117,7 @@ class FusedFineStep:
         self.adam_state = {}
         self.adam_steps = 0
         self.bitmap_probe = None   # bench.py: list collecting copies of (touched, live) as the k0 Adam launch sees them
-        self.timings = None   # bench.py: list collecting (start, end) CUDA events around the k0 Adam launch
+        self.timings = None   # bench.py: list collecting (group, (start, end) CUDA events) around the k0 / sdf Adam launches
         if self.cfg is not None:
             c = self.cfg
             self.groups = [('sdf', [m.sdf.grid], c['lrate_sdf']), ('k0', [m.k0.grid], c['lrate_k0']),
@@ -343,7 +343,7 @@ class FusedFineStep:
                 if st is None:
                     st = (torch.zeros_like(p, memory_format=torch.preserve_format), torch.zeros_like(p, memory_format=torch.preserve_format))
                     self.adam_state[id(p)] = st
-                timed = self.timings is not None and name == 'k0'
+                timed = self.timings is not None and name in ('k0', 'sdf')
                 if timed:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                     ev[0].record()
@@ -356,7 +356,7 @@ class FusedFineStep:
                     call('vx_bitmap_merge', live, touched, touched.numel())
                 if timed:
                     ev[1].record()
-                    self.timings.append(ev)
+                    self.timings.append((name, ev))
 
     def mark_all_live(self):
         """Call after loading optimizer moments from elsewhere: every voxel may then hold non-zero exp_avg / exp_avg_sq."""

@@ -2,13 +2,16 @@
 run over the fixed-capacity row matrices of the fused step with explicit forward / backward passes and flat
 parameter + gradient storage (one Adam launch per network, no autograd graph).
 
-This is the one dense-contraction stage of the path.  Round-1 implementation: fp32 cuBLAS GEMMs
-(torch.addmm / mm on preallocated buffers, TF32 off) -- "plain library GEMM" per the task rules; the fused
-tensor-core (tcgen05) kernel that keeps the 79/54-wide rows and the hidden activations on chip is the next step
-and plugs in behind the same three methods (alloc / forward / backward).
+This is the one dense-contraction stage of the path.  Default: the hand-written tcgen05 kernels of
+csrc/mlp_tc.cu (TF32x3 split, fp32-grade accuracy): one fused launch per layer chain (forward, and the dX chain of
+the backward pass) that keeps the activations on chip, and one batched launch for all weight / bias gradients.
+tensor_core=False keeps the plain fp32 cuBLAS formulation (torch.addmm / mm on preallocated buffers, TF32 off) as a
+comparison path for the tests.
 """
 import torch
 import torch.nn as nn
+
+CHAIN_TIMINGS = None   # bench.py: list collecting ((start, end) CUDA events, flops per row) of every vx_mlp_chain launch
 
 
 class FlatMLP:
@@ -219,5 +222,12 @@ class TensorCoreChain:
             ptrs += [self.W_hi[i].data_ptr(), self.W_lo[i].data_ptr(), addr(L.get('bias')), addr(pick(imgs, i)),
                      addr(pick(masks, i))]
             dims += [self.Kp[i], self.Np[i], self.N[i], int(bool(L.get('relu', False)))]
+        timed = CHAIN_TIMINGS is not None
+        if timed:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         self._call('vx_mlp_chain', X, X.stride(0), k0, n_rows_dev, X.shape[0], n, ptrs, dims, Y, Y.stride(0), n_out,
                    x_img)
+        if timed:
+            ev[1].record()
+            CHAIN_TIMINGS.append((ev, 2 * sum(k * nn_ for k, nn_ in zip(self.K, self.N))))   # flops per row
