@@ -281,6 +281,26 @@ int vx_mlp_dw(const float* A_img, int FA, int M_out, const float* B_img, int FB,
 int vx_mlp_dw_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
                     cudaStream_t stream);
 
+/* ---- caller side of the path: view rays and the in-mask-cache ray filter ---------------- */
+/* get_rays_of_a_view (lib/voxurf_fine.py:1001-1067): rays_o, rays_d, viewdirs (H*W,3) of one view.  K_host: 3x3 row-major
+ * intrinsics, c2w_host: first three rows of the pose (3x4 row-major); mode 0 'lefttop', 1 'center', 2 'random' (jitter_i,
+ * jitter_j: (H,W) uniform offsets drawn by the caller); ndc != 0 applies ndc_rays(H, W, K[0][0], ndc_near, ...) */
+int vx_rays_of_view(int H, int W, const float* K_host, const float* c2w_host, int inverse_y, int flip_x, int flip_y, int mode,
+                    const float* jitter_i, const float* jitter_j, int ndc, float ndc_near, float* rays_o, float* rays_d,
+                    float* viewdirs, cudaStream_t stream);
+/* hit_coarse_geo (lib/voxurf_fine.py:579-591): hit[r] = some sample of ray r (same sampling as vx_ray_setup /
+ * sample_pts_on_rays) is inside the bbox and inside the mask cache; nothing per-sample is materialised */
+int vx_rays_hit_mask(const float* rays_o, const float* rays_d, int n_rays, const float* xyz_min_host,
+                     const float* xyz_max_host, float near, float far, float stepdist, const float* mc_density, int mc_X,
+                     int mc_Y, int mc_Z, const float* mc_min_host, const float* mc_max_host, float act_shift,
+                     float voxel_size_ratio, float thres, bool* hit, cudaStream_t stream);
+/* the img[mask] / rays[mask] copies of get_training_rays_in_maskcache_sampling (lib/voxurf_fine.py:1150-1156) without a
+ * host sync: rows of up to four (n,3) arrays with mask set are appended, in order, at row *top_in of the destinations
+ * (rows >= capacity are dropped); *top_out = *top_in + count.  incl = inclusive int32 prefix sum of mask */
+int vx_compact_rows3(const bool* mask, const int* incl, int n, const int64_t* top_in, int64_t* top_out, int64_t capacity,
+                     const float* src0, const float* src1, const float* src2, const float* src3, float* dst0, float* dst1,
+                     float* dst2, float* dst3, cudaStream_t stream);
+
 /* development probe: one M = 128, K = 8 TF32 tcgen05.mma on caller-laid-out shared-memory operand images (<= 32 KB each)
  * with caller-chosen descriptor fields; used by tests/test_gpu_mlp.py to pin the operand layouts the kernels rely on */
 int vx_umma_probe(const float* A_img, int a_floats, const float* B_img, int b_floats, int64_t desc_a_fields,

@@ -511,3 +511,73 @@ def nonempty_mask(mc, xyz_min, xyz_max, shape):
     out = mask_cache_forward(mc['density'], xyz.reshape(-1, 3), mc['xyz_min'], mc['xyz_max'], mc['act_shift'],
                              mc['voxel_size_ratio'], mc['thres'])
     return out.reshape(1, 1, *shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# caller side: view rays and the in-mask-cache ray filter (pinned by tests/golden/rays.npz)
+# ------------------------------------------------------------------------------------------------
+def view_rays(H, W, K, c2w, *, ndc=False, inverse_y=False, flip_x=False, flip_y=False, mode='center', jitter=None):
+    """get_rays + get_rays_of_a_view, voxurf_fine.py:1001-1029,1065-1070 (ndc_rays :1043-1062 with near = 1).
+    K (3,3), c2w (>=3,4) fp32 tensors.  jitter = (ji, jj) replaces the two torch.rand_like draws of mode 'random'.
+    -> rays_o, rays_d, viewdirs (H,W,3)"""
+    cols = torch.arange(W, dtype=torch.float32).view(1, W).expand(H, W)
+    rows = torch.arange(H, dtype=torch.float32).view(H, 1).expand(H, W)
+    if mode == 'center':
+        u, v = cols + 0.5, rows + 0.5
+    elif mode == 'lefttop':
+        u, v = cols, rows
+    elif mode == 'random':
+        u, v = cols + jitter[0], rows + jitter[1]
+    else:
+        raise NotImplementedError(mode)
+    if flip_x:
+        u = torch.flip(u, dims=(1,))
+    if flip_y:
+        v = torch.flip(v, dims=(0,))
+    x = (u - float(K[0][2])) / float(K[0][0])
+    y = (v - float(K[1][2])) / float(K[1][1])
+    cam = torch.stack([x, y, torch.ones_like(x)] if inverse_y else [x, -y, -torch.ones_like(x)], -1)
+    R = c2w[:3, :3].float()
+    prod = cam.unsqueeze(-2) * R                                   # (H,W,3,3): cam[l] * R[k][l]
+    rays_d = (prod[..., 0] + prod[..., 1]) + prod[..., 2]
+    rays_o = c2w[:3, 3].float().expand(rays_d.shape)
+    sq = rays_d * rays_d
+    viewdirs = rays_d / torch.sqrt((sq[..., 0] + sq[..., 1]) + sq[..., 2]).unsqueeze(-1)
+    if ndc:
+        focal, near = float(K[0][0]), 1.0
+        cw, ch = -1. / (W / (2. * focal)), -1. / (H / (2. * focal))
+        t = -(near + rays_o[..., 2]) / rays_d[..., 2]
+        o = rays_o + t.unsqueeze(-1) * rays_d
+        new_o = torch.stack([cw * o[..., 0] / o[..., 2], ch * o[..., 1] / o[..., 2], 1. + 2. * near / o[..., 2]], -1)
+        new_d = torch.stack([cw * (rays_d[..., 0] / rays_d[..., 2] - o[..., 0] / o[..., 2]),
+                             ch * (rays_d[..., 1] / rays_d[..., 2] - o[..., 1] / o[..., 2]),
+                             -2. * near / o[..., 2]], -1)
+        rays_o, rays_d = new_o, new_d
+    return rays_o, rays_d, viewdirs
+
+
+def hit_coarse_geo(mc, rays_o, rays_d, xyz_min, xyz_max, near, stepsize, voxel_size):
+    """voxurf_fine.py:579-591: rays with at least one in-bbox sample inside the mask cache. -> bool, rays_o.shape[:-1]"""
+    shape = rays_o.shape[:-1]
+    o, d = rays_o.reshape(-1, 3).contiguous(), rays_d.reshape(-1, 3).contiguous()
+    pts, mask_outbbox, ray_id = K.sample_pts_on_rays(o, d, xyz_min, xyz_max, near, 1e9, float(stepsize * voxel_size))[:3]
+    inb = ~mask_outbbox
+    inside = mask_cache_forward(mc['density'], pts[inb], mc['xyz_min'], mc['xyz_max'], mc['act_shift'],
+                                mc['voxel_size_ratio'], mc['thres'])
+    hit = torch.zeros(o.shape[0], dtype=torch.bool)
+    hit[ray_id[inb][inside]] = True
+    return hit.reshape(shape)
+
+
+def training_rays_in_maskcache(images, poses, HW, Ks, mc, xyz_min, xyz_max, voxel_size, *, near, stepsize, ndc=False,
+                               inverse_y=False, flip_x=False, flip_y=False):
+    """get_training_rays_in_maskcache_sampling, voxurf_fine.py:1127-1164 -> rgb, rays_o, rays_d, viewdirs (n,3), counts"""
+    out = [[], [], [], []]
+    counts = []
+    for img, c2w, (H, W), Kc in zip(images, poses, HW, Ks):
+        ro, rd, vd = view_rays(H, W, Kc, c2w, ndc=ndc, inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y)
+        keep = hit_coarse_geo(mc, ro, rd, xyz_min, xyz_max, near, stepsize, voxel_size)
+        for dst, src in zip(out, (img, ro, rd, vd)):
+            dst.append(src[keep])
+        counts.append(int(keep.sum()))
+    return [torch.cat(x) for x in out] + [counts]

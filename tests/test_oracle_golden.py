@@ -171,3 +171,34 @@ def test_maskgrid_matches_reference():
     close(scale, g['scale'], 0, 0); close(shift, g['shift'], 0, 0)
     q = T(rs.uniform(-1.2, 1.2, (400, 3)).astype(np.float32))
     assert (K.maskcache_lookup(T(mk), q, scale, shift).numpy() == g['out']).all()
+
+
+def _train_views():
+    views = [S.make_view(seed=40 + i, H=h, W=w, inverse_y=False) for i, (h, w) in enumerate(S.TRAIN_VIEW_SIZES)]
+    imgs = [T(S.make_image(h, w, seed=i)) for i, (h, w, _, _) in enumerate(views)]
+    return views, imgs
+
+
+def test_view_rays_match_reference():
+    """get_rays_of_a_view / ndc_rays (lib/voxurf_fine.py:1001-1070) as run by the reference's own code."""
+    g = load_golden('rays.npz')
+    for name, kw in S.RAY_CASES.items():
+        H, W, K_, c2w = S.make_view(seed=kw['seed'], H=kw['H'], W=kw['W'], inverse_y=kw['inverse_y'])
+        ro, rd, vd = R.view_rays(H, W, T(K_), T(c2w), ndc=kw['ndc'], inverse_y=kw['inverse_y'], flip_x=kw['flip_x'],
+                                 flip_y=kw['flip_y'], mode=kw['mode'])
+        close(ro, g[name + '_rays_o'], 2e-6, 1e-6); close(rd, g[name + '_rays_d'], 2e-6, 1e-6)
+        close(vd, g[name + '_viewdirs'], 2e-6, 1e-7)
+
+
+def test_training_rays_in_maskcache_match_reference():
+    """get_training_rays_in_maskcache_sampling (lib/voxurf_fine.py:1127-1164): per-view counts and row order exact."""
+    g = load_golden('rays.npz')
+    sc = S.make_fine_scene(20, 6, 32, seed=3, mask_G=12)
+    m = oracle_fine_model(sc, requires_grad=False)
+    views, imgs = _train_views()
+    rgb, ro, rd, vd, counts = R.training_rays_in_maskcache(
+        imgs, [T(v[3]) for v in views], [(v[0], v[1]) for v in views], [T(v[2]) for v in views], m['mask_cache'], XYZ_MIN,
+        XYZ_MAX, m['voxel_size'], near=0.3, stepsize=0.5)
+    assert counts == g['tr_imsz'].tolist()
+    assert np.array_equal(rgb.numpy(), g['tr_rgb'])          # the kept pixels, in order: identifies the kept rays exactly
+    close(ro, g['tr_rays_o'], 2e-6, 1e-6); close(rd, g['tr_rays_d'], 2e-6, 1e-6); close(vd, g['tr_viewdirs'], 2e-6, 1e-7)

@@ -205,7 +205,12 @@ class VoxurfBase(nn.Module):
     def hit_coarse_geo(self, rays_o, rays_d, near, far, stepsize, **render_kwargs):
         """lib/voxurf_fine.py:579-591: which rays have at least one sample inside the mask cache."""
         shape = rays_o.shape[:-1]
-        m = self._march(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), near, stepsize, want_mask_outbbox=False)
-        cnt = m['keep_off'][1:] - m['keep_off'][:-1]
-        return (cnt > 0).reshape(shape)
+        o, d = rays_o.reshape(-1, 3).contiguous(), rays_d.reshape(-1, 3).contiguous()
+        hit = torch.empty(o.shape[0], dtype=torch.bool, device=o.device)
+        stepdist = float(np.float32(float(stepsize) * self._voxel_size_host))
+        # warp-per-ray march that stops at the first sample inside the mask: nothing per-sample is materialised
+        # (the reference's sample_pts_on_rays + MaskCache on every sample is why it feeds this 64 image rows at a time)
+        call('vx_rays_hit_mask', o, d, o.shape[0], self._min_host, self._max_host, float(near), 1e9, stepdist,
+             *self.mask_cache.march_args(), hit)
+        return hit.reshape(shape)
 

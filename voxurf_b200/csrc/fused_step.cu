@@ -19,7 +19,75 @@
 // S4: SDF value + 6-neighbour gradient + NeuS alpha for every M2 sample
 //     (grid_sampler(sample_grad=True) lib/voxurf_fine.py:640 + neus_alpha_from_sdf_scatter :643 + mask :648)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_sdf_alpha_fwd(VxGrid g, const float* __restrict__ grid, VxPts pts, const int* __restrict__ n_dev,
+// The 7 trilinear taps of a sample (centre + one voxel to either side on each axis) read 56 corners, but only 32
+// distinct voxels: the centre cell plus one more layer on each of its six faces.  The kernel is bound by L1 wavefronts
+// (every corner read of a warp spreads over ~10 sectors), so the 32 voxels are loaded once into registers and every tap
+// whose cell is where it is expected -- all of them, except when a coordinate sits within an ulp of a cell boundary or
+// is clamped at the grid border -- takes its corners from there; the arithmetic (weights, corner order, predicates)
+// is vx_tap_eval's, so the result is bit-identical to evaluating each tap from memory, which remains the fallback.
+struct SdfNeighbourhood {
+  float cube[8];        // corner c of the centre cell (bit 0: +Z, bit 1: +Y, bit 2: +X)
+  float ext[3][2][4];   // [axis][0: index -1, 1: index +2][the other two axes' bits, lower axis first]
+};
+
+__device__ __forceinline__ float nb_load(const float* __restrict__ grid, const VxGrid& g, int x, int y, int z) {
+  const bool ok = (x >= 0) & (x < g.X) & (y >= 0) & (y < g.Y) & (z >= 0) & (z < g.Z);
+  return ok ? __ldg(grid + ((int64_t)x * g.Y + y) * g.Z + z) : 0.f;
+}
+
+__device__ __forceinline__ void nb_fill(const float* __restrict__ grid, const VxGrid& g, int cx, int cy, int cz,
+                                        SdfNeighbourhood& nb) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) nb.cube[c] = nb_load(grid, g, cx + ((c >> 2) & 1), cy + ((c >> 1) & 1), cz + (c & 1));
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int o = m ? 2 : -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      nb.ext[0][m][i] = nb_load(grid, g, cx + ((i >> 1) & 1), cy + (i & 1), cz + o);        // Z displaced: bits (Y, X)
+      nb.ext[1][m][i] = nb_load(grid, g, cx + ((i >> 1) & 1), cy + o, cz + (i & 1));        // Y displaced: bits (Z, X)
+      nb.ext[2][m][i] = nb_load(grid, g, cx + o, cy + ((i >> 1) & 1), cz + (i & 1));        // X displaced: bits (Z, Y)
+    }
+  }
+}
+
+// tap displaced by kS (-1 / +1) cells along axis kA (0 = Z, 1 = Y, 2 = X), or the centre cell (kS = 0)
+template <int kA, int kS>
+__device__ __forceinline__ float nb_tap_eval(const SdfNeighbourhood& nb, const VxTap& t) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int bit = (c >> kA) & 1;
+    const int pos = kS + bit;                                   // cell index on the displaced axis: -1..2
+    const int oi = (kA == 0) ? (c >> 1) : (kA == 1) ? ((c & 1) | ((c >> 1) & 2)) : (c & 3);
+    const float v = (pos == -1) ? nb.ext[kA][0][oi] : (pos == 2) ? nb.ext[kA][1][oi] : nb.cube[(c & ~(1 << kA)) | (pos << kA)];
+    if (t.off[c] >= 0) acc += v * t.w[c];
+  }
+  return acc;
+}
+
+template <int kA, int kS>
+__device__ __forceinline__ float sdf_tap_value(const VxGrid& g, const float* __restrict__ grid, const SdfNeighbourhood& nb,
+                                               int cx, int cy, int cz, float ix, float iy, float iz) {
+  VxTap t;
+  vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+  const int ex = cx + (kA == 2 ? kS : 0), ey = cy + (kA == 1 ? kS : 0), ez = cz + (kA == 0 ? kS : 0);
+  const bool cached = ((int)floorf(iz) == ex) & ((int)floorf(iy) == ey) & ((int)floorf(ix) == ez);
+  return cached ? nb_tap_eval<kA, kS>(nb, t) : vx_tap_eval(grid, t);
+}
+
+template <int kA>
+__device__ __forceinline__ float sdf_axis_gradient(const VxGrid& g, const float* __restrict__ grid, const SdfNeighbourhood& nb,
+                                                   const SdfTapCoords& tc, int cx, int cy, int cz, float voxel_size) {
+  float ix, iy, iz;
+  const float cm = sdf_tap_coords(g, tc, kA, -1.f, ix, iy, iz);
+  const float fm = sdf_tap_value<kA, -1>(g, grid, nb, cx, cy, cz, ix, iy, iz);
+  const float cp = sdf_tap_coords(g, tc, kA, 1.f, ix, iy, iz);
+  const float fp = sdf_tap_value<kA, 1>(g, grid, nb, cx, cy, cz, ix, iy, iz);
+  return __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp, cm)), voxel_size);
+}
+
+__global__ void __launch_bounds__(256) k_sdf_alpha_fwd(VxGrid g, const float* __restrict__ grid, VxPts pts, const int* __restrict__ n_dev,
                                 const float* __restrict__ viewdirs, float voxel_size, float dist, float inv_s,
                                 float thres, float* __restrict__ sdf, float* __restrict__ grad,
                                 float* __restrict__ alpha, uint8_t* __restrict__ keep, float* __restrict__ d_w,
@@ -28,25 +96,19 @@ __global__ void k_sdf_alpha_fwd(VxGrid g, const float* __restrict__ grid, VxPts 
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     float px, py, pz;
     vx_load_pt(pts, p, px, py, pz);
-    VxTap t;
     float ix, iy, iz;
     point_to_index(g, px, py, pz, ix, iy, iz);
-    vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
-    const float s = vx_tap_eval(grid, t);
     SdfTapCoords tc;
     sdf_tap_setup(g, px, py, pz, tc);
-    float gr[3];  // reference axis order z,y,x
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float cm = sdf_tap_coords(g, tc, a, -1.f, ix, iy, iz);
-      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
-      const float fm = vx_tap_eval(grid, t);
-      const float cp = sdf_tap_coords(g, tc, a, 1.f, ix, iy, iz);
-      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
-      const float fp = vx_tap_eval(grid, t);
-      gr[a] = __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp, cm)), voxel_size);
-    }
-    const float gx = gr[2], gy = gr[1], gz = gr[0];
+    // neighbourhood anchored at the cell of the displaced taps' shared (clamped, round-tripped) coordinates
+    const int cz = (int)floorf(tc.c[0]), cy = (int)floorf(tc.c[1]), cx = (int)floorf(tc.c[2]);
+    SdfNeighbourhood nb;
+    nb_fill(grid, g, cx, cy, cz, nb);
+    const float s = sdf_tap_value<0, 0>(g, grid, nb, cx, cy, cz, ix, iy, iz);
+    // reference axis order z,y,x
+    const float gz = sdf_axis_gradient<0>(g, grid, nb, tc, cx, cy, cz, voxel_size);
+    const float gy = sdf_axis_gradient<1>(g, grid, nb, tc, cx, cy, cz, voxel_size);
+    const float gx = sdf_axis_gradient<2>(g, grid, nb, tc, cx, cy, cz, voxel_size);
     const int r = pts.ray_id[p];
     const float true_cos = __fadd_rn(__fadd_rn(__fmul_rn(viewdirs[3 * r], gx), __fmul_rn(viewdirs[3 * r + 1], gy)),
                                      __fmul_rn(viewdirs[3 * r + 2], gz));

@@ -501,3 +501,173 @@ VX_API int vx_points_from_steps(const int* ray_id, const int* step_id, const flo
   k_points_from_steps<<<blocks, 256, 0, st>>>(src, n_dev, n_host, out);
   return vx_check_launch("vx_points_from_steps");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Caller side of the path: per-view ray generation and the in-mask-cache ray filter.
+//   get_rays / ndc_rays / get_rays_of_a_view                      lib/voxurf_fine.py:1001-1067
+//   hit_coarse_geo                                                lib/voxurf_fine.py:579-591
+//   get_training_rays_in_maskcache_sampling                       lib/voxurf_fine.py:1127-1164
+// The reference builds every view with a dozen elementwise ATen ops, tests 64 image rows at a time by materialising
+// every sample of every ray (sample_pts_on_rays + MaskCache on ~600 points per ray), and compacts with boolean
+// indexing (one host sync per view).  Here: one kernel writes rays_o / rays_d / viewdirs of a view, one warp-per-ray
+// kernel marches until the first sample inside the mask (nothing per-sample is stored), one kernel compacts the four
+// per-ray arrays of the view behind a running device-side row counter.  One rounding per reference op, same order.
+// ---------------------------------------------------------------------------------------------
+struct VxCamera {
+  float fx, fy, cx, cy;
+  float R[3][3];   // c2w[:3,:3]
+  float t[3];      // c2w[:3,3]
+};
+
+__global__ void k_rays_of_view(int H, int W, VxCamera cam, int inverse_y, int flip_x, int flip_y, float pixel_offset,
+                               const float* __restrict__ jitter_i, const float* __restrict__ jitter_j, int ndc, float ndc_cw,
+                               float ndc_ch, float ndc_near, float* __restrict__ rays_o, float* __restrict__ rays_d,
+                               float* __restrict__ viewdirs) {
+  const int n = H * W;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n; pix += gridDim.x * blockDim.x) {
+    const int r = pix / W, c = pix - r * W;
+    const int cc = flip_x ? W - 1 - c : c, rr = flip_y ? H - 1 - r : r;     // i.flip((1,)), j.flip((0,))
+    float i = (float)cc, j = (float)rr;
+    if (jitter_i) { i = __fadd_rn(i, jitter_i[r * W + cc]); j = __fadd_rn(j, jitter_j[rr * W + c]); }   // mode 'random'
+    else { i = __fadd_rn(i, pixel_offset); j = __fadd_rn(j, pixel_offset); }                            // 'center' / 'lefttop'
+    float d0 = __fdiv_rn(__fsub_rn(i, cam.cx), cam.fx);
+    float d1 = __fdiv_rn(__fsub_rn(j, cam.cy), cam.fy);
+    float d2 = 1.f;
+    if (!inverse_y) { d1 = -d1; d2 = -1.f; }
+    float o[3], d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {   // torch.sum(dirs[..., None, :] * c2w[:3,:3], -1)
+      d[k] = __fadd_rn(__fadd_rn(__fmul_rn(d0, cam.R[k][0]), __fmul_rn(d1, cam.R[k][1])), __fmul_rn(d2, cam.R[k][2]));
+      o[k] = cam.t[k];
+    }
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) viewdirs[3 * pix + k] = __fdiv_rn(d[k], nrm);
+    if (ndc) {   // ndc_rays(H, W, focal, near = 1., rays_o, rays_d), lib/voxurf_fine.py:1037-1056
+      const float t = __fdiv_rn(-__fadd_rn(ndc_near, o[2]), d[2]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o[k] = __fadd_rn(o[k], __fmul_rn(t, d[k]));
+      const float o0 = __fdiv_rn(__fmul_rn(ndc_cw, o[0]), o[2]);
+      const float o1 = __fdiv_rn(__fmul_rn(ndc_ch, o[1]), o[2]);
+      const float o2 = __fadd_rn(1.f, __fdiv_rn(__fmul_rn(2.f, ndc_near), o[2]));
+      const float e0 = __fmul_rn(ndc_cw, __fsub_rn(__fdiv_rn(d[0], d[2]), __fdiv_rn(o[0], o[2])));
+      const float e1 = __fmul_rn(ndc_ch, __fsub_rn(__fdiv_rn(d[1], d[2]), __fdiv_rn(o[1], o[2])));
+      const float e2 = __fdiv_rn(__fmul_rn(-2.f, ndc_near), o[2]);
+      o[0] = o0; o[1] = o1; o[2] = o2; d[0] = e0; d[1] = e1; d[2] = e2;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { rays_o[3 * pix + k] = o[k]; rays_d[3 * pix + k] = d[k]; }
+  }
+}
+
+// K_host: 3x3 row-major intrinsics; c2w_host: the first three rows of the pose, 3x4 row-major.
+// mode: 0 'lefttop', 1 'center', 2 'random' (needs jitter_i, jitter_j: (H,W) uniform [0,1) offsets).
+VX_API int vx_rays_of_view(int H, int W, const float* K_host, const float* c2w_host, int inverse_y, int flip_x, int flip_y,
+                           int mode, const float* jitter_i, const float* jitter_j, int ndc, float ndc_near, float* rays_o,
+                           float* rays_d, float* viewdirs, cudaStream_t st) {
+  VX_REQUIRE(H >= 0 && W >= 0 && (int64_t)H * W < ((int64_t)1 << 30), "vx_rays_of_view", "image size");
+  VX_REQUIRE(mode >= 0 && mode <= 2, "vx_rays_of_view", "mode must be 0 (lefttop), 1 (center) or 2 (random)");
+  VX_REQUIRE(mode != 2 || (jitter_i && jitter_j), "vx_rays_of_view", "mode 'random' needs the jitter arrays");
+  if (H * W == 0) return 0;
+  VxCamera cam;
+  cam.fx = K_host[0]; cam.cx = K_host[2]; cam.fy = K_host[4]; cam.cy = K_host[5];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) cam.R[r][c] = c2w_host[4 * r + c];
+    cam.t[r] = c2w_host[4 * r + 3];
+  }
+  // -1./(W/(2.*focal)) evaluated in double like the Python expression, then narrowed once
+  const double focal = (double)K_host[0];
+  const float cw = (float)(-1.0 / ((double)W / (2.0 * focal))), ch = (float)(-1.0 / ((double)H / (2.0 * focal)));
+  const int blocks = min(vx_blocks((int64_t)H * W, 256), vx_num_sms() * 16);
+  k_rays_of_view<<<blocks, 256, 0, st>>>(H, W, cam, inverse_y, flip_x, flip_y, mode == 1 ? 0.5f : 0.f,
+                                         mode == 2 ? jitter_i : nullptr, mode == 2 ? jitter_j : nullptr, ndc, cw, ch,
+                                         ndc_near, rays_o, rays_d, viewdirs);
+  return vx_check_launch("vx_rays_of_view");
+}
+
+// hit[r] = any sample of ray r lies inside the bbox and inside the mask cache; one warp per ray, 32 steps per round,
+// stops at the first round with a hit
+__global__ void k_rays_hit(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n_rays, VxGrid box,
+                           float near, float far, float stepdist, VxMaskCache mc, bool* __restrict__ hit) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * warps_per_block) {
+    const float* o = rays_o + 3 * r;
+    const float* d = rays_d + 3 * r;
+    float tmn, tmx;
+    ray_t_minmax(o, d, box.min, box.max, near, far, tmn, tmx);
+    const float rnorm = ray_norm(d);
+    const int n = (int)ray_n_samples(tmn, tmx, rnorm, stepdist);
+    const float sx = o[0] + d[0] * tmn, sy = o[1] + d[1] * tmn, sz = o[2] + d[2] * tmn;
+    const float dx = d[0] / rnorm, dy = d[1] / rnorm, dz = d[2] / rnorm;
+    bool any = false;
+    for (int s0 = 0; s0 < n && !any; s0 += 32) {
+      const int s = s0 + lane;
+      bool keep = false;
+      if (s < n) {
+        const float dist = stepdist * s;
+        const float px = sx + dx * dist;
+        const float py = sy + dy * dist;
+        const float pz = sz + dz * dist;
+        const bool inb = !((box.min[0] > px) | (box.min[1] > py) | (box.min[2] > pz) | (box.max[0] < px) | (box.max[1] < py) |
+                           (box.max[2] < pz));
+        keep = inb && mask_cache_keep(mc, px, py, pz);
+      }
+      any = __any_sync(0xffffffffu, keep);
+    }
+    if (lane == 0) hit[r] = any;
+  }
+}
+
+VX_API int vx_rays_hit_mask(const float* rays_o, const float* rays_d, int n_rays, const float* xyz_min_host,
+                            const float* xyz_max_host, float near, float far, float stepdist, const float* mc_density,
+                            int mc_X, int mc_Y, int mc_Z, const float* mc_min_host, const float* mc_max_host,
+                            float act_shift, float voxel_size_ratio, float thres, bool* hit, cudaStream_t st) {
+  VX_REQUIRE(mc_density != nullptr, "vx_rays_hit_mask", "needs a mask cache");
+  if (n_rays <= 0) return 0;
+  VxGrid box;
+  box.X = box.Y = box.Z = box.C = 1; box.cl = 0;
+  VxMaskCache mc;
+  mc.density = mc_density; mc.X = mc_X; mc.Y = mc_Y; mc.Z = mc_Z;
+  for (int c = 0; c < 3; ++c) {
+    box.min[c] = xyz_min_host[c]; box.max[c] = xyz_max_host[c];
+    mc.min[c] = mc_min_host[c]; mc.max[c] = mc_max_host[c];
+  }
+  mc.act_shift = act_shift; mc.voxel_size_ratio = voxel_size_ratio; mc.thres = thres;
+  const int blocks = min(vx_blocks((int64_t)n_rays * 32, 256), vx_num_sms() * 16);
+  k_rays_hit<<<blocks, 256, 0, st>>>(rays_o, rays_d, n_rays, box, near, far, stepdist, mc, hit);
+  return vx_check_launch("vx_rays_hit_mask");
+}
+
+// stable compaction of the rows of up to four (n,3) arrays selected by `mask`, appended at row tops[k]; writes
+// tops[k+1] = tops[k] + count.  incl = inclusive prefix sum of mask (int32).
+__global__ void k_compact_rows3(const bool* __restrict__ mask, const int* __restrict__ incl, int n,
+                                const int64_t* __restrict__ top_in, int64_t* __restrict__ top_out, int64_t capacity,
+                                const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
+                                const float* __restrict__ s3, float* __restrict__ d0, float* __restrict__ d1,
+                                float* __restrict__ d2, float* __restrict__ d3) {
+  const int64_t top = *top_in;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i == n - 1) *top_out = top + incl[i];
+    if (!mask[i]) continue;
+    const int64_t dst = top + incl[i] - 1;
+    if (dst >= capacity) continue;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (s0) d0[3 * dst + k] = s0[3 * (int64_t)i + k];
+      if (s1) d1[3 * dst + k] = s1[3 * (int64_t)i + k];
+      if (s2) d2[3 * dst + k] = s2[3 * (int64_t)i + k];
+      if (s3) d3[3 * dst + k] = s3[3 * (int64_t)i + k];
+    }
+  }
+}
+
+VX_API int vx_compact_rows3(const bool* mask, const int* incl, int n, const int64_t* top_in, int64_t* top_out,
+                            int64_t capacity, const float* src0, const float* src1, const float* src2, const float* src3,
+                            float* dst0, float* dst1, float* dst2, float* dst3, cudaStream_t st) {
+  VX_REQUIRE(top_in && top_out && top_in != top_out, "vx_compact_rows3", "top_in / top_out must be distinct device slots");
+  if (n <= 0) return 0;
+  k_compact_rows3<<<min(vx_blocks(n, 256), vx_num_sms() * 16), 256, 0, st>>>(mask, incl, n, top_in, top_out, capacity, src0,
+                                                                           src1, src2, src3, dst0, dst1, dst2, dst3);
+  return vx_check_launch("vx_compact_rows3");
+}

@@ -112,3 +112,39 @@ def make_coarse_scene(G, C=12, width=128, seed=0, mask_G=None, sdf_noise=0.01, w
         sc['mask_act_shift'] = float(np.log(1 / (1 - 1e-6) - 1))
         sc['mask_voxel_size_ratio'] = 1.0
     return sc
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic views (pinhole cameras on a sphere looking at the origin) for the ray-generation path
+# ------------------------------------------------------------------------------------------------
+def make_view(seed, H, W, inverse_y=False, r_cam=3.0, fov_scale=1.1):
+    """-> H, W, K (3,3) float32, c2w (4,4) float32.  OpenGL convention (camera looks along -z, y up) unless inverse_y
+    (OpenCV: looks along +z, y down), matching the two branches of lib/voxurf_fine.py:1020-1023."""
+    rs = np.random.RandomState(seed)
+    p = rs.standard_normal(3)
+    p = p / np.linalg.norm(p) * r_cam
+    fwd = -p / np.linalg.norm(p)
+    up0 = np.array([0.0, 0.0, 1.0]) if abs(fwd[2]) < 0.9 else np.array([0.0, 1.0, 0.0])
+    right = np.cross(fwd, up0)
+    right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    R = np.stack([right, -up, fwd], 1) if inverse_y else np.stack([right, up, -fwd], 1)
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[:3, :3] = R.astype(np.float32)
+    c2w[:3, 3] = p.astype(np.float32)
+    focal = fov_scale * r_cam * max(H, W) / 2.0          # the unit-ish object fills most of the frame
+    K = np.array([[focal, 0, W / 2.0 - 0.3], [0, focal * 1.01, H / 2.0 + 0.2], [0, 0, 1]], np.float32)
+    return H, W, K, c2w
+
+
+def make_image(H, W, seed):
+    return np.random.RandomState(1000 + seed).uniform(0, 1, (H, W, 3)).astype(np.float32)
+
+
+RAY_CASES = {
+    'gl_center': dict(seed=1, H=12, W=16, inverse_y=False, flip_x=False, flip_y=False, mode='center', ndc=False),
+    'cv_center': dict(seed=2, H=9, W=14, inverse_y=True, flip_x=False, flip_y=False, mode='center', ndc=False),
+    'gl_flip_lefttop': dict(seed=3, H=10, W=7, inverse_y=False, flip_x=True, flip_y=True, mode='lefttop', ndc=False),
+    'gl_ndc': dict(seed=4, H=8, W=8, inverse_y=False, flip_x=False, flip_y=False, mode='center', ndc=True),
+}
+TRAIN_VIEW_SIZES = [(40, 48), (33, 37), (40, 48)]

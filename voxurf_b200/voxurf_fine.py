@@ -31,6 +31,8 @@ from .grid import MaskCache  # noqa: F401  (lib/voxurf_fine.py:917 lives next to
 from .ops import Alphas2Weights  # noqa: F401
 from .torch_scatter import segment_coo
 from ._base import SmoothConv, VoxurfBase, _binomial_weights, _gaussian_weights, _mlp  # noqa: F401
+from .rays import (batch_indices_generator, get_rays, get_rays_np, get_rays_of_a_view, get_training_rays,  # noqa: F401
+                   get_training_rays_flatten, get_training_rays_in_maskcache_sampling, ndc_rays)
 
 
 class Voxurf(VoxurfBase):
