@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--cpu-rays', type=int, default=256, help='ray sample of the CPU baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--path', default='fused', choices=['fused', 'dropin'], help='fused = sync-free FusedFineStep; dropin = Voxurf.forward + autograd')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel of the step separately (no CUDA-graph replay)')
     ap.add_argument('--dense-adam', action='store_true', help='k0 Adam over every voxel (no touched/live bitmaps)')
     ap.add_argument('--dense-k0-allreduce', action='store_true', help='multi-GPU: all-reduce the dense k0 gradient grid instead of exchanging rows')
     ap.add_argument('--phases', action='store_true', help='also print a per-phase CUDA-event breakdown to stderr')
@@ -267,7 +268,8 @@ def main():
     fused = None
     if args.path == 'fused':
         from voxurf_b200.fused import FusedFineStep
-        fused = FusedFineStep(model, args.rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank, sparse_adam=not args.dense_adam)
+        fused = FusedFineStep(model, args.rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank, sparse_adam=not args.dense_adam,
+                              use_graph=(world == 1 and not args.no_graph))
         fused.calibrate(*dev_pool[0][:3], global_step=START_STEP, headroom=1.35)
         sync = None   # FusedFineStep.grad_sync(): dense all-reduce for sdf + MLPs, row exchange for k0 (or --dense-k0-allreduce)
         fused.sparse_k0_exchange = not args.dense_k0_allreduce
@@ -306,19 +308,29 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()
+    from voxurf_b200 import mlp as _mlp
+    graph = fused is not None and fused.use_graph
+    config['cuda_graph'] = bool(graph)   # the timed steps are replays of two captured graphs (TV / non-TV iteration)
+    r0 = fused.launches_replayed if graph else 0
     if fused is None:
         trainer.optimizer.timed_param = model.k0.grid
-    trainer.optimizer.timings = []
-    from voxurf_b200 import mlp as _mlp
-    if fused is not None:
-        _mlp.CHAIN_TIMINGS = []
+    if not graph:                       # per-kernel event timing inside the timed steps
+        trainer.optimizer.timings = []
+        if fused is not None:
+            _mlp.CHAIN_TIMINGS = []
     with ClockSampler(local_rank) as clk:
         ev0.record()
         ret = run(args.steps, START_STEP + args.warmup, False)
         ev1.record()
         barrier()
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() - l0 + ((fused.launches_replayed - r0) if graph else 0)
     ms = ev0.elapsed_time(ev1)
+    if graph:
+        # the timed steps were CUDA-graph replays (no events inside a graph): time the same kernels with events over the
+        # same number of separately launched steps right after, outside the headline measurement
+        fused.timings, _mlp.CHAIN_TIMINGS = [], []
+        run(args.steps, START_STEP + args.warmup + 3 * args.steps, False)
+        barrier()
     tm = trainer.optimizer.timings
     if fused is not None:
         adam_ms = [ev[0].elapsed_time(ev[1]) for name, ev in tm if name == 'k0']

@@ -94,11 +94,13 @@ int vx_adam_upd(float* param, const float* grad, float* exp_avg, float* exp_avg_
  * optional skip of zero gradients, optional fused zero-fill of grad).  `touched` / `live`: optional bitmaps, one bit
  * per `group` consecutive elements: touched = a gradient was scattered there this step (elsewhere grad == 0 and is
  * not read), live = a gradient was ever scattered there (elsewhere exp_avg == exp_avg_sq == 0: with grad == 0 the
- * dense update is the identity and the element is skipped).  Same result as the dense pass, bit for bit. */
+ * dense update is the identity and the element is skipped).  Same result as the dense pass, bit for bit.
+ * step_dev (optional, device): {step_size, sqrt_bias_correction2} read by the kernel instead of the by-value arguments,
+ * so that a captured CUDA graph can be replayed with new per-step values (likewise inv_s_dev of the fused NeuS kernels). */
 int vx_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const float* perlr, int64_t numel,
                  float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
                  float sqrt_bias_correction2, float eps, int skip_zero_grad, int zero_grad, const uint32_t* touched,
-                 const uint32_t* live, int group, cudaStream_t stream);
+                 const uint32_t* live, int group, const float* step_dev, cudaStream_t stream);
 /* live |= touched; touched = 0 -- after the vx_adam_step that consumed both */
 int vx_bitmap_merge(uint32_t* live, uint32_t* touched, int64_t n_words, cudaStream_t stream);
 
@@ -208,7 +210,7 @@ int vx_fused_sdf_alpha(const float* grid, int X, int Y, int Z, const float* xyz_
                        const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
                        float stepdist, const int* n_dev, const float* viewdirs, float voxel_size, float dist,
                        float inv_s, float thres, float* sdf, float* grad, float* alpha, uint8_t* keep, float* d_w,
-                       float* d_sdf_s, float* d_grad_s, cudaStream_t stream);
+                       float* d_sdf_s, float* d_grad_s, const float* inv_s_dev, cudaStream_t stream);
 /* weights > thres compaction as an index list                                   lib/voxurf_fine.py:668-676 */
 int vx_fused_emit_rows(const uint8_t* w_keep, const int* seg_off, const int* off4, int n_rays, int capacity,
                        int* idx4, int* overflow, cudaStream_t stream);
@@ -252,7 +254,7 @@ int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min_host, 
                                 float stepdist, const int* n_dev, const float* viewdirs, const float* sdf,
                                 const float* grad, const uint8_t* keep, const float* d_alpha, const float* d_sdf_s,
                                 const float* d_grad_s, float voxel_size, float dist, float inv_s, float* sdf_grad,
-                                cudaStream_t stream);
+                                const float* inv_s_dev, cudaStream_t stream);
 
 /* ---- tensor-core MLP (tcgen05, TF32x3 split; lib/voxurf_fine.py:132-187,718,749) ---------------------------- */
 /* "chunked K-major image" CH(F): IMG[(k/4)*F + f][k%4] -- the UMMA K-major no-swizzle operand layout; a K=32 slice is one

@@ -109,3 +109,33 @@ def test_fused_render_matches_dropin_forward():
     out = fs.render(ro, rd, vd)
     for k in ['rgb_marched', 'rgb_marched0', 'normal_marched', 'depth', 'alphainv_cum']:
         close(out[k], ref[k], 1e-5, 3e-6, k)
+
+
+def test_fused_step_cuda_graph_replay_matches_eager():
+    """use_graph=True (one CUDA-graph launch per step, step-dependent scalars read from device memory) follows the eager
+    step: same losses and parameters over 9 iterations that include TV iterations, replays of both graph variants, a
+    changing NeuS s_val, Adam bias corrections and a decaying learning rate."""
+    from voxurf_b200.fused import FusedFineStep
+    from voxurf_b200.trainer import FINE_TRAIN
+    sc = S.make_fine_scene(40, 12, 64, seed=23)
+    ma, mb = product_fine_model(sc, k0_channels_last=True), product_fine_model(sc, k0_channels_last=True)
+    n_rays = 640
+    fa = FusedFineStep(ma, n_rays, FINE_TRAIN, RK, row_capacity=8192)
+    fb = FusedFineStep(mb, n_rays, FINE_TRAIN, RK, row_capacity=8192, use_graph=True)
+    assert fb.use_graph
+    for it in range(9):
+        step = 15001 + it
+        ro, rd, vd = (T(x).to(DEV) for x in S.make_rays(n_rays, seed=300 + it))
+        target = T(S.make_target(vd.cpu().numpy(), seed=it)).to(DEV)
+        la = fa.step(ro, rd, vd, target, step).clone()
+        lb = fb.step(ro, rd, vd, target, step).clone()
+        fa.apply_lr_decay(); fb.apply_lr_decay()
+        close(lb, la, 2e-5, 1e-7, f'loss step {step}')
+        assert fa.counts() == fb.counts()
+    assert len(fb._graphs) == 2 and fa.adam_steps == fb.adam_steps == 9
+    close(mb.sdf.grid, ma.sdf.grid, 1e-4, 2e-2 * 5e-3, 'sdf')
+    close(mb.k0.grid, ma.k0.grid, 1e-4, 2e-2 * 1e-1, 'k0')
+    for la_, lb_ in zip(fa.mlp1.linears, fb.mlp1.linears):
+        close(lb_.weight, la_.weight, 1e-3, 5e-2 * 3e-3, 'rgbnet W')
+    fb.sync_s_val()
+    close(mb.s_val, ma.s_val, 1e-6, 0)

@@ -239,7 +239,7 @@ def test_adam_touched_live_bitmaps_are_bit_identical_to_dense(C):
             st[1].copy_(cu(T(g.reshape(-1))))
             bm = (touched, live) if k == 'sparse' else (None, None)
             call('vx_adam_step', st[0], st[1], st[2], st[3], None, N, 0.9, 0.99, 1 - 0.9, 1 - 0.99, 0.1 / bc1,
-                 float(np.sqrt(bc2)), 1e-8, 0, 1, bm[0], bm[1], C)
+                 float(np.sqrt(bc2)), 1e-8, 0, 1, bm[0], bm[1], C, None)
         call('vx_bitmap_merge', live, touched, n_words)
         assert (touched == 0).all()
         got = np.unpackbits(live.cpu().numpy().view(np.uint8), bitorder='little')[:V].astype(bool)

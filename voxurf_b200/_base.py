@@ -89,7 +89,7 @@ class VoxurfBase(nn.Module):
         """lib/voxurf_fine.py:466-473 -> (s_val to report, 1/s_val as float32)."""
         if global_step is not None:
             s_val = 1. / (global_step + self.s_ratio / self.s_start - self.step_start) * self.s_ratio
-            self.s_val.data = torch.ones_like(self.s_val) * s_val
+            self.s_val.data.fill_(s_val)       # (== torch.ones_like(self.s_val) * s_val of the reference, one launch)
             self._s_val_host = float(np.float32(s_val))
         else:
             s_val = 0

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
                                               float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                               const float* __restrict__ perlr, int64_t N, AdamCoef c,
                                               const uint32_t* __restrict__ touched, const uint32_t* __restrict__ live,
-                                              uint32_t group) {
+                                              uint32_t group, const float* __restrict__ step_dev) {
+  if (step_dev) { c.step_size = __ldg(step_dev); c.sqrt_bc2 = __ldg(step_dev + 1); }   // CUDA-graph replays
   const int64_t n4 = N >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float4* p4 = reinterpret_cast<float4*>(param);
@@ -100,7 +101,9 @@ __global__ void __launch_bounds__(256) k_adam_sparse(float* __restrict__ param, 
                                                      float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                                      int64_t n_words, int64_t n_vox, AdamCoef c,
                                                      const uint32_t* __restrict__ touched,
-                                                     const uint32_t* __restrict__ live, uint32_t group) {
+                                                     const uint32_t* __restrict__ live, uint32_t group,
+                                                     const float* __restrict__ step_dev) {
+  if (step_dev) { c.step_size = __ldg(step_dev); c.sqrt_bc2 = __ldg(step_dev + 1); }
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -142,14 +145,14 @@ __global__ void __launch_bounds__(256) k_adam_sparse(float* __restrict__ param, 
 template <bool kRef>
 static int launch_adam(float* param, float* grad, float* m, float* v, const float* perlr, int64_t N, const AdamCoef& c,
                        int mode, int zero_grad, cudaStream_t st, const uint32_t* touched = nullptr,
-                       const uint32_t* live = nullptr, int group = 1) {
+                       const uint32_t* live = nullptr, int group = 1, const float* step_dev = nullptr) {
   const bool aligned = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                          reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
                          reinterpret_cast<uintptr_t>(perlr)) & 15) == 0;
   if (!aligned) { vx_set_error("vx_adam", "tensors must be 16-byte aligned"); return -1; }
   const int64_t want = (N / 4 + 255) / 256 + 1;
   const int blocks = (int)min(want, (int64_t)vx_num_sms() * 8);
-#define VX_ADAM(MODE, ZG) k_adam<kRef, MODE, ZG><<<blocks, 256, 0, st>>>(param, grad, m, v, perlr, N, c, touched, live, (uint32_t)group)
+#define VX_ADAM(MODE, ZG) k_adam<kRef, MODE, ZG><<<blocks, 256, 0, st>>>(param, grad, m, v, perlr, N, c, touched, live, (uint32_t)group, step_dev)
   if (mode == 0) { if (zero_grad) VX_ADAM(0, true); else VX_ADAM(0, false); }
   else if (mode == 1) { if (zero_grad) VX_ADAM(1, true); else VX_ADAM(1, false); }
   else { if (zero_grad) VX_ADAM(2, true); else VX_ADAM(2, false); }
@@ -172,7 +175,7 @@ VX_API int vx_adam_upd(float* param, const float* grad, float* exp_avg, float* e
 VX_API int vx_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const float* perlr, int64_t N,
                         float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
                         float sqrt_bias_correction2, float eps, int skip_zero_grad, int zero_grad,
-                        const uint32_t* touched, const uint32_t* live, int group, cudaStream_t st) {
+                        const uint32_t* touched, const uint32_t* live, int group, const float* step_dev, cudaStream_t st) {
   if (N <= 0) return 0;
   VX_REQUIRE(!touched || (group >= 1 && N % 4 == 0 && N < ((int64_t)1 << 32)), "vx_adam_step",
              "touched bitmap needs group >= 1, numel % 4 == 0 and numel < 2^32");
@@ -187,11 +190,11 @@ VX_API int vx_adam_step(float* param, float* grad, float* exp_avg, float* exp_av
     VX_REQUIRE(aligned && N % group == 0, "vx_adam_step", "bitmap pass: 16-byte aligned tensors, numel % group == 0");
     const int64_t n_vox = N / group, n_words = (n_vox + 31) / 32;
     const int blocks = (int)min((n_words + 255) / 256, (int64_t)vx_num_sms() * 8);
-    if (zero_grad) k_adam_sparse<true><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_words, n_vox, c, touched, live, (uint32_t)group);
-    else k_adam_sparse<false><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_words, n_vox, c, touched, live, (uint32_t)group);
+    if (zero_grad) k_adam_sparse<true><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_words, n_vox, c, touched, live, (uint32_t)group, step_dev);
+    else k_adam_sparse<false><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_words, n_vox, c, touched, live, (uint32_t)group, step_dev);
     return vx_check_launch("vx_adam_step");
   }
-  return launch_adam<false>(param, grad, exp_avg, exp_avg_sq, perlr, N, c, mode, zero_grad, st, touched, live, group);
+  return launch_adam<false>(param, grad, exp_avg, exp_avg_sq, perlr, N, c, mode, zero_grad, st, touched, live, group, step_dev);
 }
 
 // live |= touched; touched = 0  (after the Adam pass that consumed both)

@@ -91,8 +91,10 @@ __global__ void __launch_bounds__(256) k_sdf_alpha_fwd(VxGrid g, const float* __
                                 const float* __restrict__ viewdirs, float voxel_size, float dist, float inv_s,
                                 float thres, float* __restrict__ sdf, float* __restrict__ grad,
                                 float* __restrict__ alpha, uint8_t* __restrict__ keep, float* __restrict__ d_w,
-                                float* __restrict__ d_sdf_s, float* __restrict__ d_grad_s) {
+                                float* __restrict__ d_sdf_s, float* __restrict__ d_grad_s,
+                                const float* __restrict__ inv_s_dev) {
   const int64_t n = *n_dev;
+  if (inv_s_dev) inv_s = __ldg(inv_s_dev);   // CUDA-graph replays: the step-dependent 1/s lives in device memory
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     float px, py, pz;
     vx_load_pt(pts, p, px, py, pz);
@@ -131,12 +133,12 @@ VX_API int vx_fused_sdf_alpha(const float* grid, int X, int Y, int Z, const floa
                               const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
                               float stepdist, const int* n_dev, const float* viewdirs, float voxel_size, float dist,
                               float inv_s, float thres, float* sdf, float* grad, float* alpha, uint8_t* keep, float* d_w,
-                              float* d_sdf_s, float* d_grad_s, cudaStream_t st) {
+                              float* d_sdf_s, float* d_grad_s, const float* inv_s_dev, cudaStream_t st) {
   VX_REQUIRE(n_dev != nullptr, "vx_fused_sdf_alpha", "n_dev required");
   const VxGrid g = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
   const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
   k_sdf_alpha_fwd<<<vx_num_sms() * 8, 256, 0, st>>>(g, grid, pts, n_dev, viewdirs, voxel_size, dist, inv_s, thres, sdf,
-                                                    grad, alpha, keep, d_w, d_sdf_s, d_grad_s);
+                                                    grad, alpha, keep, d_w, d_sdf_s, d_grad_s, inv_s_dev);
   return vx_check_launch("vx_fused_sdf_alpha");
 }
 
@@ -680,8 +682,9 @@ __global__ void k_alpha_sdf_bwd(VxGrid g, VxPts pts, const int* __restrict__ n_d
                                 const float* __restrict__ sdf, const float* __restrict__ grad,
                                 const uint8_t* __restrict__ keep, const float* __restrict__ d_alpha,
                                 const float* __restrict__ d_sdf_s, const float* __restrict__ d_grad_s, float voxel_size,
-                                float dist, float inv_s, float* __restrict__ sdf_grad) {
+                                float dist, float inv_s, float* __restrict__ sdf_grad, const float* __restrict__ inv_s_dev) {
   const int64_t n = *n_dev;
+  if (inv_s_dev) inv_s = __ldg(inv_s_dev);
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     if (!keep[p]) continue;
     const float ga = d_alpha[p];
@@ -743,12 +746,12 @@ VX_API int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min
                                        float stepdist, const int* n_dev, const float* viewdirs, const float* sdf,
                                        const float* grad, const uint8_t* keep, const float* d_alpha, const float* d_sdf_s,
                                        const float* d_grad_s, float voxel_size, float dist, float inv_s, float* sdf_grad,
-                                       cudaStream_t st) {
+                                       const float* inv_s_dev, cudaStream_t st) {
   VX_REQUIRE(n_dev != nullptr, "vx_fused_alpha_sdf_backward", "n_dev required");
   const VxGrid g = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
   const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
   k_alpha_sdf_bwd<<<vx_num_sms() * 8, 256, 0, st>>>(g, pts, n_dev, viewdirs, sdf, grad, keep, d_alpha, d_sdf_s, d_grad_s,
-                                                    voxel_size, dist, inv_s, sdf_grad);
+                                                    voxel_size, dist, inv_s, sdf_grad, inv_s_dev);
   return vx_check_launch("vx_fused_alpha_sdf_backward");
 }
 

@@ -35,7 +35,7 @@ from .optim import _storage
 
 class FusedFineStep:
     def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0,
-                 tensor_core=True, sparse_k0_exchange=True, sparse_adam=True):
+                 tensor_core=True, sparse_k0_exchange=True, sparse_adam=True, use_graph=False):
         if model.k0_dim not in (6, 12):
             raise NotImplementedError('fused step: k0 channels must be 6 or 12')
         if model.k_center_sdf or not model.center_sdf or not model.k_res:
@@ -116,6 +116,14 @@ class FusedFineStep:
             self.smoothed, self.d_smoothed = torch.empty_like(m.sdf.grid), torch.zeros_like(m.sdf.grid)
         self.adam_state = {}
         self.adam_steps = 0
+        # CUDA-graph replay of the whole step (single GPU): static input buffers, the step-dependent scalars (1/s of the
+        # NeuS schedule, Adam step sizes / bias corrections) in a small device array the kernels read (inv_s_dev, step_dev)
+        self.use_graph = bool(use_graph) and world == 1
+        self._graphs, self._eager_seen, self._dev_consts = {}, set(), None
+        self._graph_launches, self.launches_replayed = {}, 0   # kernels per captured variant / total replayed (bench.py)
+        if self.use_graph:
+            self.consts = torch.zeros(16, dtype=torch.float32, device=dev)
+            self.in_o, self.in_d, self.in_v, self.in_t = (torch.zeros(n_rays, 3, dtype=torch.float32, device=dev) for _ in range(4))
         self.bitmap_probe = None   # bench.py: list collecting copies of (touched, live) as the k0 Adam launch sees them
         self.timings = None   # bench.py: list collecting (group, (start, end) CUDA events) around the k0 / sdf Adam launches
         if self.cfg is not None:
@@ -149,8 +157,12 @@ class FusedFineStep:
         m, N = self.m, self.N
         assert rays_o.shape[0] == N, 'FusedFineStep is sized for a fixed batch; build another for a different one'
         rays_o, rays_d, viewdirs = rays_o.contiguous(), rays_d.contiguous(), viewdirs.contiguous()
-        s_val, inv_s = m._update_s_val(global_step)
-        self.inv_s = inv_s
+        if self._dev_consts is None:
+            s_val, inv_s = m._update_s_val(global_step)
+            inv_s_dev = None
+        else:                      # graph capture / replay: the host bookkeeping happened in _step_graph
+            s_val, inv_s, inv_s_dev = 0, 0.0, self._dev_consts[0:1]
+        self.inv_s, self._inv_s_dev = inv_s, inv_s_dev
         X, Y, Z, mn, mx = self._geom()
         near = self.rk['near']
         call('vx_ray_setup', rays_o, rays_d, m.xyz_min, m.xyz_max, near, 1e9, self.stepdist, N, self.t_min, self.t_max,
@@ -168,7 +180,7 @@ class FusedFineStep:
         self._sdf_grid = sdf_grid
         thres = float(m.fast_color_thres)
         call('vx_fused_sdf_alpha', sdf_grid, X, Y, Z, mn, mx, *self._pts(), n2, viewdirs, m._voxel_size_host, self.dist,
-             inv_s, thres, self.sdf_s, self.grad_s, self.alpha, self.keep, self.d_w, self.d_sdf_s, self.d_grad_s)
+             inv_s, thres, self.sdf_s, self.grad_s, self.alpha, self.keep, self.d_w, self.d_sdf_s, self.d_grad_s, inv_s_dev)
         call('vx_alpha2weight_seg', self.alpha, self.keep if thres > 0 else None, self.keep_off, N, thres, self.weight, self.T,
              self.alphainv_last, self.i_end, self.w_keep, self.w_count)
         call('vx_scan_i32', self.w_count, N, self.off4)
@@ -238,7 +250,8 @@ class FusedFineStep:
         call('vx_alpha2weight_seg_backward', self.alpha, self.weight, self.T, self.keep if thres > 0 else None,
              self.alphainv_last, self.keep_off, self.i_end, N, self.d_w, self.d_last, self.d_alpha)
         call('vx_fused_alpha_sdf_backward', X, Y, Z, mn, mx, *self._pts(), n2, viewdirs.contiguous(), self.sdf_s, self.grad_s,
-             self.keep, self.d_alpha, self.d_sdf_s, self.d_grad_s, m._voxel_size_host, self.dist, self.inv_s, grad_target)
+             self.keep, self.d_alpha, self.d_sdf_s, self.d_grad_s, m._voxel_size_host, self.dist, self.inv_s, grad_target,
+             self._inv_s_dev)
         if m.smooth_sdf:
             call('vx_conv3d_replicate_backward', self.d_smoothed, 1, X, Y, Z, m.smooth_conv.weight_host, m.smooth_conv.ksize, 1,
                  self.sdf_grad)
@@ -295,10 +308,17 @@ class FusedFineStep:
         return c['tv_from'] < global_step < c['tv_end'] and global_step % c['tv_every'] == 0
 
     @torch.no_grad()
-    def regularise(self, global_step, global_batch=None):
+    def tv_flags(self, global_step):
+        """(is a TV iteration with an active regulariser, dense TV add-grad) -- the two step-dependent branches"""
+        c = self.cfg
+        tv = self.is_tv_iter(global_step) and c['weight_tv_density'] > 0 and not c.get('ori_tv', False)
+        return bool(tv), bool(global_step < c['tv_dense_before'])
+
+    def regularise(self, global_step, global_batch=None, flags=None):
         """run.py:612-625 (smooth-grad TV through the full-grid FD gradient) and run.py:641-655 (TV add-grad)."""
         c, m = self.cfg, self.m
-        if not self.is_tv_iter(global_step) or c['weight_tv_density'] <= 0 or c.get('ori_tv', False):
+        is_tv, dense = flags if flags is not None else self.tv_flags(global_step)
+        if not is_tv:
             return
         X, Y, Z = self.X, self.Y, self.Z
         tv = c['tv_terms']
@@ -313,7 +333,6 @@ class FusedFineStep:
             w = c['weight_tv_density'] * tv['smooth_grad_tv'] / (3.0 * m._n_nonempty)
             call('vx_smooth_grad_tv', self.G, m.nonempty_mask[0, 0], X, Y, Z, m._tv_smooth_w, w, self.dG, self.tv_scratch, self.tv_loss)
             self.loss.add_(self.tv_loss)   # run.py:622-625 adds the regulariser to the reported loss
-        dense = global_step < c['tv_dense_before']
         n_batch = global_batch or self.N * self.world
         wt = c['weight_tv_density'] * tv['sdf_tv'] / n_batch * max(X, Y, Z) / 128
         if tv['smooth_grad_tv'] > 0 and tv['sdf_tv'] > 0 and dense:
@@ -324,17 +343,17 @@ class FusedFineStep:
             call('vx_fd_gradient_backward', self.dG, X, Y, Z, m._voxel_size_host, self.sdf_grad)
         if tv['sdf_tv'] > 0:
             call('vx_total_variation_add_grad', m.sdf.grid, self.sdf_grad, None, wt, wt, wt,
-                 int(global_step < c['tv_dense_before']), X, Y, Z, m.sdf.grid.numel())
+                 int(dense), X, Y, Z, m.sdf.grid.numel())
 
     @torch.no_grad()
     def optimizer_step(self, only=None, advance=True):
         """lib/utils.py:83-199 with betas (0.9, 0.99), eps 1e-8 (lib/utils.py:229); grads are zeroed in the same pass.
         only: restrict to these group names (the multi-GPU step updates k0 while the sdf all-reduce is in flight)."""
-        if advance:
+        if advance and self._dev_consts is None:
             self.adam_steps += 1
-        step, beta1, beta2, eps = self.adam_steps, 0.9, 0.99, 1e-8
+        step, beta1, beta2, eps = max(self.adam_steps, 1), 0.9, 0.99, 1e-8
         bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
-        for name, params, _ in self.groups:
+        for gi, (name, params, _) in enumerate(self.groups):
             if only is not None and name not in only:
                 continue
             lr = self.lr[name]
@@ -351,7 +370,8 @@ class FusedFineStep:
                 if touched is not None and self.bitmap_probe is not None:
                     self.bitmap_probe.append((touched.clone(), live.clone()))
                 call('vx_adam_step', _storage(p.data), _storage(p.grad), _storage(st[0]), _storage(st[1]), None, p.numel(),
-                     beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1, touched, live, self.C)
+                     beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1, touched, live, self.C,
+                     None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
                 if touched is not None:
                     call('vx_bitmap_merge', live, touched, touched.numel())
                 if timed:
@@ -363,8 +383,65 @@ class FusedFineStep:
         if self.k0_live is not None:
             self.k0_live.fill_(-1)
 
+    def apply_lr_decay(self):
+        """run.py:679-683: every learning rate times 0.1 ** (1 / (lrate_decay * 1000)) after each optimizer step."""
+        f = 0.1 ** (1 / (self.cfg['lrate_decay'] * 1000))
+        for k in self.lr:
+            self.lr[k] *= f
+
+    def _step_body(self, rays_o, rays_d, viewdirs, target, global_step, flags):
+        loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
+        self.regularise(global_step, flags=flags)
+        self.optimizer_step()
+        return loss
+
+    def _step_graph(self, rays_o, rays_d, viewdirs, target, global_step):
+        """The same step as one CUDA-graph launch.  Per (TV iteration?, dense TV?) variant: the first occurrence runs
+        eagerly (lazy allocations, kernel attributes), the second is captured, later ones are replayed.  Host side per
+        step: the NeuS schedule and the Adam scalars (a 64-byte upload) and one fused copy of the batch into the static
+        input buffers."""
+        m = self.m
+        flags = self.tv_flags(global_step)
+        if flags not in self._eager_seen:
+            self._eager_seen.add(flags)
+            return self._step_body(rays_o, rays_d, viewdirs, target, global_step, flags)
+        s_val = 1. / (global_step + m.s_ratio / m.s_start - m.step_start) * m.s_ratio          # lib/voxurf_fine.py:466-473
+        m._s_val_host = float(np.float32(s_val))
+        self.adam_steps += 1
+        step, beta1, beta2 = self.adam_steps, 0.9, 0.99
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        host = [float(np.float32(1.0) / np.float32(m._s_val_host)), 0.0]
+        for name, _, _ in self.groups:
+            host += [self.lr[name] / bc1, math.sqrt(bc2)]
+        self.consts[:len(host)].copy_(torch.tensor(host, dtype=torch.float32))
+        torch._foreach_copy_([self.in_o, self.in_d, self.in_v, self.in_t], [rays_o, rays_d, viewdirs, target])
+        g = self._graphs.get(flags)
+        if g is None:
+            assert self.timings is None and self.bitmap_probe is None, 'kernel timing hooks need use_graph=False'
+            self._dev_consts = self.consts
+            g = torch.cuda.CUDAGraph()
+            from ._lib import launch_count
+            l0 = launch_count()
+            try:
+                with torch.cuda.graph(g):
+                    self._step_body(self.in_o, self.in_d, self.in_v, self.in_t, None, flags)
+            finally:
+                self._dev_consts = None
+            self._graphs[flags] = g
+            self._graph_launches[flags] = launch_count() - l0
+        g.replay()
+        self.launches_replayed += self._graph_launches[flags]
+        return self.loss
+
+    def sync_s_val(self):
+        """Write the host-side NeuS s_val into the model's s_val parameter (graph replays keep it on the host only)."""
+        if hasattr(self.m, '_s_val_host'):
+            self.m.s_val.data.fill_(self.m._s_val_host)
+
     def step(self, rays_o, rays_d, viewdirs, target, global_step, grad_sync=None):
         """One training iteration (run.py:600-659).  grad_sync: optional callable run between backward and TV/Adam."""
+        if self.use_graph and grad_sync is None and self.timings is None and self.bitmap_probe is None:
+            return self._step_graph(rays_o, rays_d, viewdirs, target, global_step)
         loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
         if grad_sync is None and self.world > 1:
             # overlap: the sdf / MLP all-reduces run on the NCCL stream while k0 is re-scattered and updated

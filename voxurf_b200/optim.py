@@ -79,7 +79,7 @@ class Adam(torch.optim.Optimizer):
                     ev[0].record()
                 call('vx_adam_step', _storage(p.data), _storage(g), _storage(state['exp_avg']),
                      _storage(state['exp_avg_sq']), per_lr, p.numel(), beta1, beta2, 1 - beta1, 1 - beta2, step_size,
-                     math.sqrt(bias_correction2), group['eps'], 0, int(self.zero_grad_in_step), None, None, 1)
+                     math.sqrt(bias_correction2), group['eps'], 0, int(self.zero_grad_in_step), None, None, 1, None)
                 if timed:
                     ev[1].record()
                     self.timings.append(ev)
