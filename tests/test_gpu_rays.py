@@ -57,7 +57,8 @@ def test_hit_coarse_geo_exact():
         H, W, K, c2w = S.make_view(seed=60 + seed, H=h, W=w)
         ro, rd, _ = R.view_rays(H, W, T(K), T(c2w))
         ro = ro.contiguous()
-        hit = m.hit_coarse_geo(ro.to(DEV), rd.to(DEV), near=0.3, far=6.0, stepsize=0.5, bg=0.0)
+        # far = 0.5 would end every ray before the box if it were honoured: the reference overrides it with 1e9 (hazard 4)
+        hit = m.hit_coarse_geo(ro.to(DEV), rd.to(DEV), near=0.3, far=0.5, stepsize=0.5, bg=0.0)
         ref = R.hit_coarse_geo(om['mask_cache'], ro, rd, XYZ_MIN, XYZ_MAX, 0.3, 0.5, om['voxel_size'])
         assert hit.shape == (H, W) and hit.dtype == torch.bool
         assert torch.equal(hit.cpu(), ref) and 0 < int(ref.sum()) < ref.numel()
