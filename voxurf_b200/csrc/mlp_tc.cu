@@ -818,3 +818,53 @@ VX_API int vx_umma_probe(const float* A_img, int a_floats, const float* B_img, i
                                             (uint32_t)idesc, N, D);
   return vx_check_launch("vx_umma_probe");
 }
+
+// MMA issue-rate probe (development): `n_mma` back-to-back M = 128, K = 8 TF32 MMAs of width N on zeroed operands, A from
+// shared memory (form 0) or from TMEM (form 1), accumulating into one D tile (n_acc = 1) or alternating between two;
+// cycles[block] = clock64 ticks from the first issue to the completion of the last MMA.
+__global__ void __launch_bounds__(128, 1)
+k_umma_rate(int n_mma, int N, int form, int n_acc, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  float* sA = reinterpret_cast<float*>(smem_raw);
+  float* sB = reinterpret_cast<float*>(smem_raw + 16384);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 4096; i += 128) sA[i] = 0.f;
+  for (int i = tid; i < 8192; i += 128) sB[i] = 0.f;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    const uint64_t da = make_desc(smem_u32(sA), 128 * 16, 128);
+    const uint64_t db = make_desc(smem_u32(sB), N * 16, 128);
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      const uint32_t d = tmem + ((n_acc > 1 && (i & 1)) ? 256 : 0);
+      if (form == 0) umma_tf32_ss(d, da, db, idesc, 1);
+      else umma_tf32_ts(d, tmem + 496, db, idesc, 1);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+VX_API int vx_umma_rate(int n_blocks, int n_mma, int N, int form, int n_acc, int64_t* cycles, cudaStream_t st) {
+  VX_REQUIRE(N % 16 == 0 && N >= 16 && N <= 240 && n_blocks >= 1, "vx_umma_rate", "sizes");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    attr_set = true;
+  }
+  k_umma_rate<<<n_blocks, 128, 65536, st>>>(n_mma, N, form, n_acc, reinterpret_cast<long long*>(cycles));
+  return vx_check_launch("vx_umma_rate");
+}
