@@ -513,9 +513,9 @@ VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, 
 //   warps 0-11      split a slice element-wise (hi in place, lo into a twin buffer; 128-bit loads / stores) -- the row
 //                   image already is the MN-major operand layout, nothing is transposed;
 //   warp 12 lane 0  issues the MMAs of a slice, both operands MN-major (instruction-descriptor bits 15 / 16): both
-//                   128-row M tiles (features 0..127 / 128..255) into two TMEM accumulators, plus N = 16 MMAs against
-//                   a constant K-major ones tile whose first column is the bias gradient; tcgen05.commit hands the
-//                   stage back to the producer.
+//                   128-row M tiles (features 0..127 / 128..255) into two TMEM accumulators, N = FB + 16 wide: the B slice
+//                   carries a constant ones feature whose accumulator column is the bias gradient; tcgen05.commit hands
+//                   the stage back to the producer.
 // Partial sums leave as vector atomics (warps 0-3).
 // ---------------------------------------------------------------------------------------------
 #define DW_KC 16
@@ -540,11 +540,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 #define DW_RAW_STAGES 6      // raw slices in flight (hi parts are produced in place): covers the HBM latency
 #define DW_LO_STAGES 2       // lo twins only live from the split to the MMAs of a slice
+// The B slice lives in shared memory with one extra 32-feature group per 4-row group (SBO = (FB/32 + 1) * 512 bytes):
+// feature FB of the hi part is the constant 1 (everything else in the group and the whole group of the lo part is 0),
+// written once at kernel start and never touched by the copies.  The MMAs then run with N = FB + 16 and column FB of
+// the accumulator is sum_r A[r][m], the bias gradient, for free -- a separate N = 16 MMA would cost the 96-clock floor of
+// every tcgen05.mma, as much as N = 128.
+#define DW_A_FLOATS (DW_KC * MLP_MAXW)                          // 12 KB
+#define DW_B_FLOATS ((DW_KC / 4) * (MLP_MAXW / 32 + 1) * 128)   // 14 KB
 struct __align__(16) DwmSmem {
-  float raw[DW_RAW_STAGES][2][DW_KC * MLP_MAXW];                // A slice, B slice (raw -> hi), 12 KB each
-  float lo[DW_LO_STAGES][2][DW_KC * MLP_MAXW];                  // A_lo, B_lo
-  float slack[1024];                                            // M tile 1 over-reads up to 2 KB past the last slice
-  float ones[2 * 16 * 4];
+  float rawA[DW_RAW_STAGES][DW_A_FLOATS];                       // A slices (raw -> hi)
+  float rawB[DW_RAW_STAGES][DW_B_FLOATS];                       // B slices (raw -> hi) + ones group
+  float loA[DW_LO_STAGES][DW_A_FLOATS];
+  float loB[DW_LO_STAGES][DW_B_FLOATS];
+  float slack[1024];                                            // M tile 1 over-reads up to 2 KB past an A slice
   uint64_t full[DW_RAW_STAGES], empty[DW_RAW_STAGES];
   uint64_t split[DW_LO_STAGES], lo_empty[DW_LO_STAGES];
   uint64_t bar_acc;
@@ -580,7 +588,14 @@ k_mlp_dw(const __grid_constant__ DwBatch batch, const int* __restrict__ n_rows_d
     mbar_init(&s.bar_acc, 1);
     fence_barrier_init();
   }
-  if (tid < 128) s.ones[tid] = ((tid >> 2) % 16 == 0) ? 1.f : 0.f;   // K-major [chunk][feature][row]: feature 0 of both chunks
+  const int b_groups = FB >> 5;                             // 32-feature groups of the B image; the ones group follows
+  const uint32_t b_sbo = (uint32_t)(b_groups + 1) * 512;    // bytes between 4-row groups of the B slice in shared memory
+  for (int i = tid; i < (DW_RAW_STAGES + DW_LO_STAGES) * (DW_KC / 4) * 128; i += DW_THREADS) {
+    const int buf = i / ((DW_KC / 4) * 128), kg = (i / 128) % (DW_KC / 4), e = i % 128;   // e: float within the 512-byte atom
+    float* base = (buf < DW_RAW_STAGES ? s.rawB[buf] : s.loB[buf - DW_RAW_STAGES]) + kg * (b_sbo / 4) + b_groups * 128;
+    // feature 0 of the group, row r of the 4-row group: byte (r * 128) + ((0 ^ r) * 32)
+    base[e] = (buf < DW_RAW_STAGES && (e & 31) == ((e >> 5) << 3)) ? 1.f : 0.f;
+  }
   if (warp == 0) tmem_alloc(&s.tmem_base, MLP_TMEM_COLS);
   fence_proxy_async();
   tc_fence_before();
@@ -598,20 +613,20 @@ k_mlp_dw(const __grid_constant__ DwBatch batch, const int* __restrict__ n_rows_d
         if (i >= DW_RAW_STAGES) mbar_wait(&s.empty[st], (i / DW_RAW_STAGES - 1) & 1);
         const int64_t sl = (int64_t)cta + (int64_t)i * n_cta;
         mbar_expect_tx(&s.full[st], a_bytes + b_bytes);
-        bulk_g2s(s.raw[st][0], J.A + sl * DW_KC * FA, a_bytes, &s.full[st]);
-        bulk_g2s(s.raw[st][1], J.B + sl * DW_KC * FB, b_bytes, &s.full[st]);
+        bulk_g2s(s.rawA[st], J.A + sl * DW_KC * FA, a_bytes, &s.full[st]);
+#pragma unroll
+        for (int kg = 0; kg < DW_KC / 4; ++kg)   // one copy per 4-row group: the shared-memory stride leaves room for the ones group
+          bulk_g2s(s.rawB[st] + kg * (b_sbo / 4), J.B + sl * DW_KC * FB + kg * 4 * FB, b_bytes / (DW_KC / 4), &s.full[st]);
       }
   } else if (warp == DW_T_THREADS / 32) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_major(MLP_ROWS, FB, 1, 1);
-      const uint32_t idesc1 = make_idesc_tf32_major(MLP_ROWS, 16, 1, 0);
-      const uint64_t d_ones = make_desc(smem_u32(s.ones), 16 * 16, 128);
-      const uint32_t a_sbo = 16u * FA, b_sbo = 16u * FB;          // bytes between 4-row groups; 512 between 32-feature groups
+      const uint32_t idesc = make_idesc_tf32_major(MLP_ROWS, FB + 16, 1, 1);   // + the ones group: column FB = bias gradient
+      const uint32_t a_sbo = 16u * FA;                             // bytes between 4-row groups; 512 between 32-feature groups
       // descriptors of stage 0 / K-step 0 / M tile 0; the others differ only in the start-address field (bytes >> 4)
-      const uint64_t da_hi0 = make_desc_mn(smem_u32(s.raw[0][0]), 512, a_sbo), db_hi0 = make_desc_mn(smem_u32(s.raw[0][1]), 512, b_sbo);
-      const uint64_t da_lo0 = make_desc_mn(smem_u32(s.lo[0][0]), 512, a_sbo), db_lo0 = make_desc_mn(smem_u32(s.lo[0][1]), 512, b_sbo);
-      constexpr uint32_t kRawStage = 2 * DW_KC * MLP_MAXW * 4 >> 4, kLoStage = kRawStage;
+      const uint64_t da_hi0 = make_desc_mn(smem_u32(s.rawA[0]), 512, a_sbo), db_hi0 = make_desc_mn(smem_u32(s.rawB[0]), 512, b_sbo);
+      const uint64_t da_lo0 = make_desc_mn(smem_u32(s.loA[0]), 512, a_sbo), db_lo0 = make_desc_mn(smem_u32(s.loB[0]), 512, b_sbo);
+      constexpr uint32_t kStageA = DW_A_FLOATS * 4 >> 4, kStageB = DW_B_FLOATS * 4 >> 4;
       for (int i = 0; i < my_slices; ++i) {
         const int rs = i % DW_RAW_STAGES, ls = i % DW_LO_STAGES;
         mbar_wait(&s.split[ls], (i / DW_LO_STAGES) & 1);
@@ -621,15 +636,13 @@ k_mlp_dw(const __grid_constant__ DwBatch batch, const int* __restrict__ n_rows_d
           for (int kk = 0; kk < DW_KC / 8; ++kk) {             // one MMA K-step = two 4-row groups
             const uint32_t a_off = ((uint32_t)(2 * kk) * a_sbo + (uint32_t)mt * (MLP_ROWS / 32) * 512) >> 4;
             const uint32_t b_off = ((uint32_t)(2 * kk) * b_sbo) >> 4;
-            const uint64_t da_hi = da_hi0 + rs * kRawStage + a_off, da_lo = da_lo0 + ls * kLoStage + a_off;
-            const uint64_t db_hi = db_hi0 + rs * kRawStage + b_off, db_lo = db_lo0 + ls * kLoStage + b_off;
+            const uint64_t da_hi = da_hi0 + rs * kStageA + a_off, da_lo = da_lo0 + ls * kStageA + a_off;
+            const uint64_t db_hi = db_hi0 + rs * kStageB + b_off, db_lo = db_lo0 + ls * kStageB + b_off;
             const uint32_t d = tmem + mt * 256;
             const uint32_t acc = (i > 0) || (kk > 0);
             umma_tf32_ss(d, da_hi, db_hi, idesc, acc);
             umma_tf32_ss(d, da_hi, db_lo, idesc, 1);
             umma_tf32_ss(d, da_lo, db_hi, idesc, 1);
-            umma_tf32_ss(d + FB, da_hi, d_ones, idesc1, acc);  // bias gradient columns [FB, FB + 16)
-            umma_tf32_ss(d + FB, da_lo, d_ones, idesc1, 1);
           }
         }
         umma_commit(&s.empty[rs]);
@@ -644,24 +657,28 @@ k_mlp_dw(const __grid_constant__ DwBatch batch, const int* __restrict__ n_rows_d
       const int rs = i % DW_RAW_STAGES, ls = i % DW_LO_STAGES;
       mbar_wait(&s.full[rs], (i / DW_RAW_STAGES) & 1);
       if (i >= DW_LO_STAGES) mbar_wait(&s.lo_empty[ls], (i / DW_LO_STAGES - 1) & 1);
-      float4* hiA = reinterpret_cast<float4*>(s.raw[rs][0]);
-      float4* hiB = reinterpret_cast<float4*>(s.raw[rs][1]);
-      float4* loA = reinterpret_cast<float4*>(s.lo[ls][0]);
-      float4* loB = reinterpret_cast<float4*>(s.lo[ls][1]);
+      float4* hiA = reinterpret_cast<float4*>(s.rawA[rs]);
+      float4* hiB = reinterpret_cast<float4*>(s.rawB[rs]);
+      float4* loA = reinterpret_cast<float4*>(s.loA[ls]);
+      float4* loB = reinterpret_cast<float4*>(s.loB[ls]);
+      const int b_sbo4 = (int)(b_sbo >> 4);                        // float4s per 4-row group of the B slice in shared memory
       if (na4 == 2 * DW_T_THREADS && nb4 == 2 * DW_T_THREADS) {   // 192 x 192: four independent 128-bit loads per thread
-        const float4 a0 = hiA[tid], a1 = hiA[tid + DW_T_THREADS], b0 = hiB[tid], b1 = hiB[tid + DW_T_THREADS];
-        dw_split4(hiA, loA, tid, a0);
-        dw_split4(hiA, loA, tid + DW_T_THREADS, a1);
-        dw_split4(hiB, loB, tid, b0);
-        dw_split4(hiB, loB, tid + DW_T_THREADS, b1);
+        const int i0 = tid, i1 = tid + DW_T_THREADS;
+        const int j0 = (i0 / MLP_MAXW) * b_sbo4 + i0 % MLP_MAXW, j1 = (i1 / MLP_MAXW) * b_sbo4 + i1 % MLP_MAXW;
+        const float4 a0 = hiA[i0], a1 = hiA[i1], b0 = hiB[j0], b1 = hiB[j1];
+        dw_split4(hiA, loA, i0, a0);
+        dw_split4(hiA, loA, i1, a1);
+        dw_split4(hiB, loB, j0, b0);
+        dw_split4(hiB, loB, j1, b1);
       } else {
         for (int idx = tid; idx < max(na4, nb4); idx += DW_T_THREADS) {
           const bool va = idx < na4, vb = idx < nb4;
+          const int j = (idx / FB) * b_sbo4 + idx % FB;             // FB float4s per 4-row group
           float4 xa, xb;
           if (va) xa = hiA[idx];
-          if (vb) xb = hiB[idx];
+          if (vb) xb = hiB[j];
           if (va) dw_split4(hiA, loA, idx, xa);
-          if (vb) dw_split4(hiB, loB, idx, xb);
+          if (vb) dw_split4(hiB, loB, j, xb);
         }
       }
       fence_proxy_async();           // every thread: its own stores -> async proxy
