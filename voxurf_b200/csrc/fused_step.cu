@@ -30,60 +30,99 @@ struct SdfNeighbourhood {
   float ext[3][2][4];   // [axis][0: index -1, 1: index +2][the other two axes' bits, lower axis first]
 };
 
-__device__ __forceinline__ float nb_load(const float* __restrict__ grid, const VxGrid& g, int x, int y, int z) {
-  const bool ok = (x >= 0) & (x < g.X) & (y >= 0) & (y < g.Y) & (z >= 0) & (z < g.Z);
-  return ok ? __ldg(grid + ((int64_t)x * g.Y + y) * g.Z + z) : 0.f;
+// one axis of a trilinear tap, spelled like vx_make_tap: floor index, the two weights, validity of index i0 / i0 + 1
+struct AxisTap {
+  int i0;
+  float w0, w1;
+  bool v0, v1;
+};
+__device__ __forceinline__ AxisTap axis_tap(float c, int size) {
+  const float f = floorf(c);
+  AxisTap a;
+  a.i0 = (int)f;
+  a.w1 = c - f;
+  a.w0 = (f + 1.f) - c;
+  a.v0 = (a.i0 >= 0) & (a.i0 < size);
+  a.v1 = (a.i0 + 1 >= 0) & (a.i0 + 1 < size);
+  return a;
 }
 
 __device__ __forceinline__ void nb_fill(const float* __restrict__ grid, const VxGrid& g, int cx, int cy, int cz,
                                         SdfNeighbourhood& nb) {
+  // validity of the cell indices -1..2 on each axis, once; every voxel then costs two ANDs and an add
+  bool okx[4], oky[4], okz[4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) nb.cube[c] = nb_load(grid, g, cx + ((c >> 2) & 1), cy + ((c >> 1) & 1), cz + (c & 1));
+  for (int o = 0; o < 4; ++o) {
+    okx[o] = (cx + o - 1 >= 0) & (cx + o - 1 < g.X);
+    oky[o] = (cy + o - 1 >= 0) & (cy + o - 1 < g.Y);
+    okz[o] = (cz + o - 1 >= 0) & (cz + o - 1 < g.Z);
+  }
+  const int sY = g.Z, sX = g.Y * g.Z;
+  const float* base = grid + ((int64_t)cx * g.Y + cy) * g.Z + cz;
+  auto ld = [&](int dx, int dy, int dz) -> float {   // offsets -1..2, compile-time after unrolling
+    return (okx[dx + 1] & oky[dy + 1] & okz[dz + 1]) ? __ldg(base + dx * sX + dy * sY + dz) : 0.f;
+  };
+#pragma unroll
+  for (int c = 0; c < 8; ++c) nb.cube[c] = ld((c >> 2) & 1, (c >> 1) & 1, c & 1);
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
     const int o = m ? 2 : -1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      nb.ext[0][m][i] = nb_load(grid, g, cx + ((i >> 1) & 1), cy + (i & 1), cz + o);        // Z displaced: bits (Y, X)
-      nb.ext[1][m][i] = nb_load(grid, g, cx + ((i >> 1) & 1), cy + o, cz + (i & 1));        // Y displaced: bits (Z, X)
-      nb.ext[2][m][i] = nb_load(grid, g, cx + o, cy + ((i >> 1) & 1), cz + (i & 1));        // X displaced: bits (Z, Y)
+      nb.ext[0][m][i] = ld((i >> 1) & 1, i & 1, o);        // Z displaced: bits (Y, X)
+      nb.ext[1][m][i] = ld((i >> 1) & 1, o, i & 1);        // Y displaced: bits (Z, X)
+      nb.ext[2][m][i] = ld(o, (i >> 1) & 1, i & 1);        // X displaced: bits (Z, Y)
     }
   }
 }
 
-// tap displaced by kS (-1 / +1) cells along axis kA (0 = Z, 1 = Y, 2 = X), or the centre cell (kS = 0)
+// Trilinear tap from its three axis parts (az: Z / fastest, ay: Y, ax: X), displaced by kS cells along axis kA relative
+// to the neighbourhood's anchor cell (kS = 0: the anchor cell itself).  Weights (wz * wy) * wx, corner order, the
+// validity predicates and the accumulation are those of vx_make_tap + vx_tap_eval.
 template <int kA, int kS>
-__device__ __forceinline__ float nb_tap_eval(const SdfNeighbourhood& nb, const VxTap& t) {
+__device__ __forceinline__ float nb_tap_eval(const SdfNeighbourhood& nb, const AxisTap& az, const AxisTap& ay, const AxisTap& ax) {
   float acc = 0.f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
+    const int bz = c & 1, by = (c >> 1) & 1, bx = (c >> 2) & 1;
+    const float w = (bz ? az.w1 : az.w0) * (by ? ay.w1 : ay.w0) * (bx ? ax.w1 : ax.w0);
+    const bool valid = (bz ? az.v1 : az.v0) & (by ? ay.v1 : ay.v0) & (bx ? ax.v1 : ax.v0);
     const int bit = (c >> kA) & 1;
     const int pos = kS + bit;                                   // cell index on the displaced axis: -1..2
     const int oi = (kA == 0) ? (c >> 1) : (kA == 1) ? ((c & 1) | ((c >> 1) & 2)) : (c & 3);
     const float v = (pos == -1) ? nb.ext[kA][0][oi] : (pos == 2) ? nb.ext[kA][1][oi] : nb.cube[(c & ~(1 << kA)) | (pos << kA)];
-    if (t.off[c] >= 0) acc += v * t.w[c];
+    if (valid) acc += v * w;
   }
   return acc;
 }
 
+// value of the tap at index coordinates (ix, iy, iz) whose axis parts are (az, ay, ax); from the neighbourhood when the
+// tap's cell is the expected one, from memory otherwise
 template <int kA, int kS>
 __device__ __forceinline__ float sdf_tap_value(const VxGrid& g, const float* __restrict__ grid, const SdfNeighbourhood& nb,
-                                               int cx, int cy, int cz, float ix, float iy, float iz) {
+                                               int cx, int cy, int cz, const AxisTap& az, const AxisTap& ay, const AxisTap& ax,
+                                               float ix, float iy, float iz) {
+  const bool cached = (ax.i0 == cx + (kA == 2 ? kS : 0)) & (ay.i0 == cy + (kA == 1 ? kS : 0)) & (az.i0 == cz + (kA == 0 ? kS : 0));
+  if (cached) return nb_tap_eval<kA, kS>(nb, az, ay, ax);
   VxTap t;
   vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
-  const int ex = cx + (kA == 2 ? kS : 0), ey = cy + (kA == 1 ? kS : 0), ez = cz + (kA == 0 ? kS : 0);
-  const bool cached = ((int)floorf(iz) == ex) & ((int)floorf(iy) == ey) & ((int)floorf(ix) == ez);
-  return cached ? nb_tap_eval<kA, kS>(nb, t) : vx_tap_eval(grid, t);
+  return vx_tap_eval(grid, t);
 }
 
+// (f(+1) - f(-1)) / (c(+1) - c(-1)) / voxel_size along axis kA; sz / sy / sx: the axis parts of the shared, undisplaced
+// (clamped, round-tripped) coordinates tc.c[]
 template <int kA>
 __device__ __forceinline__ float sdf_axis_gradient(const VxGrid& g, const float* __restrict__ grid, const SdfNeighbourhood& nb,
-                                                   const SdfTapCoords& tc, int cx, int cy, int cz, float voxel_size) {
+                                                   const SdfTapCoords& tc, int cx, int cy, int cz, const AxisTap& sz,
+                                                   const AxisTap& sy, const AxisTap& sx, float voxel_size) {
   float ix, iy, iz;
+  const int size = axis_size(g, kA);
   const float cm = sdf_tap_coords(g, tc, kA, -1.f, ix, iy, iz);
-  const float fm = sdf_tap_value<kA, -1>(g, grid, nb, cx, cy, cz, ix, iy, iz);
+  const AxisTap dm = axis_tap(kA == 0 ? ix : (kA == 1 ? iy : iz), size);
+  const float fm = sdf_tap_value<kA, -1>(g, grid, nb, cx, cy, cz, kA == 0 ? dm : sz, kA == 1 ? dm : sy, kA == 2 ? dm : sx, ix, iy, iz);
   const float cp = sdf_tap_coords(g, tc, kA, 1.f, ix, iy, iz);
-  const float fp = sdf_tap_value<kA, 1>(g, grid, nb, cx, cy, cz, ix, iy, iz);
+  const AxisTap dp = axis_tap(kA == 0 ? ix : (kA == 1 ? iy : iz), size);
+  const float fp = sdf_tap_value<kA, 1>(g, grid, nb, cx, cy, cz, kA == 0 ? dp : sz, kA == 1 ? dp : sy, kA == 2 ? dp : sx, ix, iy, iz);
   return __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp, cm)), voxel_size);
 }
 
@@ -102,15 +141,17 @@ __global__ void __launch_bounds__(256) k_sdf_alpha_fwd(VxGrid g, const float* __
     point_to_index(g, px, py, pz, ix, iy, iz);
     SdfTapCoords tc;
     sdf_tap_setup(g, px, py, pz, tc);
-    // neighbourhood anchored at the cell of the displaced taps' shared (clamped, round-tripped) coordinates
-    const int cz = (int)floorf(tc.c[0]), cy = (int)floorf(tc.c[1]), cx = (int)floorf(tc.c[2]);
+    // neighbourhood anchored at the cell of the displaced taps' shared (clamped, round-tripped) coordinates; the axis
+    // parts of those coordinates are shared by the six displaced taps (each replaces one of them)
+    const AxisTap sz = axis_tap(tc.c[0], g.Z), sy = axis_tap(tc.c[1], g.Y), sx = axis_tap(tc.c[2], g.X);
+    const int cz = sz.i0, cy = sy.i0, cx = sx.i0;
     SdfNeighbourhood nb;
     nb_fill(grid, g, cx, cy, cz, nb);
-    const float s = sdf_tap_value<0, 0>(g, grid, nb, cx, cy, cz, ix, iy, iz);
+    const float s = sdf_tap_value<0, 0>(g, grid, nb, cx, cy, cz, axis_tap(ix, g.Z), axis_tap(iy, g.Y), axis_tap(iz, g.X), ix, iy, iz);
     // reference axis order z,y,x
-    const float gz = sdf_axis_gradient<0>(g, grid, nb, tc, cx, cy, cz, voxel_size);
-    const float gy = sdf_axis_gradient<1>(g, grid, nb, tc, cx, cy, cz, voxel_size);
-    const float gx = sdf_axis_gradient<2>(g, grid, nb, tc, cx, cy, cz, voxel_size);
+    const float gz = sdf_axis_gradient<0>(g, grid, nb, tc, cx, cy, cz, sz, sy, sx, voxel_size);
+    const float gy = sdf_axis_gradient<1>(g, grid, nb, tc, cx, cy, cz, sz, sy, sx, voxel_size);
+    const float gx = sdf_axis_gradient<2>(g, grid, nb, tc, cx, cy, cz, sz, sy, sx, voxel_size);
     const int r = pts.ray_id[p];
     const float true_cos = __fadd_rn(__fadd_rn(__fmul_rn(viewdirs[3 * r], gx), __fmul_rn(viewdirs[3 * r + 1], gy)),
                                      __fmul_rn(viewdirs[3 * r + 2], gz));
