@@ -254,55 +254,46 @@ __global__ void k_row_features(VxGrid gs, const float* __restrict__ sdf_grid, Vx
 #pragma unroll
     for (int d = 0; d < 3; ++d) xn[d] = __fdiv_rn(__fsub_rn(p[d], gs.min[d]), __fsub_rn(gs.max[d], gs.min[d]));
     int c1 = 0, c2 = kC;
-    if (sub == 0) {
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { x1[c1 + d] = xn[d]; x2[c2 + d] = xn[d]; }
-    }
-    c1 += 3; c2 += 3;
-    if (sub == 0) {
-    for (int d = 0; d < 3; ++d)
-      for (int f = 0; f < lay.P; ++f) {
-        const float e = __fmul_rn(xn[d], (float)(1 << f));
-        x1[c1 + d * lay.P + f] = sinf(e);
-        x1[c1 + 3 * lay.P + d * lay.P + f] = cosf(e);
-      }
-    }
-    c1 += 6 * lay.P;
-    if (sub == 0) {
-    for (int d = 0; d < 3; ++d)
-      for (int f = 0; f < lay.P2; ++f) {
-        const float e = __fmul_rn(xn[d], (float)(1 << f));
-        x2[c2 + d * lay.P2 + f] = sinf(e);
-        x2[c2 + 3 * lay.P2 + d * lay.P2 + f] = cosf(e);
-      }
-    }
-    c2 += 6 * lay.P2;
     float vd[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) vd[d] = viewdirs[3 * r + d];
+    // The sin / cos evaluations dominate this kernel: both networks take the same encodings of the same arguments, so
+    // every (dimension, frequency) pair is evaluated once, written to both rows, and the pairs are dealt round-robin
+    // to the four sub-threads of the row.
     if (sub == 0) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) { x1[c1 + d] = vd[d]; x2[c2 + d] = vd[d]; }
+      for (int d = 0; d < 3; ++d) { x1[c1 + d] = xn[d]; x2[c2 + d] = xn[d]; }
     }
     c1 += 3; c2 += 3;
-    if (sub == 0) {
-    for (int d = 0; d < 3; ++d)
-      for (int f = 0; f < lay.Vp; ++f) {
-        const float e = __fmul_rn(vd[d], (float)(1 << f));
-        x1[c1 + d * lay.Vp + f] = sinf(e);
-        x1[c1 + 3 * lay.Vp + d * lay.Vp + f] = cosf(e);
+    {
+      const int Pm = max(lay.P, lay.P2);
+      for (int q = sub; q < 3 * Pm; q += 4) {
+        const int d = q / Pm, f = q - d * Pm;
+        const float e = __fmul_rn(xn[d], (float)(1 << f));
+        float sn, cs;
+        sincosf(e, &sn, &cs);
+        if (f < lay.P) { x1[c1 + d * lay.P + f] = sn; x1[c1 + 3 * lay.P + d * lay.P + f] = cs; }
+        if (f < lay.P2) { x2[c2 + d * lay.P2 + f] = sn; x2[c2 + 3 * lay.P2 + d * lay.P2 + f] = cs; }
       }
     }
-    c1 += 6 * lay.Vp;
-    if (sub == 0) {
-    for (int d = 0; d < 3; ++d)
-      for (int f = 0; f < lay.V2; ++f) {
+    c1 += 6 * lay.P; c2 += 6 * lay.P2;
+    if (sub == 1) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { x1[c1 + d] = vd[d]; x2[c2 + d] = vd[d]; }
+    }
+    c1 += 3; c2 += 3;
+    {
+      const int Vm = max(lay.Vp, lay.V2);
+      for (int q = sub; q < 3 * Vm; q += 4) {
+        const int d = q / Vm, f = q - d * Vm;
         const float e = __fmul_rn(vd[d], (float)(1 << f));
-        x2[c2 + d * lay.V2 + f] = sinf(e);
-        x2[c2 + 3 * lay.V2 + d * lay.V2 + f] = cosf(e);
+        float sn, cs;
+        sincosf(e, &sn, &cs);
+        if (f < lay.Vp) { x1[c1 + d * lay.Vp + f] = sn; x1[c1 + 3 * lay.Vp + d * lay.Vp + f] = cs; }
+        if (f < lay.V2) { x2[c2 + d * lay.V2 + f] = sn; x2[c2 + 3 * lay.V2 + d * lay.V2 + f] = cs; }
       }
     }
-    c2 += 6 * lay.V2;
+    c1 += 6 * lay.Vp; c2 += 6 * lay.V2;
     // ---- centre sdf, gradient (values of the M2-level pass)
     if (sub == 2) x1[c1] = sdf_s[i];
     c1 += 1;
