@@ -30,23 +30,6 @@ struct SdfNeighbourhood {
   float ext[3][2][4];   // [axis][0: index -1, 1: index +2][the other two axes' bits, lower axis first]
 };
 
-// one axis of a trilinear tap, spelled like vx_make_tap: floor index, the two weights, validity of index i0 / i0 + 1
-struct AxisTap {
-  int i0;
-  float w0, w1;
-  bool v0, v1;
-};
-__device__ __forceinline__ AxisTap axis_tap(float c, int size) {
-  const float f = floorf(c);
-  AxisTap a;
-  a.i0 = (int)f;
-  a.w1 = c - f;
-  a.w0 = (f + 1.f) - c;
-  a.v0 = (a.i0 >= 0) & (a.i0 < size);
-  a.v1 = (a.i0 + 1 >= 0) & (a.i0 + 1 < size);
-  return a;
-}
-
 __device__ __forceinline__ void nb_fill(const float* __restrict__ grid, const VxGrid& g, int cx, int cy, int cz,
                                         SdfNeighbourhood& nb) {
   // validity of the cell indices -1..2 on each axis, once; every voxel then costs two ANDs and an add
@@ -269,7 +252,7 @@ __global__ void k_row_features(VxGrid gs, const float* __restrict__ sdf_grid, Vx
       const int Pm = max(lay.P, lay.P2);
       for (int q = sub; q < 3 * Pm; q += 4) {
         const int d = q / Pm, f = q - d * Pm;
-        const float e = __fmul_rn(xn[d], (float)(1 << f));
+        const float e = __fmul_rn(d == 0 ? xn[0] : (d == 1 ? xn[1] : xn[2]), (float)(1 << f));
         float sn, cs;
         sincosf(e, &sn, &cs);
         if (f < lay.P) { x1[c1 + d * lay.P + f] = sn; x1[c1 + 3 * lay.P + d * lay.P + f] = cs; }
@@ -286,7 +269,7 @@ __global__ void k_row_features(VxGrid gs, const float* __restrict__ sdf_grid, Vx
       const int Vm = max(lay.Vp, lay.V2);
       for (int q = sub; q < 3 * Vm; q += 4) {
         const int d = q / Vm, f = q - d * Vm;
-        const float e = __fmul_rn(vd[d], (float)(1 << f));
+        const float e = __fmul_rn(d == 0 ? vd[0] : (d == 1 ? vd[1] : vd[2]), (float)(1 << f));
         float sn, cs;
         sincosf(e, &sn, &cs);
         if (f < lay.Vp) { x1[c1 + d * lay.Vp + f] = sn; x1[c1 + 3 * lay.Vp + d * lay.Vp + f] = cs; }
@@ -307,18 +290,20 @@ __global__ void k_row_features(VxGrid gs, const float* __restrict__ sdf_grid, Vx
     const int L = lay.L;
     SdfTapCoords tc;
     sdf_tap_setup(gs, p[0], p[1], p[2], tc);
+    const AxisTap sz = axis_tap(tc.c[0], gs.Z), sy = axis_tap(tc.c[1], gs.Y), sx = axis_tap(tc.c[2], gs.X);   // shared axis parts
     VxTap t;
     for (int l = sub; l < L; l += 4) {
       float gr[3];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         float ix, iy, iz;
+        const int size = axis_size(gs, a);
         const float cm = sdf_tap_coords(gs, tc, a, -lay.disp[l], ix, iy, iz);
-        vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
-        const float fm = vx_tap_eval(sdf_grid, t);
+        const AxisTap dm = axis_tap(a == 0 ? ix : (a == 1 ? iy : iz), size);
+        const float fm = tap_eval_axes(sdf_grid, gs.Y, gs.Z, VX_AXES(a, dm, sz, sy, sx));
         const float cp = sdf_tap_coords(gs, tc, a, lay.disp[l], ix, iy, iz);
-        vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
-        const float fp = vx_tap_eval(sdf_grid, t);
+        const AxisTap dp = axis_tap(a == 0 ? ix : (a == 1 ? iy : iz), size);
+        const float fp = tap_eval_axes(sdf_grid, gs.Y, gs.Z, VX_AXES(a, dp, sz, sy, sx));
         gr[a] = __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp, cm)), voxel_size);
         x1[c1 + (a * 2 + 0) * L + l] = fm;
         x1[c1 + (a * 2 + 1) * L + l] = fp;
@@ -592,8 +577,8 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
       d_sdf_s[i] = g1[col_sdf];
       d_grad_s[3 * i] = g2[col_grad2]; d_grad_s[3 * i + 1] = g2[col_grad2 + 1]; d_grad_s[3 * i + 2] = g2[col_grad2 + 2];
     }
-    // ---- k0 scatter
-    if (sub == 0) {
+    // ---- k0 scatter: corners 2 sub, 2 sub + 1 of the tap on each of the row's four threads
+    {
       float go[kC];
       bool any = false;
 #pragma unroll
@@ -604,14 +589,10 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
         VxTap t;
         vx_make_tap(ix, iy, iz, gk.X, gk.Y, gk.Z, t);
         const int64_t V = (int64_t)gk.X * gk.Y * gk.Z;
-        if (k0_touched) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (t.off[k] >= 0) atomicOr(k0_touched + (t.off[k] >> 5), 1u << (t.off[k] & 31));
-        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          if (t.off[k] < 0) continue;
+          if ((k >> 1) != sub || t.off[k] < 0) continue;
+          if (k0_touched) atomicOr(k0_touched + (t.off[k] >> 5), 1u << (t.off[k] & 31));
           if (gk.cl) {
             float* dst = k0_grad + (int64_t)t.off[k] * kC;
             if (kC % 4 == 0) {
@@ -631,26 +612,33 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
         }
       }
     }
-    // ---- sample_sdfs backward
+    // ---- sample_sdfs backward: the six taps of a displacement level are built once (axis parts) and used for the
+    //      re-evaluation of the normalised gradient and for the scatter
     const float* dfeat = g1 + col_sdf + 1;
     const float* dgrad = dfeat + 6 * L;
     SdfTapCoords tc;
     sdf_tap_setup(gs, p[0], p[1], p[2], tc);
-    VxTap t, tm;
+    const AxisTap sz = axis_tap(tc.c[0], gs.Z), sy = axis_tap(tc.c[1], gs.Y), sx = axis_tap(tc.c[2], gs.X);
     for (int l = sub; l < L; l += 4) {
+      AxisTap dm[3], dp[3];
+      float cm[3], cp[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float ix, iy, iz;
+        const int size = axis_size(gs, a);
+        cm[a] = sdf_tap_coords(gs, tc, a, -lay.disp[l], ix, iy, iz);
+        dm[a] = axis_tap(a == 0 ? ix : (a == 1 ? iy : iz), size);
+        cp[a] = sdf_tap_coords(gs, tc, a, lay.disp[l], ix, iy, iz);
+        dp[a] = axis_tap(a == 0 ? ix : (a == 1 ? iy : iz), size);
+      }
       float dgr[3] = {dgrad[0 * L + l], dgrad[1 * L + l], dgrad[2 * L + l]};
       if (use_grad_norm && (dgr[0] != 0.f || dgr[1] != 0.f || dgr[2] != 0.f)) {
         float gr[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          float ix, iy, iz;
-          const float cm = sdf_tap_coords(gs, tc, a, -lay.disp[l], ix, iy, iz);
-          vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
-          const float fm = vx_tap_eval(sdf_grid, t);
-          const float cp = sdf_tap_coords(gs, tc, a, lay.disp[l], ix, iy, iz);
-          vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
-          const float fp = vx_tap_eval(sdf_grid, t);
-          gr[a] = __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp, cm)), voxel_size);
+          const float fm = tap_eval_axes(sdf_grid, gs.Y, gs.Z, VX_AXES(a, dm[a], sz, sy, sx));
+          const float fp = tap_eval_axes(sdf_grid, gs.Y, gs.Z, VX_AXES(a, dp[a], sz, sy, sx));
+          gr[a] = __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp[a], cm[a])), voxel_size);
         }
         const float nrm = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
         const float den = nrm + 1e-5f;
@@ -663,18 +651,13 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
       for (int a = 0; a < 3; ++a) {
         float dfm = dfeat[(a * 2 + 0) * L + l];
         float dfp = dfeat[(a * 2 + 1) * L + l];
-        float ix, iy, iz;
-        const float cm = sdf_tap_coords(gs, tc, a, -lay.disp[l], ix, iy, iz);
-        vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, tm);
-        const float cp = sdf_tap_coords(gs, tc, a, lay.disp[l], ix, iy, iz);
-        vx_make_tap(ix, iy, iz, gs.X, gs.Y, gs.Z, t);
         if (dgr[a] != 0.f) {
-          const float d = (dgr[a] / voxel_size) / (cp - cm);
+          const float d = (dgr[a] / voxel_size) / (cp[a] - cm[a]);
           dfp += d;
           dfm -= d;
         }
-        vx_tap_scatter(sdf_grad, tm, dfm);
-        vx_tap_scatter(sdf_grad, t, dfp);
+        tap_scatter_axes(sdf_grad, gs.Y, gs.Z, VX_AXES(a, dm[a], sz, sy, sx), dfm);
+        tap_scatter_axes(sdf_grad, gs.Y, gs.Z, VX_AXES(a, dp[a], sz, sy, sx), dfp);
       }
     }
   }

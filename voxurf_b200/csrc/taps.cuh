@@ -55,6 +55,57 @@ __device__ __forceinline__ float sdf_tap_coords(const VxGrid& g, const SdfTapCoo
 }
 
 
+// one axis of a trilinear tap, spelled like vx_make_tap: floor index, the two weights, validity of index i0 / i0 + 1
+struct AxisTap {
+  int i0;
+  float w0, w1;
+  bool v0, v1;
+};
+__device__ __forceinline__ AxisTap axis_tap(float c, int size) {
+  const float f = floorf(c);
+  AxisTap a;
+  a.i0 = (int)f;
+  a.w1 = c - f;
+  a.w0 = (f + 1.f) - c;
+  a.v0 = (a.i0 >= 0) & (a.i0 < size);
+  a.v1 = (a.i0 + 1 >= 0) & (a.i0 + 1 < size);
+  return a;
+}
+
+// The three axis parts of a tap (az: Z / fastest, ay: Y, ax: X) -> value / scatter, with vx_make_tap's weights
+// (wz * wy) * wx, corner order and zero padding, and vx_tap_eval's / vx_tap_scatter's accumulation.  The displaced taps
+// of sample_sdfs differ from each other in one axis part only, so callers build the shared parts once.
+__device__ __forceinline__ float tap_eval_axes(const float* __restrict__ grid, int Y, int Z, const AxisTap& az, const AxisTap& ay,
+                                               const AxisTap& ax) {
+  const int base = (ax.i0 * Y + ay.i0) * Z + az.i0, sY = Z, sX = Y * Z;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int bz = c & 1, by = (c >> 1) & 1, bx = (c >> 2) & 1;
+    const float w = (bz ? az.w1 : az.w0) * (by ? ay.w1 : ay.w0) * (bx ? ax.w1 : ax.w0);
+    const bool valid = (bz ? az.v1 : az.v0) & (by ? ay.v1 : ay.v0) & (bx ? ax.v1 : ax.v0);
+    if (valid) acc += __ldg(grid + base + bx * sX + by * sY + bz) * w;
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void tap_scatter_axes(float* __restrict__ grad, int Y, int Z, const AxisTap& az, const AxisTap& ay,
+                                                 const AxisTap& ax, float g) {
+  if (g == 0.f) return;   // adding +0 is a no-op
+  const int base = (ax.i0 * Y + ay.i0) * Z + az.i0, sY = Z, sX = Y * Z;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int bz = c & 1, by = (c >> 1) & 1, bx = (c >> 2) & 1;
+    const float w = (bz ? az.w1 : az.w0) * (by ? ay.w1 : ay.w0) * (bx ? ax.w1 : ax.w0);
+    const bool valid = (bz ? az.v1 : az.v0) & (by ? ay.v1 : ay.v0) & (bx ? ax.v1 : ax.v0);
+    if (valid) atomicAdd(grad + base + bx * sX + by * sY + bz, g * w);
+  }
+}
+
+// axis parts of the tap displaced by +-d along axis kA (0 = Z, 1 = Y, 2 = X): `disp` replaces the shared part of axis kA
+#define VX_AXES(kA, disp, sz, sy, sx) ((kA) == 0 ? (disp) : (sz)), ((kA) == 1 ? (disp) : (sy)), ((kA) == 2 ? (disp) : (sx))
+
+
 static inline VxGrid make_grid(int X, int Y, int Z, int C, int cl, const float* mn, const float* mx) {
   VxGrid g;
   g.X = X; g.Y = Y; g.Z = Z; g.C = C; g.cl = cl;
