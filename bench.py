@@ -407,7 +407,10 @@ def main():
             fl = float(np.mean([f for _, f in chain])) * M4
             roof = {'bound': 'tensor', 'kernel': 'k_mlp_chain (fused 4-layer MLP chain on tcgen05, TF32x3; %d rows, 4 launches/step)' % M4,
                     'achieved': fl / (t_chain * 1e-3) / 1e12, 'peak': tf_peak, 'peak_source': tf_src, 'unit': 'TFLOP/s',
-                    'traffic': None, 'ms_per_launch': t_chain, 'algorithmic_flops_per_launch': fl,
+                    # dram read + write bytes per launch, mean of the four chain launches of one step, from
+                    # profiles/r01j_final_launches.md (ncu --set full); only valid for the profiled configuration
+                    'traffic': (1.693e8 if (C == 12 and G == 256 and args.rays == 8192) else None), 'ms_per_launch': t_chain,
+                    'algorithmic_flops_per_launch': fl,
                     'issued_tf32_flops_per_launch': 3 * fl, 'formulation_ceiling_frac': 1.0 / 6.0,
                     'share_of_step': sum(t for t, _ in chain) / args.steps / step_ms}
             roof['frac'] = roof['achieved'] / tf_peak
