@@ -151,10 +151,15 @@ int vx_neus_alpha_backward(const float* viewdirs, const int* ray_id, const int64
 int vx_fd_gradient(const float* sdf, int X, int Y, int Z, float voxel_size, float* grad, cudaStream_t stream);
 int vx_fd_gradient_backward(const float* dgrad, int X, int Y, int Z, float voxel_size, float* dsdf,
                             cudaStream_t stream);
+/* vx_fd_gradient only where `active` (one byte per voxel, groups of 4 along z): the rest of grad is left untouched.  The
+ * smooth-gradient TV reads the gradient grid only within one voxel of the non-empty mask (lib/voxurf_fine.py:417-420) */
+int vx_fd_gradient_active(const float* sdf, int X, int Y, int Z, float voxel_size, const bool* active, float* grad,
+                          cudaStream_t stream);
 /* vx_fd_gradient_backward then the dense unmasked vx_total_variation_add_grad(param) with one pass over grad
- * (run.py:612-655: both sdf regularisers of a fine-stage TV iteration); identical result to the two calls */
+ * (run.py:612-655: both sdf regularisers of a fine-stage TV iteration); identical result to the two calls.
+ * active (optional): voxels outside it have dgrad == 0 at all six neighbours, their FD part is skipped */
 int vx_sdf_regularisers_backward(const float* dgrad, const float* param, int X, int Y, int Z, float voxel_size,
-                                 float wx, float wy, float wz, float* grad, cudaStream_t stream);
+                                 float wx, float wy, float wz, float* grad, const bool* active, cudaStream_t stream);
 /* _gaussian_3dconv / tv_smooth_conv: Conv3d(1,1,k,padding=k//2,'replicate')  lib/voxurf_fine.py:236-258 ;
  * B independent volumes; weight_host is (k,k,k) on the HOST, k in {1,3,5} */
 int vx_conv3d_replicate(const float* in, int B, int X, int Y, int Z, const float* weight_host, int ksize,
@@ -166,6 +171,9 @@ int vx_conv3d_replicate_backward(const float* dout, int B, int X, int Y, int Z, 
 int vx_smooth_grad_tv_scratch_floats(void);
 int vx_smooth_grad_tv(const float* G, const bool* mask, int X, int Y, int Z, const float* weight3_host,
                       float w_over_3n, float* dG, float* scratch, float* loss_out, cudaStream_t stream);
+/* same, but dG is not written outside the mask (zero by definition): for a zero-initialised dG and a static mask */
+int vx_smooth_grad_tv_masked_writes(const float* G, const bool* mask, int X, int Y, int Z, const float* weight3_host,
+                                    float w_over_3n, float* dG, float* scratch, float* loss_out, cudaStream_t stream);
 
 /* total_variation(v, mask)  lib/voxurf_fine.py:956-969 (autograd form used by the coarse stage): loss_out[0] = tv,
  * grad = d tv / d v.  mask (X,Y,Z) bool shared by the C channels or NULL; inv_cnt_host[a] = 1/(3 * #pairs on axis a);

@@ -422,7 +422,7 @@ def test_sdf_regularisers_backward_and_vector_paths_are_bit_identical(shape):
         call('vx_fd_gradient', s_, X, Y, Z, vs, G)
         call('vx_fd_gradient_backward', d_, X, Y, Z, vs, ga)
         call('vx_total_variation_add_grad', s_, ga, None, w, w, w, 1, X, Y, Z, V)
-        call('vx_sdf_regularisers_backward', d_, s_, X, Y, Z, vs, w, w, w, gb)
+        call('vx_sdf_regularisers_backward', d_, s_, X, Y, Z, vs, w, w, w, gb, None)
         res[name] = (G.clone(), ga.clone(), gb.clone())
     assert torch.equal(res['vec'][1], res['vec'][2]) and torch.equal(res['scalar'][1], res['scalar'][2])
     for a, b in zip(res['vec'], res['scalar']):

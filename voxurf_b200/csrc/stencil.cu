@@ -60,10 +60,13 @@ static bool vec4_ok(int X, int Y, int Z, int64_t planes, const void* a, const vo
          ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
 }
 
+// `active` (optional, one byte per voxel): groups of 4 voxels with no active voxel are skipped -- their entries of grad
+// are left as they are.  The smooth-gradient TV only reads the gradient within one voxel of the non-empty mask.
 __global__ void __launch_bounds__(256) k_fd_gradient_v4(const float* __restrict__ sdf, uint32_t X, uint32_t Y, uint32_t Z,
-                                                        float vs, float* __restrict__ grad) {
+                                                        float vs, float* __restrict__ grad, const bool* __restrict__ active) {
   const uint32_t Z4 = Z >> 2, n4 = X * Y * Z4, V = X * Y * Z, sX = Y * Z;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
+    if (active && __ldg(reinterpret_cast<const uint32_t*>(active) + t) == 0u) continue;
     const uint32_t k4 = t % Z4, ij = t / Z4, j = ij % Y, i = ij / Y, v = t << 2;
     const float4 c = ld4(sdf + v);
     float4 gx = make_float4(0.f, 0.f, 0.f, 0.f), gy = gx, gz;
@@ -81,16 +84,21 @@ __global__ void __launch_bounds__(256) k_fd_gradient_v4(const float* __restrict_
 
 // grad += FD^T(dgrad) (vx_fd_gradient_backward), then, when kTv, grad += the dense unmasked total_variation_add_grad
 // of `param` (total_variation_kernel.cu:14-35) -- one read-modify-write of grad for both regularisers.
+// `active` (optional): where no voxel of the group of 4 is active, dgrad is known to be zero at all six neighbours and the
+// FD part is skipped.
 template <bool kFd, bool kTv>
 __global__ void __launch_bounds__(256) k_sdf_reg_backward_v4(const float* __restrict__ dgrad, const float* __restrict__ param,
                                                              uint32_t X, uint32_t Y, uint32_t Z, float vs, float w_fast,
-                                                             float w_mid, float w_slow, float* __restrict__ grad) {
+                                                             float w_mid, float w_slow, float* __restrict__ grad,
+                                                             const bool* __restrict__ active) {
   const uint32_t Z4 = Z >> 2, n4 = X * Y * Z4, V = X * Y * Z, sX = Y * Z;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
     const uint32_t k4 = t % Z4, ij = t / Z4, j = ij % Y, i = ij / Y, v = t << 2, k = k4 << 2;
+    const bool fd_here = kFd && !(active && __ldg(reinterpret_cast<const uint32_t*>(active) + t) == 0u);
+    if (!kTv && !fd_here) continue;
     float4 g = *reinterpret_cast<const float4*>(grad + v);
     float* gp = reinterpret_cast<float*>(&g);
-    if (kFd) {
+    if (fd_here) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       // same order as k_fd_gradient_bwd: x-, x+, y-, y+, z-, z+ ; a source contributes iff it is interior on its axis
       if (i >= 2 && i - 1 < X - 1) { const float4 a = ld4(dgrad + v - sX); acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; }
@@ -141,11 +149,24 @@ VX_API int vx_fd_gradient(const float* sdf, int X, int Y, int Z, float voxel_siz
   const int64_t V = (int64_t)X * Y * Z;
   if (V <= 0) return 0;
   if (vec4_ok(X, Y, Z, 3, sdf, grad) && V % 4 == 0) {   // (the y/z component planes start at multiples of V floats)
-    k_fd_gradient_v4<<<grid_blocks(V / 4), 256, 0, st>>>(sdf, X, Y, Z, voxel_size, grad);
+    k_fd_gradient_v4<<<grid_blocks(V / 4), 256, 0, st>>>(sdf, X, Y, Z, voxel_size, grad, nullptr);
     return vx_check_launch("vx_fd_gradient");
   }
   k_fd_gradient<<<grid_blocks(V), 256, 0, st>>>(sdf, X, Y, Z, voxel_size, grad);
   return vx_check_launch("vx_fd_gradient");
+}
+
+// vx_fd_gradient restricted to the groups of 4 z-consecutive voxels that contain an active voxel; the rest of grad is
+// left untouched (callers keep it zero-initialised).  Falls back to the full pass when the vectorised form does not apply.
+VX_API int vx_fd_gradient_active(const float* sdf, int X, int Y, int Z, float voxel_size, const bool* active, float* grad,
+                                 cudaStream_t st) {
+  const int64_t V = (int64_t)X * Y * Z;
+  if (V <= 0) return 0;
+  if (active && vec4_ok(X, Y, Z, 3, sdf, grad) && V % 4 == 0 && (reinterpret_cast<uintptr_t>(active) & 3) == 0) {
+    k_fd_gradient_v4<<<grid_blocks(V / 4), 256, 0, st>>>(sdf, X, Y, Z, voxel_size, grad, active);
+    return vx_check_launch("vx_fd_gradient_active");
+  }
+  return vx_fd_gradient(sdf, X, Y, Z, voxel_size, grad, st);
 }
 
 VX_API int vx_fd_gradient_backward(const float* dgrad, int X, int Y, int Z, float voxel_size, float* dsdf,
@@ -153,7 +174,7 @@ VX_API int vx_fd_gradient_backward(const float* dgrad, int X, int Y, int Z, floa
   const int64_t V = (int64_t)X * Y * Z;
   if (V <= 0) return 0;
   if (vec4_ok(X, Y, Z, 3, dgrad, dsdf)) {
-    k_sdf_reg_backward_v4<true, false><<<grid_blocks(V / 4), 256, 0, st>>>(dgrad, nullptr, X, Y, Z, voxel_size, 0.f, 0.f, 0.f, dsdf);
+    k_sdf_reg_backward_v4<true, false><<<grid_blocks(V / 4), 256, 0, st>>>(dgrad, nullptr, X, Y, Z, voxel_size, 0.f, 0.f, 0.f, dsdf, nullptr);
     return vx_check_launch("vx_fd_gradient_backward");
   }
   k_fd_gradient_bwd<<<grid_blocks(V), 256, 0, st>>>(dgrad, X, Y, Z, voxel_size, dsdf);
@@ -310,7 +331,7 @@ __global__ void k_smooth_grad_tv(const float* __restrict__ G, const bool* __rest
 
 __global__ void __launch_bounds__(256) k_smooth_grad_tv_v4(const float* __restrict__ G, const bool* __restrict__ mask,
                                                           uint32_t X, uint32_t Y, uint32_t Z, VxKernel3 ker, float scale,
-                                                          float* __restrict__ dG, float* __restrict__ partial) {
+                                                          float* __restrict__ dG, float* __restrict__ partial, int skip_unmasked) {
   __shared__ float red[32];
   const uint32_t Z4 = Z >> 2, V = X * Y * Z, V4 = V >> 2;
   float local = 0.f;
@@ -319,7 +340,9 @@ __global__ void __launch_bounds__(256) k_smooth_grad_tv_v4(const float* __restri
     const uint32_t k4 = u4 % Z4, ij = u4 / Z4, y = ij % Y, x = ij / Y;
     const uchar4 mk = __ldg(reinterpret_cast<const uchar4*>(mask) + u4);
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mk.x | mk.y | mk.z | mk.w) {
+    if (!(mk.x | mk.y | mk.z | mk.w)) {
+      if (skip_unmasked) continue;     // the caller keeps dG zero there (static mask, zero-initialised buffer)
+    } else {
       const float* src = G + comp * V;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       float ctr[4];
@@ -382,15 +405,15 @@ __global__ void k_sum_partials(const float* __restrict__ partial, int n, float s
 // scratch: at least vx_smooth_grad_tv_scratch_floats() floats
 VX_API int vx_smooth_grad_tv_scratch_floats() { return vx_num_sms() * 16; }
 
-VX_API int vx_smooth_grad_tv(const float* G, const bool* mask, int X, int Y, int Z, const float* weight3_host,
-                             float w_over_3n, float* dG, float* scratch, float* loss_out, cudaStream_t st) {
+static int smooth_grad_tv_impl(const float* G, const bool* mask, int X, int Y, int Z, const float* weight3_host,
+                               float w_over_3n, float* dG, float* scratch, float* loss_out, int skip_unmasked, cudaStream_t st) {
   VxKernel3 ker;
   VX_REQUIRE(fill_kernel(ker, weight3_host, 3) == 0, "vx_smooth_grad_tv", "bad kernel");
   const int64_t n = (int64_t)X * Y * Z * 3;
   if (n <= 0) return 0;
   const bool v4 = vec4_ok(X, Y, Z, 3, G, dG) && (reinterpret_cast<uintptr_t>(mask) & 3) == 0 && (n / 3) % 4 == 0;
   const int blocks = grid_blocks(v4 ? n / 4 : n);
-  if (v4) k_smooth_grad_tv_v4<<<blocks, 256, 0, st>>>(G, mask, X, Y, Z, ker, w_over_3n, dG, scratch);
+  if (v4) k_smooth_grad_tv_v4<<<blocks, 256, 0, st>>>(G, mask, X, Y, Z, ker, w_over_3n, dG, scratch, skip_unmasked);
   else k_smooth_grad_tv<<<blocks, 256, 0, st>>>(G, mask, X, Y, Z, ker, w_over_3n, dG, scratch);
   int rc = vx_check_launch("vx_smooth_grad_tv");
   if (rc) return rc;
@@ -399,6 +422,18 @@ VX_API int vx_smooth_grad_tv(const float* G, const bool* mask, int X, int Y, int
     rc = vx_check_launch("vx_smooth_grad_tv(sum)");
   }
   return rc;
+}
+
+VX_API int vx_smooth_grad_tv(const float* G, const bool* mask, int X, int Y, int Z, const float* weight3_host,
+                             float w_over_3n, float* dG, float* scratch, float* loss_out, cudaStream_t st) {
+  return smooth_grad_tv_impl(G, mask, X, Y, Z, weight3_host, w_over_3n, dG, scratch, loss_out, 0, st);
+}
+
+// Same, but entries of dG outside the mask are not written (they are zero by definition): for a caller that keeps dG
+// zero-initialised and whose mask does not change.  Only the vectorised form (Z % 4 == 0) skips; otherwise identical.
+VX_API int vx_smooth_grad_tv_masked_writes(const float* G, const bool* mask, int X, int Y, int Z, const float* weight3_host,
+                                           float w_over_3n, float* dG, float* scratch, float* loss_out, cudaStream_t st) {
+  return smooth_grad_tv_impl(G, mask, X, Y, Z, weight3_host, w_over_3n, dG, scratch, loss_out, 1, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,7 +484,7 @@ VX_API int vx_total_variation_add_grad(const float* param, float* grad, const fl
   const float w_fast = mask ? wx : wz, w_mid = wy, w_slow = wz;
   if (!mask && dense_mode && N == sz_i * sz_j * sz_k && vec4_ok((int)sz_i, (int)sz_j, (int)sz_k, 1, param, grad)) {
     k_sdf_reg_backward_v4<false, true><<<grid_blocks(N / 4), 256, 0, st>>>(nullptr, param, (uint32_t)sz_i, (uint32_t)sz_j,
-                                                                         (uint32_t)sz_k, 1.f, w_fast, w_mid, w_slow, grad);
+                                                                         (uint32_t)sz_k, 1.f, w_fast, w_mid, w_slow, grad, nullptr);
     return vx_check_launch("vx_total_variation_add_grad");
   }
 #define VX_TV(D, M) k_total_variation_add_grad<D, M><<<blocks, threads, 0, st>>>(param, grad, mask, w_fast, w_mid, w_slow, (size_t)sz_i, (size_t)sz_j, (size_t)sz_k, (size_t)N)
@@ -463,12 +498,12 @@ VX_API int vx_total_variation_add_grad(const float* param, float* grad, const fl
 // read-modify-write of grad (the fine stage's two sdf regularisers, run.py:612-655).  Same result, bit for bit, as the
 // two separate calls.
 VX_API int vx_sdf_regularisers_backward(const float* dgrad, const float* param, int X, int Y, int Z, float voxel_size,
-                                        float wx, float wy, float wz, float* grad, cudaStream_t st) {
+                                        float wx, float wy, float wz, float* grad, const bool* active, cudaStream_t st) {
   const int64_t V = (int64_t)X * Y * Z;
   if (V <= 0) return 0;
-  if (vec4_ok(X, Y, Z, 3, dgrad, grad, param)) {
+  if (vec4_ok(X, Y, Z, 3, dgrad, grad, param) && (reinterpret_cast<uintptr_t>(active) & 3) == 0) {
     (void)wx;  // the reference's unmasked kernel routes wz to the fastest and the slowest axis (total_variation_kernel.cu:27-32)
-    k_sdf_reg_backward_v4<true, true><<<grid_blocks(V / 4), 256, 0, st>>>(dgrad, param, X, Y, Z, voxel_size, wz / 6, wy / 6, wz / 6, grad);
+    k_sdf_reg_backward_v4<true, true><<<grid_blocks(V / 4), 256, 0, st>>>(dgrad, param, X, Y, Z, voxel_size, wz / 6, wy / 6, wz / 6, grad, active);
     return vx_check_launch("vx_sdf_regularisers_backward");
   }
   int rc = vx_fd_gradient_backward(dgrad, X, Y, Z, voxel_size, grad, st);

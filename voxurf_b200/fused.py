@@ -27,6 +27,7 @@ import math
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from ._lib import call
 from .mlp import FlatMLP, prepare_chains, run_dw_batch
@@ -324,20 +325,27 @@ class FusedFineStep:
         tv = c['tv_terms']
         if tv['smooth_grad_tv'] > 0:
             if self.G is None:
-                self.G = torch.empty(1, 3, X, Y, Z, dtype=torch.float32, device=self.dev)
-                self.dG = torch.empty_like(self.G)
+                # Only the part of the gradient grid within one voxel of the non-empty mask is ever read by the
+                # regulariser (3^3 smoothing of masked voxels), and dL/dG is zero outside the mask: G and dG are
+                # zero-initialised once, the FD gradient is evaluated inside the dilated mask only, dG is written inside
+                # the mask only, and the FD adjoint is skipped outside the dilated mask.  Same numbers, ~85 % less
+                # traffic for a typical mask.  (m.gradient is therefore only valid near the mask in this path.)
+                self.G = torch.zeros(1, 3, X, Y, Z, dtype=torch.float32, device=self.dev)
+                self.dG = torch.zeros_like(self.G)
+                self.tv_active = (F.max_pool3d(m.nonempty_mask.float(), 3, 1, 1) > 0)[0, 0].contiguous()
                 self.tv_loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
                 self.tv_scratch = torch.empty(int(call('vx_smooth_grad_tv_scratch_floats')), dtype=torch.float32, device=self.dev)
-            call('vx_fd_gradient', m.sdf.grid, X, Y, Z, m._voxel_size_host, self.G)
+            call('vx_fd_gradient_active', m.sdf.grid, X, Y, Z, m._voxel_size_host, self.tv_active, self.G)
             m.gradient = self.G
             w = c['weight_tv_density'] * tv['smooth_grad_tv'] / (3.0 * m._n_nonempty)
-            call('vx_smooth_grad_tv', self.G, m.nonempty_mask[0, 0], X, Y, Z, m._tv_smooth_w, w, self.dG, self.tv_scratch, self.tv_loss)
+            call('vx_smooth_grad_tv_masked_writes', self.G, m.nonempty_mask[0, 0], X, Y, Z, m._tv_smooth_w, w, self.dG, self.tv_scratch, self.tv_loss)
             self.loss.add_(self.tv_loss)   # run.py:622-625 adds the regulariser to the reported loss
         n_batch = global_batch or self.N * self.world
         wt = c['weight_tv_density'] * tv['sdf_tv'] / n_batch * max(X, Y, Z) / 128
         if tv['smooth_grad_tv'] > 0 and tv['sdf_tv'] > 0 and dense:
             # both regularisers land in the sdf gradient with one read-modify-write
-            call('vx_sdf_regularisers_backward', self.dG, m.sdf.grid, X, Y, Z, m._voxel_size_host, wt, wt, wt, self.sdf_grad)
+            call('vx_sdf_regularisers_backward', self.dG, m.sdf.grid, X, Y, Z, m._voxel_size_host, wt, wt, wt, self.sdf_grad,
+                 self.tv_active)
             return
         if tv['smooth_grad_tv'] > 0:
             call('vx_fd_gradient_backward', self.dG, X, Y, Z, m._voxel_size_host, self.sdf_grad)
