@@ -423,7 +423,9 @@ def main():
                                               'algorithmic_bytes_per_launch': 32 * V, 'share_of_step': t_sdf / step_ms}
         B = algorithmic_bytes(V, C, 1 / 3, M2, M3, M4, args.rays, 1 / 3)
         step_roof = {'algorithmic_bytes_per_step': B, 'achieved_gbs': B / (ms / args.steps * 1e-3) / 1e9,
-                     'frac_of_hbm': B / (ms / args.steps * 1e-3) / 1e9 / peak, 'M0': M0, 'M2': M2, 'M3': M3, 'M4': M4}
+                     'frac_of_hbm': B / (ms / args.steps * 1e-3) / 1e9 / peak, 'M0': M0, 'M2': M2, 'M3': M3, 'M4': M4,
+                     'note': 'B = algorithmic bytes of the DENSE formulation (SURVEY 8d); the fused step moves fewer (sparse-aware k0 Adam, '
+                             'mask-aware TV), so this is a dense-equivalent rate, not measured traffic'}
         h2d = sum(t.numel() * t.element_size() for t in pool[0])
         line = {'metric': 'rays/sec fwd+bwd+Adam (fine 256^3, 8192-ray batch)', 'value': value, 'unit': 'rays/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
