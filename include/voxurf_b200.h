@@ -316,9 +316,9 @@ int vx_compact_rows3(const bool* mask, const int* incl, int n, const int64_t* to
 int vx_umma_probe(const float* A_img, int a_floats, const float* B_img, int b_floats, int64_t desc_a_fields,
                   int64_t desc_b_fields, int64_t idesc, int N, float* D, cudaStream_t stream);
 
-/* development probe: cycles for n_mma back-to-back M = 128, K = 8 TF32 MMAs of width N (form 0: A from shared memory,
+/* development probe: cycles for n_mma back-to-back M = 64 / 128, K = 8 TF32 MMAs of width N (form 0: A from shared memory,
  * 1: A from TMEM; n_acc: 1 accumulator tile or 2 alternating), one value per block */
-int vx_umma_rate(int n_blocks, int n_mma, int N, int form, int n_acc, int64_t* cycles, cudaStream_t stream);
+int vx_umma_rate(int n_blocks, int n_mma, int M, int N, int form, int n_acc, int64_t* cycles, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -840,7 +840,7 @@ VX_API int vx_umma_probe(const float* A_img, int a_floats, const float* B_img, i
 // shared memory (form 0) or from TMEM (form 1), accumulating into one D tile (n_acc = 1) or alternating between two;
 // cycles[block] = clock64 ticks from the first issue to the completion of the last MMA.
 __global__ void __launch_bounds__(128, 1)
-k_umma_rate(int n_mma, int N, int form, int n_acc, long long* __restrict__ cycles) {
+k_umma_rate(int n_mma, int M, int N, int form, int n_acc, long long* __restrict__ cycles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* sA = reinterpret_cast<float*>(smem_raw);
   float* sB = reinterpret_cast<float*>(smem_raw + 16384);
@@ -857,7 +857,7 @@ k_umma_rate(int n_mma, int N, int form, int n_acc, long long* __restrict__ cycle
   tc_fence_after();
   const uint32_t tmem = tmem_base;
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_tf32(128, N);
+    const uint32_t idesc = make_idesc_tf32(M, N);
     const uint64_t da = make_desc(smem_u32(sA), 128 * 16, 128);
     const uint64_t db = make_desc(smem_u32(sB), N * 16, 128);
     const long long t0 = clock64();
@@ -875,13 +875,13 @@ k_umma_rate(int n_mma, int N, int form, int n_acc, long long* __restrict__ cycle
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-VX_API int vx_umma_rate(int n_blocks, int n_mma, int N, int form, int n_acc, int64_t* cycles, cudaStream_t st) {
-  VX_REQUIRE(N % 16 == 0 && N >= 16 && N <= 240 && n_blocks >= 1, "vx_umma_rate", "sizes");
+VX_API int vx_umma_rate(int n_blocks, int n_mma, int M, int N, int form, int n_acc, int64_t* cycles, cudaStream_t st) {
+  VX_REQUIRE((M == 64 || M == 128) && N % 16 == 0 && N >= 16 && N <= 240 && n_blocks >= 1, "vx_umma_rate", "sizes");
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     attr_set = true;
   }
-  k_umma_rate<<<n_blocks, 128, 65536, st>>>(n_mma, N, form, n_acc, reinterpret_cast<long long*>(cycles));
+  k_umma_rate<<<n_blocks, 128, 65536, st>>>(n_mma, M, N, form, n_acc, reinterpret_cast<long long*>(cycles));
   return vx_check_launch("vx_umma_rate");
 }
