@@ -135,6 +135,45 @@ __global__ void k_grid_gather_bwd(VxGrid g, VxPts pts, const int* __restrict__ n
   else if ((cl) && (C) == 4) { CALL(4); }           \
   else { CALL(0); }
 
+// channels-last scatter with four threads per point (corners 2 sub, 2 sub + 1 each): the 24 vector atomics of a 12-channel
+// point are spread over four lanes instead of serialised in one (the multi-GPU step re-scatters world x rows with this)
+template <int kC>
+__global__ void k_grid_gather_bwd_cl4(VxGrid g, VxPts pts, const int* __restrict__ n_dev, int64_t n_host,
+                                      const float* __restrict__ grad_out, float* __restrict__ grad_grid,
+                                      uint32_t* __restrict__ touched) {
+  const int64_t n = vx_count(n_dev, n_host);
+  for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n * 4; item += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = item >> 2;
+    const int sub = (int)(item & 3);
+    float go[kC];
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) { go[c] = grad_out[p * kC + c]; any |= (go[c] != 0.f); }
+    if (!any) continue;
+    float px, py, pz, ix, iy, iz;
+    vx_load_pt(pts, p, px, py, pz);
+    point_to_index(g, px, py, pz, ix, iy, iz);
+    VxTap t;
+    vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if ((k >> 1) != sub || t.off[k] < 0) continue;
+      if (touched) atomicOr(touched + (t.off[k] >> 5), 1u << (t.off[k] & 31));
+      float* dst = grad_grid + (int64_t)t.off[k] * kC;
+      if (kC % 4 == 0) {
+#pragma unroll
+        for (int c = 0; c < kC; c += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + c),
+                    make_float4(go[c] * t.w[k], go[c + 1] * t.w[k], go[c + 2] * t.w[k], go[c + 3] * t.w[k]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < kC; c += 2)
+          atomicAdd(reinterpret_cast<float2*>(dst + c), make_float2(go[c] * t.w[k], go[c + 1] * t.w[k]));
+      }
+    }
+  }
+}
+
 // xyz_min / xyz_max are HOST float[3] (grid geometry is static model configuration).
 VX_API int vx_grid_gather(const float* grid, int X, int Y, int Z, int C, int channels_last, const float* xyz_min_host,
                           const float* xyz_max_host, const float* xyz, const int* ray_id, const int* step_id,
@@ -160,6 +199,12 @@ VX_API int vx_grid_gather_backward(int X, int Y, int Z, int C, int channels_last
   if (!n_dev && n_host <= 0) return 0;
   const VxGrid g = make_grid(X, Y, Z, C, channels_last, xyz_min_host, xyz_max_host);
   const VxPts pts{xyz, ray_id, step_id, rays_start, rays_dir, stepdist};
+  if (channels_last && (C == 12 || C == 6)) {
+    const int blocks4 = n_dev ? vx_num_sms() * 8 : (int)min((int64_t)vx_blocks(n_host * 4, 256), (int64_t)vx_num_sms() * 16);
+    if (C == 12) k_grid_gather_bwd_cl4<12><<<blocks4, 256, 0, st>>>(g, pts, n_dev, n_host, grad_out, grad_grid, touched);
+    else k_grid_gather_bwd_cl4<6><<<blocks4, 256, 0, st>>>(g, pts, n_dev, n_host, grad_out, grad_grid, touched);
+    return vx_check_launch("vx_grid_gather_backward");
+  }
   const int blocks = launch_blocks(n_dev, n_host);
 #define CALL(KC) k_grid_gather_bwd<KC><<<blocks, 256, 0, st>>>(g, pts, n_dev, n_host, grad_out, grad_grid, touched)
   VX_DISPATCH_C(C, channels_last, CALL)

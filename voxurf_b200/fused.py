@@ -232,21 +232,23 @@ class FusedFineStep:
              self.alphainv_last, target.contiguous(), N, w_main, w_rgb0, w_ent, ent_scale, float(self.rk.get('bg', 0.0)), 1,
              self.rgb_marched, self.rgb_marched0, self.d_logit1, self.d_kout, self.d_w, self.d_last, self.loss_ray)
         call('vx_sum_f32', self.loss_ray, N, self.loss)
+        sparse_dp = self.world > 1 and self.sparse_k0_exchange
         if self.tensor_core:   # both dX chains, then the 8 weight-gradient GEMMs of both networks in one launch
             self.mlp2.backward(self.d_kout, self.dX2, defer_dw=True)
+            if sparse_dp:      # dL/dk0 of this rank's rows is final here: its all-gather runs under the rest of the backward
+                self._start_k0_exchange(n4)
             self.mlp1.backward(self.d_logit1, self.dX1, defer_dw=True)
             run_dw_batch([self.mlp2, self.mlp1])
         else:
             self.mlp2.backward(self.d_kout, self.dX2)
+            if sparse_dp:
+                self._start_k0_exchange(n4)
             self.mlp1.backward(self.d_logit1, self.dX1)
         grad_target = self.d_smoothed if m.smooth_sdf else self.sdf_grad
-        sparse_dp = self.world > 1 and self.sparse_k0_exchange
         call('vx_fused_row_backward', self._sdf_grid, X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(), self.idx4, n4,
              self.cap4, m._voxel_size_host, int(m.use_grad_norm), self.P, self.Vp, self.P2, self.V2, self.disp, self.L,
              self.ld1, self.ld2, self.dX1, self.dX2, self.d_sdf_s, self.d_grad_s, grad_target,
              None if sparse_dp else _storage(self.k0_grad), None if sparse_dp else self.k0_touched)
-        if sparse_dp:
-            self._start_k0_exchange(n4)
         thres = float(m.fast_color_thres)
         call('vx_alpha2weight_seg_backward', self.alpha, self.weight, self.T, self.keep if thres > 0 else None,
              self.alphainv_last, self.keep_off, self.i_end, N, self.d_w, self.d_last, self.d_alpha)
