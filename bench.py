@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--cpu-rays', type=int, default=256, help='ray sample of the CPU baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--path', default='fused', choices=['fused', 'dropin'], help='fused = sync-free FusedFineStep; dropin = Voxurf.forward + autograd')
+    ap.add_argument('--graph-multi', action='store_true', help='N > 1: capture the step including its NCCL collectives (experimental)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel of the step separately (no CUDA-graph replay)')
     ap.add_argument('--dense-adam', action='store_true', help='k0 Adam over every voxel (no touched/live bitmaps)')
     ap.add_argument('--dense-k0-allreduce', action='store_true', help='multi-GPU: all-reduce the dense k0 gradient grid instead of exchanging rows')
@@ -269,7 +270,7 @@ def main():
     if args.path == 'fused':
         from voxurf_b200.fused import FusedFineStep
         fused = FusedFineStep(model, args.rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank, sparse_adam=not args.dense_adam,
-                              use_graph=(world == 1 and not args.no_graph))
+                              use_graph=((world == 1 or args.graph_multi) and not args.no_graph), graph_multi_gpu=args.graph_multi)
         fused.calibrate(*dev_pool[0][:3], global_step=START_STEP, headroom=1.35)
         sync = None   # FusedFineStep.grad_sync(): dense all-reduce for sdf + MLPs, row exchange for k0 (or --dense-k0-allreduce)
         fused.sparse_k0_exchange = not args.dense_k0_allreduce
@@ -439,6 +440,9 @@ def main():
             line['cpu_baseline'] = cpu_reference_arm(args, 1, 1, args.cpu_rays)
         print(json.dumps(line))
     if world > 1:
+        if fused is not None and fused._graphs:     # release captured NCCL work before tearing the group down
+            fused._graphs.clear()
+            torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

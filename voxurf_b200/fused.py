@@ -36,7 +36,8 @@ from .optim import _storage
 
 class FusedFineStep:
     def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0,
-                 tensor_core=True, sparse_k0_exchange=True, sparse_adam=True, use_graph=False):
+                 tensor_core=True, sparse_k0_exchange=True, sparse_adam=True, use_graph=False,
+                 graph_multi_gpu=False):
         if model.k0_dim not in (6, 12):
             raise NotImplementedError('fused step: k0 channels must be 6 or 12')
         if model.k_center_sdf or not model.center_sdf or not model.k_res:
@@ -119,7 +120,8 @@ class FusedFineStep:
         self.adam_steps = 0
         # CUDA-graph replay of the whole step (single GPU): static input buffers, the step-dependent scalars (1/s of the
         # NeuS schedule, Adam step sizes / bias corrections) in a small device array the kernels read (inv_s_dev, step_dev)
-        self.use_graph = bool(use_graph) and world == 1
+        # (world > 1: the NCCL collectives of the step are captured with it -- opt-in, graph_multi_gpu=True)
+        self.use_graph = bool(use_graph) and (world == 1 or bool(graph_multi_gpu))
         self._graphs, self._eager_seen, self._dev_consts = {}, set(), None
         self._graph_launches, self.launches_replayed = {}, 0   # kernels per captured variant / total replayed (bench.py)
         if self.use_graph:
@@ -401,6 +403,15 @@ class FusedFineStep:
 
     def _step_body(self, rays_o, rays_d, viewdirs, target, global_step, flags):
         loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
+        if self.world > 1:
+            # overlap: the sdf / MLP all-reduces run on the NCCL stream while k0 is re-scattered and updated
+            self._sync_begin()
+            self._sync_k0()
+            self.optimizer_step(only=('k0',))
+            self._sync_end()
+            self.regularise(global_step, flags=flags)
+            self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet'), advance=False)
+            return loss
         self.regularise(global_step, flags=flags)
         self.optimizer_step()
         return loss
@@ -452,16 +463,9 @@ class FusedFineStep:
         """One training iteration (run.py:600-659).  grad_sync: optional callable run between backward and TV/Adam."""
         if self.use_graph and grad_sync is None and self.timings is None and self.bitmap_probe is None:
             return self._step_graph(rays_o, rays_d, viewdirs, target, global_step)
-        loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
         if grad_sync is None and self.world > 1:
-            # overlap: the sdf / MLP all-reduces run on the NCCL stream while k0 is re-scattered and updated
-            self._sync_begin()
-            self._sync_k0()
-            self.optimizer_step(only=('k0',))
-            self._sync_end()
-            self.regularise(global_step)
-            self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet'), advance=False)
-            return loss
+            return self._step_body(rays_o, rays_d, viewdirs, target, global_step, self.tv_flags(global_step))
+        loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
         if grad_sync is not None:
             grad_sync()
         self.regularise(global_step)
