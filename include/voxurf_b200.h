@@ -166,6 +166,11 @@ int vx_conv3d_replicate(const float* in, int B, int X, int Y, int Z, const float
                         float* out, cudaStream_t stream);
 int vx_conv3d_replicate_backward(const float* dout, int B, int X, int Y, int Z, const float* weight_host,
                                  int ksize, int accumulate, float* din, cudaStream_t stream);
+/* the same convolution (adjoint = 0) or its adjoint (adjoint = 1) for a SEPARABLE kernel w1 (x) w1 (x) w1 -- the reference's
+ * normalised Gaussian is one (lib/voxurf_fine.py:246-254) -- as three 1-D passes (15 taps instead of 125 for k = 5);
+ * w1_host: the k 1-D weights; scratch: 2 * B*X*Y*Z floats; out (+)= result.  Rounding-level agreement with the k^3 form. */
+int vx_conv3d_replicate_separable(const float* in, int B, int X, int Y, int Z, const float* w1_host, int ksize, int adjoint,
+                                  int accumulate, float* scratch, float* out, cudaStream_t stream);
 /* density_total_variation(smooth_grad_tv)  lib/voxurf_fine.py:417-420: from the FD gradient G (3,X,Y,Z) and the
  * bool nonempty mask: dG = dLoss/dG, loss_out[0] = loss.  w_over_3n = smooth_grad_tv_weight / (3 * mask.sum()) */
 int vx_smooth_grad_tv_scratch_floats(void);

@@ -35,9 +35,13 @@ class SmoothConv:
     def __init__(self, ksize, sigma):
         self.ksize, self.sigma = ksize, sigma
         self.weight_host = _gaussian_weights(ksize, sigma)
+        # the normalised Gaussian factorises: k^3 weights = w1 (x) w1 (x) w1 -> three 1-D passes instead of k^3 taps
+        r = np.arange(-(ksize // 2), ksize // 2 + 1, 1)
+        g = np.exp(-(r.astype(np.float64) ** 2) / (2 * sigma ** 2))
+        self.weight1d_host = [float(np.float32(v)) for v in g / g.sum()]
 
     def __call__(self, x):
-        return ops.conv3d_replicate(x, self.weight_host, self.ksize)
+        return ops.conv3d_replicate(x, self.weight_host, self.ksize, weight1d=self.weight1d_host)
 
 
 def _mlp(dim0, width, depth):

@@ -282,6 +282,75 @@ VX_API int vx_conv3d_replicate_backward(const float* dout, int B, int X, int Y, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Separable form of the same convolution.  The reference's smoothing kernel is a normalised Gaussian
+// exp(-(x^2+y^2+z^2) / 2 sigma^2) / sum (lib/voxurf_fine.py:246-254) = g (x) g (x) g with g the normalised 1-D
+// Gaussian, and replicate padding commutes with the factorisation, so three 1-D passes of k taps (15 taps for k = 5)
+// replace k^3 = 125; the adjoint is the three 1-D adjoints.  Z pass in -> out, Y pass out -> scratch, X pass
+// scratch -> out.  Agreement with the k^3 form is at rounding level (different summation order).
+// ---------------------------------------------------------------------------------------------
+struct VxKernel1 {
+  int k;
+  float w[5];
+};
+
+template <bool kAdjoint>
+__global__ void __launch_bounds__(256) k_conv1d_replicate(const float* __restrict__ in, float* __restrict__ out, uint32_t n_total,
+                                                          uint32_t n_axis, uint32_t stride, VxKernel1 ker, int accumulate) {
+  const int p = ker.k / 2, n = (int)n_axis;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_total; v += gridDim.x * blockDim.x) {
+    const int a = (int)((v / stride) % n_axis);
+    const float* line = in + v - (uint32_t)a * stride;        // element 0 of this voxel's line along the axis
+    float acc = 0.f;
+    if (!kAdjoint) {
+      for (int o = 0; o < ker.k; ++o) acc += __ldg(line + (uint32_t)min(max(a + o - p, 0), n - 1) * stride) * ker.w[o];
+    } else {
+      // din[a] = sum_d w[d + p] * sum_{v : clamp(v + d) == a} dout[v]
+      for (int o = 0; o < ker.k; ++o) {
+        const int d = o - p;
+        int lo, hi;
+        if (n == 1) { lo = 0; hi = 0; }
+        else if (a > 0 && a < n - 1) { lo = hi = a - d; if (lo < 0 || lo > n - 1) { lo = 1; hi = 0; } }
+        else if (a == 0) { lo = 0; hi = min(-d, n - 1); }
+        else { lo = max(n - 1 - d, 0); hi = n - 1; }
+        float sm = 0.f;
+        for (int u = lo; u <= hi; ++u) sm += __ldg(line + (uint32_t)u * stride);
+        acc += sm * ker.w[o];
+      }
+    }
+    out[v] = accumulate ? out[v] + acc : acc;
+  }
+}
+
+// w1_host: the k 1-D weights.  adjoint = 0: out (+)= conv(in); adjoint = 1: out (+)= conv^T(in).
+// scratch: 2 * B*X*Y*Z floats (the two intermediate volumes); `in` is not modified, `out` may alias nothing else.
+VX_API int vx_conv3d_replicate_separable(const float* in, int B, int X, int Y, int Z, const float* w1_host, int ksize, int adjoint,
+                                         int accumulate, float* scratch, float* out, cudaStream_t st) {
+  VX_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, "vx_conv3d_replicate_separable", "ksize must be 1, 3 or 5");
+  const int64_t n64 = (int64_t)B * X * Y * Z;
+  if (n64 <= 0) return 0;
+  VX_REQUIRE(n64 < ((int64_t)1 << 31), "vx_conv3d_replicate_separable", "more than 2^31 elements");
+  VX_REQUIRE(scratch && scratch != in && scratch != out && in != out, "vx_conv3d_replicate_separable", "distinct in / scratch / out");
+  VxKernel1 ker;
+  ker.k = ksize;
+  for (int i = 0; i < 5; ++i) ker.w[i] = i < ksize ? w1_host[i] : 0.f;
+  const uint32_t n = (uint32_t)n64;
+  float* s0 = scratch;
+  float* s1 = scratch + n64;
+  const int blocks = grid_blocks(n64);
+  const uint32_t sZ = 1u, sY = (uint32_t)Z, sX = (uint32_t)Y * (uint32_t)Z;
+  if (!adjoint) {
+    k_conv1d_replicate<false><<<blocks, 256, 0, st>>>(in, s0, n, (uint32_t)Z, sZ, ker, 0);
+    k_conv1d_replicate<false><<<blocks, 256, 0, st>>>(s0, s1, n, (uint32_t)Y, sY, ker, 0);
+    k_conv1d_replicate<false><<<blocks, 256, 0, st>>>(s1, out, n, (uint32_t)X, sX, ker, accumulate);
+  } else {
+    k_conv1d_replicate<true><<<blocks, 256, 0, st>>>(in, s0, n, (uint32_t)X, sX, ker, 0);
+    k_conv1d_replicate<true><<<blocks, 256, 0, st>>>(s0, s1, n, (uint32_t)Y, sY, ker, 0);
+    k_conv1d_replicate<true><<<blocks, 256, 0, st>>>(s1, out, n, (uint32_t)Z, sZ, ker, accumulate);
+  }
+  return vx_check_launch("vx_conv3d_replicate_separable");
+}
+
+// ---------------------------------------------------------------------------------------------
 // smooth-gradient TV (lib/voxurf_fine.py:417-420):
 //   E_a = tv_smooth_conv(G_a).detach() - G_a ;  loss = w * mean(E[mask x 3]^2)
 // pass 1 (this kernel): E from the materialised FD gradient G (3,X,Y,Z); writes dL/dG (3,X,Y,Z)

@@ -112,6 +112,7 @@ class FusedFineStep:
             n_words = (self.X * self.Y * self.Z + 31) // 32
             self.k0_touched = torch.zeros(n_words, dtype=torch.int32, device=dev)
             self.k0_live = torch.zeros(n_words, dtype=torch.int32, device=dev)
+        self.conv_scratch = None
         self.G = None       # FD gradient grid + its gradient, allocated on the first TV iteration
         self.smoothed = self.d_smoothed = None
         if m.smooth_sdf:
@@ -176,7 +177,10 @@ class FusedFineStep:
         call('vx_march_emit', self.offsets, N, self.bits_keep, self.keep_off, self.cap2, self.ray_id, self.step_id, None)
         n2 = self.keep_off[N:]
         if m.smooth_sdf:
-            call('vx_conv3d_replicate', m.sdf.grid, 1, X, Y, Z, m.smooth_conv.weight_host, m.smooth_conv.ksize, self.smoothed)
+            if self.conv_scratch is None:
+                self.conv_scratch = torch.empty(2 * m.sdf.grid.numel(), dtype=torch.float32, device=self.dev)
+            call('vx_conv3d_replicate_separable', m.sdf.grid, 1, X, Y, Z, m.smooth_conv.weight1d_host, m.smooth_conv.ksize, 0, 0,
+                 self.conv_scratch, self.smoothed)
             sdf_grid = self.smoothed
         else:
             sdf_grid = m.sdf.grid
@@ -258,8 +262,8 @@ class FusedFineStep:
              self.keep, self.d_alpha, self.d_sdf_s, self.d_grad_s, m._voxel_size_host, self.dist, self.inv_s, grad_target,
              self._inv_s_dev)
         if m.smooth_sdf:
-            call('vx_conv3d_replicate_backward', self.d_smoothed, 1, X, Y, Z, m.smooth_conv.weight_host, m.smooth_conv.ksize, 1,
-                 self.sdf_grad)
+            call('vx_conv3d_replicate_separable', self.d_smoothed, 1, X, Y, Z, m.smooth_conv.weight1d_host, m.smooth_conv.ksize, 1, 1,
+                 self.conv_scratch, self.sdf_grad)
             self.d_smoothed.zero_()
         return self.loss
 

@@ -180,25 +180,34 @@ class _Conv3dReplicate(torch.autograd.Function):
     """Conv3d(1,1,k,padding=k//2,padding_mode='replicate'), frozen weights: lib/voxurf_fine.py:246-258."""
 
     @staticmethod
-    def forward(ctx, x, weight, ksize):
+    def forward(ctx, x, weight, ksize, weight1d):
         B, X, Y, Z = x.shape[0] * x.shape[1], x.shape[2], x.shape[3], x.shape[4]
         out = torch.empty_like(x)
-        call('vx_conv3d_replicate', x, B, X, Y, Z, weight, ksize, out)
-        ctx.cfg = (B, X, Y, Z, weight, ksize)
+        if weight1d is not None:     # separable kernel: three 1-D passes
+            scratch = torch.empty(2 * x.numel(), dtype=torch.float32, device=x.device)
+            call('vx_conv3d_replicate_separable', x, B, X, Y, Z, weight1d, ksize, 0, 0, scratch, out)
+        else:
+            call('vx_conv3d_replicate', x, B, X, Y, Z, weight, ksize, out)
+        ctx.cfg = (B, X, Y, Z, weight, ksize, weight1d)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        B, X, Y, Z, weight, ksize = ctx.cfg
+        B, X, Y, Z, weight, ksize, weight1d = ctx.cfg
         din = torch.empty_like(g)
-        call('vx_conv3d_replicate_backward', g.contiguous(), B, X, Y, Z, weight, ksize, 0, din)
-        return din, None, None
+        if weight1d is not None:
+            scratch = torch.empty(2 * g.numel(), dtype=torch.float32, device=g.device)
+            call('vx_conv3d_replicate_separable', g.contiguous(), B, X, Y, Z, weight1d, ksize, 1, 0, scratch, din)
+        else:
+            call('vx_conv3d_replicate_backward', g.contiguous(), B, X, Y, Z, weight, ksize, 0, din)
+        return din, None, None, None
 
 
-def conv3d_replicate(x, weight_host, ksize):
-    """x (B,1,X,Y,Z) or (1,B,X,Y,Z): every leading slice is convolved independently; weight_host: flat list k^3."""
-    return _Conv3dReplicate.apply(x.contiguous(), weight_host, int(ksize))
+def conv3d_replicate(x, weight_host, ksize, weight1d=None):
+    """x (B,1,X,Y,Z) or (1,B,X,Y,Z): every leading slice is convolved independently; weight_host: flat list k^3;
+    weight1d: the k 1-D weights when the kernel is separable (w1 (x) w1 (x) w1)."""
+    return _Conv3dReplicate.apply(x.contiguous(), weight_host, int(ksize), weight1d)
 
 
 class _SmoothGradTV(torch.autograd.Function):
