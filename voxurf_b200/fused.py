@@ -2,8 +2,8 @@
 per-voxel Adam (lib/voxurf_fine.py:620-802, run.py:600-659) on persistent device buffers.
 
 What this replaces, per training iteration of the reference: ~150 kernel launches, >= 13 host syncs, ~10
-boolean-mask compactions and a dense autograd graph.  Here the iteration is ~45 launches, ZERO host syncs and no
-per-step allocation: every data-dependent count (M2 = samples after bbox + mask cache, M4 = MLP rows) stays in
+boolean-mask compactions and a dense autograd graph.  Here the iteration is 29 kernels (34 on TV iterations), replayed
+as ONE CUDA graph on a single GPU (use_graph=True), ZERO host syncs and no per-step allocation: every data-dependent count (M2 = samples after bbox + mask cache, M4 = MLP rows) stays in
 device memory and is read by the consuming kernels; threshold compactions are a keep-flag and one index list.
 Results are the same numbers as `voxurf_fine.Voxurf.forward` + autograd (tests/test_gpu_fused.py).
 
@@ -14,14 +14,16 @@ Sequence (kernel -> reference lines):
   vx_alpha2weight_seg     T / weights (bit-exact recurrence), w > thres   voxurf_fine.py:667-669
   vx_scan_i32, vx_fused_emit_rows   row list                              voxurf_fine.py:670-676
   vx_fused_row_features   k0 gather, sample_sdfs (L=4), PEs -> X1, X2     voxurf_fine.py:678-739
-  MLP rgbnet / k_rgbnet   (mlp.py)                                        voxurf_fine.py:718,749
+  vx_mlp_prep_batch       hi / lo TF32 weight images of both networks     (mlp.py, csrc/mlp_tc.cu)
+  vx_mlp_chain x2         rgbnet, k_rgbnet forward (tcgen05, TF32x3)      voxurf_fine.py:718,749
   vx_fused_composite_loss sigmoid, segment sums, losses, their backward   voxurf_fine.py:752-763, run.py:604-636
-  MLP backward            dX1, dX2, weight grads
+  vx_mlp_chain x2         dX chains of both networks
+  vx_mlp_dw_batch         all 8 weight / bias gradient GEMMs, one launch
   vx_fused_row_backward   k0 scatter, sample_sdfs scatter                 (ATen grid_sampler backward)
   vx_alpha2weight_seg_backward                                            render_utils_kernel.cu:653-677
   vx_fused_alpha_sdf_backward  NeuS alpha backward + 7-tap sdf scatter
-  [TV iters] vx_fd_gradient, vx_smooth_grad_tv, vx_fd_gradient_backward, vx_total_variation_add_grad
-  vx_adam_step x4         sdf, k0 (fused grad zero-fill), rgbnet, k_rgbnet lib/utils.py:154-199
+  [TV iters] vx_fd_gradient_active, vx_smooth_grad_tv_masked_writes, vx_sdf_regularisers_backward  run.py:612-655
+  vx_adam_step x4         sdf, k0 (sparse-aware, touched / live bitmaps), rgbnet, k_rgbnet    lib/utils.py:154-199
 """
 import math
 
