@@ -242,9 +242,12 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        cb = cpu_reference_arm(args, max(1, min(args.steps, 2)), min(args.warmup, 1), args.cpu_rays)
+        # every step is a bounded sample (256 rays + one full grid-proportional part, ~1.4 s of CPU work): K steps are
+        # honoured up to 30 so that the run stays within a few minutes
+        k_used, w_used = max(1, min(args.steps, 30)), max(0, min(args.warmup, 3))
+        cb = cpu_reference_arm(args, k_used, w_used, args.cpu_rays)
         line = {'impl': 'reference', 'metric': 'rays/sec fwd+bwd+Adam (fine 256^3, 8192-ray batch)', 'value': cb['value'], 'unit': 'rays/s',
-                'n_gpus': 0, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * N_RAYS / cb['value'],
+                'n_gpus': args.gpus, 'steps': k_used, 'warmup': w_used, 'ms_per_step': 1e3 * N_RAYS / cb['value'],
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
                 'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
