@@ -581,3 +581,20 @@ def training_rays_in_maskcache(images, poses, HW, Ks, mc, xyz_min, xyz_max, voxe
             dst.append(src[keep])
         counts.append(int(keep.sum()))
     return [torch.cat(x) for x in out] + [counts]
+
+
+# ------------------------------------------------------------------------------------------------
+# off-step callers: mesh field query and progressive grid growing
+# ------------------------------------------------------------------------------------------------
+def sdf_field(sdf, xyz_min, xyz_max, resolution, smooth=True, sigma=0.5):
+    """The field part of extract_geometry: voxurf_fine.py:894-910 (k = 3 Gaussian-smoothed grid, query of -sdf) on the
+    lattice of dvgo_ori.py:679-693 (torch.linspace per axis). -> u (res, res, res)"""
+    grid = conv3d_replicate(sdf, gaussian_kernel3d(3, sigma)) if smooth else sdf
+    axes = [torch.linspace(float(xyz_min[i]), float(xyz_max[i]), resolution) for i in range(3)]
+    pts = torch.stack(torch.meshgrid(*axes, indexing='ij'), -1).reshape(-1, 3)
+    return grid_trilinear(-grid, pts, xyz_min, xyz_max).reshape(resolution, resolution, resolution)
+
+
+def scale_volume(grid, new_world_size):
+    """grid.py:60-65: trilinear resampling of a (1,C,X,Y,Z) grid to the new resolution, align_corners=True"""
+    return F.interpolate(grid, size=tuple(int(w) for w in new_world_size), mode='trilinear', align_corners=True)

@@ -156,3 +156,46 @@ def test_coarse_model_matches_oracle_with_regularisers(G, n_rays, cl):
     grad_close(m.sdf.grid.grad, om['sdf'].grad, msg='grad_sdf'); grad_close(m.k0.grid.grad, om['k0'].grad, msg='grad_k0')
     for l, (W, b) in zip([x for x in m.rgbnet.modules() if isinstance(x, torch.nn.Linear)], om['rgbnet']):
         grad_close(l.weight.grad, W.grad); grad_close(l.bias.grad, b.grad)
+
+
+def test_query_sdf_field_matches_oracle_and_shards_by_slab():
+    """Mesh field query (SURVEY 8d config 5 shape at small size): the smoothed -sdf on a lattice, whole and as X-slabs."""
+    sc = S.make_fine_scene(24, 6, 32, seed=5, mask_G=12)
+    m = product_fine_model(sc)
+    om = oracle_fine_model(sc, requires_grad=False)
+    res = 37
+    ref = R.sdf_field(om['sdf'], om['xyz_min'], om['xyz_max'], res, smooth=True, sigma=0.5)
+    u = m.query_sdf_field(res, smooth=True, sigma=0.5, chunk=res * res * 5)
+    assert u.shape == (res, res, res)
+    close(u, ref, 1e-5, 2e-6)
+    slabs = [m.query_sdf_field(res, x_range=(a, min(a + 10, res))) for a in range(0, res, 10)]
+    assert torch.equal(torch.cat(slabs, 0), m.query_sdf_field(res))
+    close(m.query_sdf_field(res, smooth=False), R.sdf_field(om['sdf'], om['xyz_min'], om['xyz_max'], res, smooth=False), 1e-5, 2e-6)
+    u2, g2 = m.query_sdf_field(res, with_gradient=True)
+    assert torch.equal(u2, m.query_sdf_field(res)) and g2.shape == (res, res, res, 3)
+
+
+@pytest.mark.parametrize('cl', [False, True])
+def test_scale_volume_grid_matches_oracle(cl):
+    """Progressive growing (lib/voxurf_fine.py:384-397, lib/grid.py:60-65): resampled grids, new voxel size, new
+    non-empty mask and the sdf = 1 fill outside it."""
+    sc = S.make_fine_scene(20, 6, 32, seed=3, mask_G=12)
+    m = product_fine_model(sc, k0_channels_last=cl)
+    om = oracle_fine_model(sc, requires_grad=False)
+    new_voxels = 28 ** 3
+    m.scale_volume_grid(new_voxels)
+    ws = tuple(int(w) for w in m.world_size)
+    assert ws == (28, 28, 28) and m.sdf.grid.shape == (1, 1) + ws and m.k0.grid.shape == (1, 6) + ws
+    nonempty = R.nonempty_mask(om['mask_cache'], om['xyz_min'], om['xyz_max'], ws)
+    assert torch.equal(m.nonempty_mask.cpu(), nonempty)
+    sdf = R.scale_volume(om['sdf'], ws)
+    sdf[~nonempty] = 1
+    close(m.sdf.grid, sdf, 1e-5, 1e-6)
+    close(m.k0.grid, R.scale_volume(om['k0'], ws), 1e-5, 1e-6)
+    assert m.k0.grid.is_contiguous(memory_format=torch.channels_last_3d) == cl or not cl
+    voxel_size = ((om['xyz_max'] - om['xyz_min']).prod() / new_voxels).pow(1 / 3)
+    close(m.voxel_size, voxel_size, 1e-6, 0)
+    # the resized model still renders
+    ro, rd, vd = (T(x).to(DEV) for x in S.make_rays(64, seed=3))
+    ret = m(ro, rd, vd, global_step=100, near=0.3, far=6.0, bg=0.0, stepsize=0.5)
+    assert torch.isfinite(ret['rgb_marched']).all()
