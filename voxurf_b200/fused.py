@@ -115,6 +115,7 @@ class FusedFineStep:
             self.k0_touched = torch.zeros(n_words, dtype=torch.int32, device=dev)
             self.k0_live = torch.zeros(n_words, dtype=torch.int32, device=dev)
         self.conv_scratch = None
+        self._dw_stream = None
         self.G = None       # FD gradient grid + its gradient, allocated on the first TV iteration
         self.smoothed = self.d_smoothed = None
         if m.smooth_sdf:
@@ -246,7 +247,16 @@ class FusedFineStep:
             if sparse_dp:      # dL/dk0 of this rank's rows is final here: its all-gather runs under the rest of the backward
                 self._start_k0_exchange(n4)
             self.mlp1.backward(self.d_logit1, self.dX1, defer_dw=True)
-            run_dw_batch([self.mlp2, self.mlp1])
+            # The weight-gradient launch (one persistent CTA per SM, tensor / latency bound, ~220 us) only feeds the
+            # optimizer; the scatter kernels below (atomics / ALU bound, independent inputs) run beside it on the main
+            # stream.  Fork here, join at the end of this method; inside a CUDA-graph capture the side stream joins
+            # the capture through the same wait_stream calls.
+            if self._dw_stream is None:
+                self._dw_stream = torch.cuda.Stream(device=self.dev)
+            main = torch.cuda.current_stream()
+            self._dw_stream.wait_stream(main)
+            with torch.cuda.stream(self._dw_stream):
+                run_dw_batch([self.mlp2, self.mlp1])
         else:
             self.mlp2.backward(self.d_kout, self.dX2)
             if sparse_dp:
@@ -267,6 +277,8 @@ class FusedFineStep:
             call('vx_conv3d_replicate_separable', self.d_smoothed, 1, X, Y, Z, m.smooth_conv.weight1d_host, m.smooth_conv.ksize, 1, 1,
                  self.conv_scratch, self.sdf_grad)
             self.d_smoothed.zero_()
+        if self.tensor_core:
+            torch.cuda.current_stream().wait_stream(self._dw_stream)   # join: the optimizer / exchange needs the weight gradients
         return self.loss
 
     # ------------------------------------------------------------------ data-parallel exchange
