@@ -337,30 +337,40 @@ class FusedFineStep:
         tv = self.is_tv_iter(global_step) and c['weight_tv_density'] > 0 and not c.get('ori_tv', False)
         return bool(tv), bool(global_step < c['tv_dense_before'])
 
-    def regularise(self, global_step, global_batch=None, flags=None):
-        """run.py:612-625 (smooth-grad TV through the full-grid FD gradient) and run.py:641-655 (TV add-grad)."""
+    def regularise_prepare(self, flags):
+        """First half of the smooth-gradient TV regulariser (run.py:612-625): FD gradient grid -> dL/dG and the loss
+        term.  It only reads the sdf grid, so _step_body runs it on the side stream beside the forward / backward pass."""
         c, m = self.cfg, self.m
-        is_tv, dense = flags if flags is not None else self.tv_flags(global_step)
+        is_tv, dense = flags
+        tv = c['tv_terms']
+        if not is_tv or tv['smooth_grad_tv'] <= 0:
+            return
+        X, Y, Z = self.X, self.Y, self.Z
+        if self.G is None:
+            # Only the part of the gradient grid within one voxel of the non-empty mask is ever read by the
+            # regulariser (3^3 smoothing of masked voxels), and dL/dG is zero outside the mask: G and dG are
+            # zero-initialised once, the FD gradient is evaluated inside the dilated mask only, dG is written inside
+            # the mask only, and the FD adjoint is skipped outside the dilated mask.  Same numbers, ~85 % less
+            # traffic for a typical mask.  (m.gradient is therefore only valid near the mask in this path.)
+            self.G = torch.zeros(1, 3, X, Y, Z, dtype=torch.float32, device=self.dev)
+            self.dG = torch.zeros_like(self.G)
+            self.tv_active = (F.max_pool3d(m.nonempty_mask.float(), 3, 1, 1) > 0)[0, 0].contiguous()
+            self.tv_loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            self.tv_scratch = torch.empty(int(call('vx_smooth_grad_tv_scratch_floats')), dtype=torch.float32, device=self.dev)
+        call('vx_fd_gradient_active', m.sdf.grid, X, Y, Z, m._voxel_size_host, self.tv_active, self.G)
+        m.gradient = self.G
+        w = c['weight_tv_density'] * tv['smooth_grad_tv'] / (3.0 * m._n_nonempty)
+        call('vx_smooth_grad_tv_masked_writes', self.G, m.nonempty_mask[0, 0], X, Y, Z, m._tv_smooth_w, w, self.dG, self.tv_scratch, self.tv_loss)
+
+    def regularise_apply(self, flags, global_batch=None):
+        """Second half: the regularisers' gradients land in the sdf gradient (run.py:622-625, 641-655)."""
+        c, m = self.cfg, self.m
+        is_tv, dense = flags
         if not is_tv:
             return
         X, Y, Z = self.X, self.Y, self.Z
         tv = c['tv_terms']
         if tv['smooth_grad_tv'] > 0:
-            if self.G is None:
-                # Only the part of the gradient grid within one voxel of the non-empty mask is ever read by the
-                # regulariser (3^3 smoothing of masked voxels), and dL/dG is zero outside the mask: G and dG are
-                # zero-initialised once, the FD gradient is evaluated inside the dilated mask only, dG is written inside
-                # the mask only, and the FD adjoint is skipped outside the dilated mask.  Same numbers, ~85 % less
-                # traffic for a typical mask.  (m.gradient is therefore only valid near the mask in this path.)
-                self.G = torch.zeros(1, 3, X, Y, Z, dtype=torch.float32, device=self.dev)
-                self.dG = torch.zeros_like(self.G)
-                self.tv_active = (F.max_pool3d(m.nonempty_mask.float(), 3, 1, 1) > 0)[0, 0].contiguous()
-                self.tv_loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
-                self.tv_scratch = torch.empty(int(call('vx_smooth_grad_tv_scratch_floats')), dtype=torch.float32, device=self.dev)
-            call('vx_fd_gradient_active', m.sdf.grid, X, Y, Z, m._voxel_size_host, self.tv_active, self.G)
-            m.gradient = self.G
-            w = c['weight_tv_density'] * tv['smooth_grad_tv'] / (3.0 * m._n_nonempty)
-            call('vx_smooth_grad_tv_masked_writes', self.G, m.nonempty_mask[0, 0], X, Y, Z, m._tv_smooth_w, w, self.dG, self.tv_scratch, self.tv_loss)
             self.loss.add_(self.tv_loss)   # run.py:622-625 adds the regulariser to the reported loss
         n_batch = global_batch or self.N * self.world
         wt = c['weight_tv_density'] * tv['sdf_tv'] / n_batch * max(X, Y, Z) / 128
@@ -374,6 +384,12 @@ class FusedFineStep:
         if tv['sdf_tv'] > 0:
             call('vx_total_variation_add_grad', m.sdf.grid, self.sdf_grad, None, wt, wt, wt,
                  int(dense), X, Y, Z, m.sdf.grid.numel())
+
+    def regularise(self, global_step, global_batch=None, flags=None):
+        """run.py:612-625 (smooth-grad TV through the full-grid FD gradient) and run.py:641-655 (TV add-grad)."""
+        flags = flags if flags is not None else self.tv_flags(global_step)
+        self.regularise_prepare(flags)
+        self.regularise_apply(flags, global_batch)
 
     @torch.no_grad()
     def optimizer_step(self, only=None, advance=True):
@@ -420,17 +436,32 @@ class FusedFineStep:
             self.lr[k] *= f
 
     def _step_body(self, rays_o, rays_d, viewdirs, target, global_step, flags):
+        if flags[0] and self.tensor_core and self.world == 1:   # (multi-GPU keeps the order its tests were run with)
+            # the first half of the TV regulariser depends on the parameters only: it runs on the side stream (ahead of
+            # the weight-gradient launch that is forked onto the same stream later) beside the forward / backward pass
+            if self._dw_stream is None:
+                self._dw_stream = torch.cuda.Stream(device=self.dev)
+            self._dw_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._dw_stream):
+                self.regularise_prepare(flags)
+            early_tv = True
+        else:
+            early_tv = False
         loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
+        if early_tv:     # forward_backward joined the side stream at its end
+            reg = lambda: self.regularise_apply(flags)
+        else:
+            reg = lambda: self.regularise(global_step, flags=flags)
         if self.world > 1:
             # overlap: the sdf / MLP all-reduces run on the NCCL stream while k0 is re-scattered and updated
             self._sync_begin()
             self._sync_k0()
             self.optimizer_step(only=('k0',))
             self._sync_end()
-            self.regularise(global_step, flags=flags)
+            reg()
             self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet'), advance=False)
             return loss
-        self.regularise(global_step, flags=flags)
+        reg()
         self.optimizer_step()
         return loss
 
