@@ -94,3 +94,41 @@ def test_hazard_18_adam_epsilon_placement():
     R.python_adam_step(p2, g.clone(), m2, v2, 1, 0.1)
     expect2 = 1.0 - (0.1 / (1 - 0.9)) * (0.1 * 1e-6) / (np.sqrt(0.01 * 1e-12) / np.sqrt(1 - 0.99) + 1e-8)
     assert abs(float(p2[0]) - expect2) < 1e-6 and abs(expect - expect2) > 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- torch half of the oracle
+def test_hazard_10_12_fd_gradient_boundaries_and_replicate_padding():
+    from oracle import voxurf_ref as R
+    rs = np.random.RandomState(0)
+    sdf = torch.from_numpy(rs.standard_normal((1, 1, 5, 6, 7)).astype(np.float32))
+    g = R.sdf_gradient_grid(sdf, torch.tensor(0.25))
+    # hazard 10: each component is zero on the two boundary planes of its own axis, central difference / 2 / voxel elsewhere
+    assert float(g[0, 0, 0].abs().max()) == 0 and float(g[0, 0, -1].abs().max()) == 0
+    assert float(g[0, 1, :, 0].abs().max()) == 0 and float(g[0, 1, :, -1].abs().max()) == 0
+    assert float(g[0, 2, :, :, 0].abs().max()) == 0 and float(g[0, 2, :, :, -1].abs().max()) == 0
+    assert abs(float(g[0, 0, 2, 3, 4]) - float((sdf[0, 0, 3, 3, 4] - sdf[0, 0, 1, 3, 4]) / 2 / 0.25)) < 1e-6
+    # hazard 12: replicate padding -- a constant grid stays constant under the normalised smoothing kernel, borders included
+    c = torch.full((1, 1, 4, 5, 6), 0.7)
+    out = R.conv3d_replicate(c, R.gaussian_kernel3d(5, 0.8))
+    assert out.shape == c.shape and float((out - 0.7).abs().max()) < 1e-6
+
+
+def test_hazard_14_16_alpha_epsilons_and_last_ray_entropy():
+    from oracle import voxurf_ref as R
+    # hazard 14: (prev - next + 1e-5) / (prev + 1e-5), clipped to [0, 1]; a sample the ray leaves the surface through
+    # (gradient along the view direction) has iter_cos = 0 -> prev == next -> alpha = 1e-5 / (prev + 1e-5)
+    vd = torch.tensor([[0., 0., 1.]])
+    a = R.neus_alpha_from_sdf_scatter(vd, torch.tensor([0]), 0.1, torch.tensor([0.0]), torch.tensor([[0., 0., 1.]]), 0.05)
+    assert abs(float(a[0]) - 1e-5 / (0.5 + 1e-5)) < 1e-9
+    a = R.neus_alpha_from_sdf_scatter(vd, torch.tensor([0]), 0.1, torch.tensor([0.0]), torch.tensor([[0., 0., -1.]]), 0.05)
+    prev, nxt = 1 / (1 + np.exp(-0.05 / 0.05)), 1 / (1 + np.exp(0.05 / 0.05))
+    assert abs(float(a[0]) - (prev - nxt + 1e-5) / (prev + 1e-5)) < 1e-6
+    # hazard 16: the entropy term reads the last ray only
+    target = torch.zeros(3, 3)
+    ret = {'rgb_marched': torch.zeros(3, 3), 'rgb_marched0': torch.zeros(3, 3), 'alphainv_cum': torch.tensor([0.3, 0.6, 0.5])}
+    base = float(R.fine_loss(ret, target))
+    ret['alphainv_cum'] = torch.tensor([0.9, 0.1, 0.5])
+    assert float(R.fine_loss(ret, target)) == base
+    ret['alphainv_cum'] = torch.tensor([0.3, 0.6, 0.9])
+    assert float(R.fine_loss(ret, target)) != base
+    assert abs(base - 0.001 * np.log(2.0)) < 1e-7          # entropy of p = 0.5, weight 0.001
