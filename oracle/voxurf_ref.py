@@ -465,6 +465,19 @@ def total_variation(v, mask=None):
     return (tv2.mean() + tv3.mean() + tv4.mean()) / 3
 
 
+def total_variation_coarse(v, mask):
+    """voxurf_coarse.py:702-715 -- NOT the fine file's formula: the three masked L1 sums are added and divided by
+    3 * mask.sum() (the number of masked VOXELS, times C when the mask is repeated over channels), not by the per-axis
+    pair counts."""
+    tv2 = (v[:, :, 1:, :, :] - v[:, :, :-1, :, :]).abs()
+    tv3 = (v[:, :, :, 1:, :] - v[:, :, :, :-1, :]).abs()
+    tv4 = (v[:, :, :, :, 1:] - v[:, :, :, :, :-1]).abs()
+    tv2 = tv2[mask[:, :, :-1] & mask[:, :, 1:]]
+    tv3 = tv3[mask[:, :, :, :-1] & mask[:, :, :, 1:]]
+    tv4 = tv4[mask[:, :, :, :, :-1] & mask[:, :, :, :, 1:]]
+    return (tv2.sum() + tv3.sum() + tv4.sum()) / 3 / mask.sum()
+
+
 def smooth_grad_tv(gradient, nonempty_mask, smooth_grad_tv_w):
     """voxurf_fine.py:417-420: ((tv_smooth_conv(G).detach() - G)[mask x3] ** 2).mean() * w.
     gradient (1,3,X,Y,Z) (autograd-connected to the sdf grid), nonempty_mask (1,1,X,Y,Z) bool."""
@@ -593,6 +606,39 @@ def sdf_field(sdf, xyz_min, xyz_max, resolution, smooth=True, sigma=0.5):
     axes = [torch.linspace(float(xyz_min[i]), float(xyz_max[i]), resolution) for i in range(3)]
     pts = torch.stack(torch.meshgrid(*axes, indexing='ij'), -1).reshape(-1, 3)
     return grid_trilinear(-grid, pts, xyz_min, xyz_max).reshape(resolution, resolution, resolution)
+
+
+def sdf_gradient_field(sdf, xyz_min, xyz_max, voxel_size, resolution, smooth=True, sigma=0.5):
+    """The 6-tap trilinear gradient of the (smoothed) sdf grid on the same lattice: voxurf_fine.py:502-534 with
+    sample_grad=True, displace 1.0 (BASELINE config 5's 'SDF + gradient field'). -> sdf (res,res,res), grad (res,res,res,3)"""
+    grid = conv3d_replicate(sdf, gaussian_kernel3d(3, sigma)) if smooth else sdf
+    axes = [torch.linspace(float(xyz_min[i]), float(xyz_max[i]), resolution) for i in range(3)]
+    pts = torch.stack(torch.meshgrid(*axes, indexing='ij'), -1).reshape(-1, 3)
+    s, g, _ = fine_grid_sampler(pts, grid, xyz_min, xyz_max, voxel_size)
+    return s.reshape(resolution, resolution, resolution), g.reshape(resolution, resolution, resolution, 3)
+
+
+def mesh_color_forward(m, pts):
+    """voxurf_fine.py:804-892: colour of mesh vertices -- the fine forward's feature build and both MLPs at given
+    points with viewdirs = -normal (normal = gradient / (|gradient| + 1e-5)), no compositing. -> rgb (P,3)"""
+    sdf_grid = conv3d_replicate(m['sdf'], m['smooth_kernel']) if m.get('smooth_kernel') is not None else m['sdf']
+    sdf, gradient, feat = fine_grid_sampler(pts, sdf_grid, m['xyz_min'], m['xyz_max'], m['voxel_size'])
+    viewdirs = -(gradient / (gradient.norm(dim=-1, keepdim=True) + 1e-5))
+    k0 = dense_grid_forward(m['k0'], pts, m['xyz_min'], m['xyz_max'])
+    disp = sorted(set(m['grad_feat']))
+    all_feat, all_grad = sample_sdfs(pts, sdf_grid, disp, m['xyz_min'], m['xyz_max'], m['voxel_size'],
+                                     use_grad_norm=m['use_grad_norm'])
+    rays_xyz = (pts - m['xyz_min']) / (m['xyz_max'] - m['xyz_min'])
+    rgb_feat = torch.cat([positional_encoding(rays_xyz, m['posfreq']), positional_encoding(viewdirs, m['viewfreq'])], -1)
+    hier = ([sdf[:, None]] if m['center_sdf'] else []) + [all_feat, all_grad]
+    rgb_logit = mlp(torch.cat([rgb_feat, *hier], dim=-1), m['rgbnet'])
+    k_feat = torch.cat([k0, positional_encoding(rays_xyz, m['k_posfreq']), positional_encoding(viewdirs, m['k_viewfreq']),
+                        gradient], -1)
+    if m.get('k_center_sdf', False):
+        k_feat = torch.cat([k_feat, sdf[:, None]], -1)
+    if m.get('k_res', True):
+        k_feat = torch.cat([k_feat, rgb_logit.detach()], dim=-1)
+    return torch.sigmoid(rgb_logit.detach() + mlp(k_feat, m['k_rgbnet']))
 
 
 def scale_volume(grid, new_world_size):

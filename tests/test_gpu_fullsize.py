@@ -1,0 +1,89 @@
+"""GPU: the BENCHMARKED configuration itself -- fine 256^3, 12-channel k0, 8192 rays, FusedFineStep(use_graph=True),
+global_step 15001.. -- against the CPU oracle following the same trajectory (bench.oracle_bench_step: forward, losses,
+backward, TV every 3rd iteration, dense python Adam).  Covers what the small-grid tests cannot: the 32-bit index paths of
+the 256^3 kernels, the MLP row buffers at ~45 k rows across ~350 tiles, the sparse-aware k0 Adam at full size, and CUDA-graph
+capture + replay of both step variants with device-side scalars.  ~1-2 minutes of host CPU for the six oracle steps."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _lin(seq):
+    return [m for m in seq.modules() if isinstance(m, torch.nn.Linear)]
+
+
+def _close(a, b, rtol, atol, msg):
+    a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=msg)
+
+
+def _grad_close(a, b, msg):
+    b = b.detach().cpu()
+    _close(a, b, 1e-4, 1e-4 * max(float(b.abs().max()), 1e-30), msg)
+
+
+@pytest.mark.timeout(1500)
+def test_benchmarked_shape_follows_the_oracle_trajectory():
+    import bench
+    from voxurf_b200.fused import FusedFineStep
+    from voxurf_b200.trainer import FINE_TRAIN
+    args = bench.parse([])
+    G, C, N = args.grid, args.k0_channels, args.rays
+    assert (G, C, N) == (256, 12, 8192)
+    m = bench.build_model(args, torch.device(DEV))
+    k0 = m.k0.grid.detach().cpu().contiguous()
+    mlps = tuple([(l.weight.detach().cpu().clone(), l.bias.detach().cpu().clone()) for l in _lin(net)] for net in (m.rgbnet, m.k_rgbnet))
+    om, params, lrs, state = bench.oracle_bench_model(G, C, 0, k0=k0, mlps=mlps, sdf=m.sdf.grid.detach().cpu())
+    # 16.7 M lattice points through the mask cache: allow a handful of alpha == thres borderline voxels, then share the mask
+    assert int((m.nonempty_mask.cpu() != om['nonempty_mask']).sum()) <= 8
+    om['nonempty_mask'] = m.nonempty_mask.cpu()
+    fs = FusedFineStep(m, N, FINE_TRAIN, bench.RENDER_KW, use_graph=True)
+    pool = bench.ray_pool(3, N, 0)
+    dpool = [tuple(t.to(DEV) for t in b) for b in pool]
+    fs.calibrate(*dpool[0][:3], global_step=bench.START_STEP, headroom=1.35)
+    decay = 0.1 ** (1 / (FINE_TRAIN['lrate_decay'] * 1000))
+
+    # ---- step 15001 in pieces: forward + backward compared in detail, then regularise (no-op: not a TV iteration) + Adam
+    gs = bench.START_STEP
+    loss = fs.forward_backward(*dpool[0], gs).clone()
+    rgb, rgb0 = fs.rgb_marched.clone(), fs.rgb_marched0.clone()
+    counts = fs.counts()
+    g_prod = {'sdf': m.sdf.grid.grad.detach().clone().cpu(), 'k0': m.k0.grid.grad.detach().contiguous().clone().cpu(),
+              'mlp': [(l.weight.grad.clone().cpu(), l.bias.grad.clone().cpu()) for mlp in (fs.mlp1, fs.mlp2) for l in mlp.linears]}
+    fs.regularise(gs)
+    fs.optimizer_step()
+    fs.apply_lr_decay()
+    grads = []
+    oloss, oret = bench.oracle_bench_step(om, params, lrs, state, pool[0], gs, 1, N, G, grads_out=grads)
+    assert counts == (oret['mask_outbbox'].shape[0], int((~oret['mask_outbbox']).sum()), oret['weights'].shape[0]), counts
+    _close(loss, oloss, 1e-5, 1e-7, 'loss 15001')
+    _close(rgb, oret['rgb_marched'], 1e-5, 3e-6, 'rgb_marched'); _close(rgb0, oret['rgb_marched0'], 1e-5, 3e-6, 'rgb_marched0')
+    _grad_close(g_prod['sdf'], grads[0], 'grad sdf'); _grad_close(g_prod['k0'], grads[1], 'grad k0')
+    for i, (gw, gb) in enumerate(g_prod['mlp']):
+        _grad_close(gw, grads[2 + 2 * i], f'grad W{i}'); _grad_close(gb, grads[3 + 2 * i], f'grad b{i}')
+    del grads, g_prod
+
+    # ---- steps 15002..15006 through step(): first occurrences eager, then capture, then replay of both variants
+    for it in range(1, 6):
+        gs = bench.START_STEP + it
+        b = it % len(pool)
+        loss = fs.step(*dpool[b], gs).clone()
+        fs.apply_lr_decay()
+        rgb = fs.rgb_marched.clone()
+        M0, M2, M4 = fs.counts()
+        oloss, oret = bench.oracle_bench_step(om, params, lrs, state, pool[b], gs, it + 1, N, G, lr_scale=decay ** it)
+        assert M0 == oret['mask_outbbox'].shape[0] and M2 == int((~oret['mask_outbbox']).sum())
+        assert abs(M4 - oret['weights'].shape[0]) <= 16, (M4, oret['weights'].shape[0])   # w > 1e-4 borderline samples
+        _close(loss, oloss, 1e-4, 1e-7, f'loss {gs}')
+        _close(rgb, oret['rgb_marched'], 1e-4, 2e-5, f'rgb_marched {gs}')
+    assert len(fs._graphs) == 2 and fs.launches_replayed > 0
+    fs.poll_overflow(force=True)
+    # parameters after six steps (Adam's first steps are sign-like: all but a small fraction within a fraction of lr)
+    d = (m.sdf.grid.detach().cpu() - om['sdf'].detach()).abs()
+    assert float((d > 2e-2 * 5e-3).float().mean()) < 1e-4 and float(d.max()) <= 6 * 5e-3 * 1.01, (float((d > 1e-4).float().mean()), float(d.max()))
+    d = (m.k0.grid.detach().cpu() - om['k0'].detach()).abs()
+    assert float((d > 2e-2 * 1e-1).float().mean()) < 1e-4, float((d > 2e-3).float().mean())

@@ -144,12 +144,12 @@ def test_coarse_model_matches_oracle_with_regularisers(G, n_rays, cl):
     # run.py:604-628 with ori_tv=True (configs/dtu_e2e/coarse.py:27-45)
     oloss = F.mse_loss(oret['rgb_marched'], target)
     oloss = oloss + 0.001 * R.smooth_grad_tv(oret['_full_gradient'], om['nonempty_mask'], 0.2)
-    oloss = oloss + 0.001 * (R.total_variation(om['sdf'], om['nonempty_mask']) / 2 / om['voxel_size'] * 0.1)
+    oloss = oloss + 0.001 * (R.total_variation_coarse(om['sdf'], om['nonempty_mask']) / 2 / om['voxel_size'] * 0.1)
     loss = F.mse_loss(ret['rgb_marched'], target.to(DEV))
     loss = loss + 0.001 * m.density_total_variation(sdf_tv=0, smooth_grad_tv=0.2)
     loss = loss + 0.001 * m.density_total_variation(sdf_tv=0.1, smooth_grad_tv=0)
     if not cl:
-        oloss = oloss + 0.01 * R.total_variation(om['k0'], om['nonempty_mask'].repeat(1, 12, 1, 1, 1))
+        oloss = oloss + 0.01 * R.total_variation_coarse(om['k0'], om['nonempty_mask'].repeat(1, 12, 1, 1, 1))
         loss = loss + 0.01 * m.k0_total_variation()
     close(loss, oloss, 1e-5, 1e-7)
     oloss.backward(); loss.backward()

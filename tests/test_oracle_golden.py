@@ -202,3 +202,52 @@ def test_training_rays_in_maskcache_match_reference():
     assert counts == g['tr_imsz'].tolist()
     assert np.array_equal(rgb.numpy(), g['tr_rgb'])          # the kept pixels, in order: identifies the kept rays exactly
     close(ro, g['tr_rays_o'], 2e-6, 1e-6); close(rd, g['tr_rays_d'], 2e-6, 1e-6); close(vd, g['tr_viewdirs'], 2e-6, 1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: tests/golden/r2_extras.npz (make_golden_r2.py) -- coarse regularisers, progressive growing, mesh fields,
+# vertex colours, all from the reference's own functions
+# ------------------------------------------------------------------------------------------------
+def test_coarse_total_variation_is_not_the_fine_formula():
+    """lib/voxurf_coarse.py:702-715 divides the three masked sums by 3 * mask.sum(); lib/voxurf_fine.py:956-969 takes
+    per-axis means.  The two differ whenever the mask has a boundary."""
+    g = load_golden('r2_extras.npz')
+    sc = S.make_coarse_scene(16, 12, 32, seed=4, mask_G=12)
+    m = oracle_coarse_model(sc)
+    close(R.total_variation_coarse(m['sdf'], m['nonempty_mask']), g['ctv_value'])
+    assert abs(float(R.total_variation(m['sdf'], m['nonempty_mask'])) - float(g['ctv_value'])) > 1e-3 * float(g['ctv_value'])
+    G = R.sdf_gradient_grid(m['sdf'], m['voxel_size'])
+    tv = R.total_variation_coarse(m['sdf'], m['nonempty_mask']) / 2 / m['voxel_size'] * 0.1 \
+        + R.smooth_grad_tv(G, m['nonempty_mask'], 0.2)
+    close(tv, g['ctv_density_value'])
+    tv.backward()
+    close(m['sdf'].grad, g['ctv_density_grad'], 1e-5, 1e-7)
+    k0l = R.total_variation_coarse(m['k0'], m['nonempty_mask'].repeat(1, 12, 1, 1, 1))
+    close(k0l, g['ctv_k0_value'])
+    k0l.backward()
+    close(m['k0'].grad, g['ctv_k0_grad'], 1e-5, 1e-9)
+
+
+def test_scale_volume_matches_reference():
+    g = load_golden('r2_extras.npz')
+    sc = S.make_fine_scene(20, 6, 32, seed=3, mask_G=12)
+    m = oracle_fine_model(sc, requires_grad=False)
+    ws = tuple(int(w) for w in g['sv_world_size'])
+    assert ws == (28, 28, 28)
+    nonempty = R.nonempty_mask(m['mask_cache'], XYZ_MIN, XYZ_MAX, ws)
+    assert (nonempty.numpy() == g['sv_nonempty']).all()
+    sdf = R.scale_volume(m['sdf'], ws)
+    sdf[~nonempty] = 1
+    close(sdf, g['sv_sdf'])
+    close(R.scale_volume(m['k0'], ws), g['sv_k0'])
+
+
+def test_mesh_fields_and_vertex_colours_match_reference():
+    g = load_golden('r2_extras.npz')
+    sc = S.make_fine_scene(24, 6, 32, seed=5, mask_G=12)
+    m = oracle_fine_model(sc, requires_grad=False)
+    close(R.sdf_field(m['sdf'], XYZ_MIN, XYZ_MAX, 24, smooth=True, sigma=0.5), g['field_u'])
+    close(R.sdf_field(m['sdf'], XYZ_MIN, XYZ_MAX, 24, smooth=False), g['field_u_raw'])
+    s, gr = R.sdf_gradient_field(m['sdf'], XYZ_MIN, XYZ_MAX, m['voxel_size'], 24, smooth=True, sigma=0.5)
+    close(s, g['field_sdf']); close(gr, g['field_grad'], 1e-5, 1e-5)
+    close(R.mesh_color_forward(m, T(g['mc_pts'])), g['mc_rgb'], 1e-5, 2e-6)

@@ -29,19 +29,46 @@ def _binomial_weights():
     return torch.from_numpy(k / k.sum()).float().flatten().tolist()
 
 
-class SmoothConv:
-    """Callable stand-in for the frozen nn.Conv3d the reference builds in _gaussian_3dconv."""
+class FrozenConv(nn.Module):
+    """Holder of the `weight` / `bias` tensors of a frozen nn.Conv3d of the reference (grad_conv, tv_smooth_conv,
+    smooth_conv*: lib/voxurf_fine.py:204-258) so that state_dict keys and shapes match the reference's checkpoints
+    (`<name>.weight`, `<name>.bias`).  The arithmetic runs in the stencil kernels from host-side weight lists."""
+
+    def __init__(self, weight, bias_len):
+        super().__init__()
+        self.weight = nn.Parameter(weight.float().clone(), requires_grad=False)
+        self.bias = nn.Parameter(torch.zeros(bias_len), requires_grad=False)
+
+
+class SmoothConv(FrozenConv):
+    """Stand-in for the frozen nn.Conv3d the reference builds in _gaussian_3dconv (lib/voxurf_fine.py:246-258)."""
 
     def __init__(self, ksize, sigma):
-        self.ksize, self.sigma = ksize, sigma
-        self.weight_host = _gaussian_weights(ksize, sigma)
+        weight_host = _gaussian_weights(ksize, sigma)
+        super().__init__(torch.tensor(weight_host).view(1, 1, ksize, ksize, ksize), 1)
+        self.ksize, self.sigma, self.weight_host = ksize, sigma, weight_host
         # the normalised Gaussian factorises: k^3 weights = w1 (x) w1 (x) w1 -> three 1-D passes instead of k^3 taps
         r = np.arange(-(ksize // 2), ksize // 2 + 1, 1)
         g = np.exp(-(r.astype(np.float64) ** 2) / (2 * sigma ** 2))
         self.weight1d_host = [float(np.float32(v)) for v in g / g.sum()]
 
-    def __call__(self, x):
+    def forward(self, x):
         return ops.conv3d_replicate(x, self.weight_host, self.ksize, weight1d=self.weight1d_host)
+
+
+def _grad_conv_weight(voxel_size):
+    """lib/voxurf_fine.py:204-227 with sigma = 0 (state_dict compatibility; the 'interpolate' gradient mode never uses it)"""
+    kernel = np.asarray([[[1, 2, 1], [2, 4, 2], [1, 2, 1]], [[2, 4, 2], [4, 8, 4], [2, 4, 2]], [[1, 2, 1], [2, 4, 2], [1, 2, 1]]],
+                        dtype=np.float64)
+    kernel1 = kernel / (kernel[0].sum() * 2 * voxel_size)
+    weight = torch.from_numpy(np.concatenate([kernel1[None] for _ in range(3)])).float()
+    weight[0, 1, :, :] *= 0
+    weight[0, 0, :, :] *= -1
+    weight[1, :, 1, :] *= 0
+    weight[1, :, 0, :] *= -1
+    weight[2, :, :, 1] *= 0
+    weight[2, :, :, 0] *= -1
+    return weight.unsqueeze(1).float()
 
 
 def _mlp(dim0, width, depth):
@@ -76,8 +103,11 @@ class VoxurfBase(nn.Module):
         ws = [int(w) for w in self.world_size]
         x, y, z = np.mgrid[-1.0:1.0:ws[0] * 1j, -1.0:1.0:ws[1] * 1j, -1.0:1.0:ws[2] * 1j]
         self.sdf.grid.data = torch.from_numpy((x ** 2 + y ** 2 + z ** 2) ** 0.5 - 1).float()[None, None, ...]
-        self.nonempty_mask = None
+        self.register_buffer('nonempty_mask', None)   # becomes a real buffer in _set_nonempty_mask (lib/voxurf_fine.py:362-365)
         self._tv_smooth_w = _binomial_weights()
+        # frozen convs of the reference (lib/voxurf_fine.py:204-239): kept for their state_dict keys
+        self.grad_conv = FrozenConv(_grad_conv_weight(self._voxel_size_host), 3)
+        self.tv_smooth_conv = FrozenConv(torch.tensor(self._tv_smooth_w).view(1, 1, 3, 3, 3), 1)
         self.gradient = None
 
     def _init_mask_cache(self, mask_cache_path, mask_cache_thres, mask_cache_state):
@@ -133,9 +163,23 @@ class VoxurfBase(nn.Module):
             torch.linspace(self._min_host[1], self._max_host[1], ws[1]),
             torch.linspace(self._min_host[2], self._max_host[2], ws[2]), indexing='ij'), -1).to(dev)
         self.nonempty_mask = self.mask_cache(xyz)[None, None].contiguous()
-        self._n_nonempty = int(self.nonempty_mask.sum().item())
+        self._refresh_derived()
         self.density[~self.nonempty_mask] = -100
         self.sdf.grid[~self.nonempty_mask] = 1
+
+    def _refresh_derived(self):
+        """Host-side values derived from buffers / parameters: recomputed whenever those change underneath us."""
+        self._n_nonempty = int(self.nonempty_mask.sum().item()) if self.nonempty_mask is not None else 0
+        self._s_val_host = float(self.s_val.detach().reshape(-1)[0].item())
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Reference checkpoints (run.py:786-793, lib/utils.py:232-300) load with strict=True: same keys and shapes.
+        A checkpoint taken after the non-empty mask was built carries a `nonempty_mask` the fresh model may not have."""
+        if 'nonempty_mask' in state_dict and self.nonempty_mask is None:
+            self.nonempty_mask = torch.zeros_like(state_dict['nonempty_mask'], device=self.sdf.grid.device)
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._refresh_derived()
+        return out
 
     @torch.no_grad()
     def scale_volume_grid(self, num_voxels):

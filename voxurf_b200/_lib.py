@@ -87,7 +87,21 @@ def launch_count():
     return int(_load().vx_launch_count())
 
 
+TIMING = None   # bench.py / profiling: a list collecting (name, start_event, end_event) of every call on its stream
+
+
 def call(name, *args):
+    if TIMING is not None and not torch.cuda.is_current_stream_capturing():
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        rc = _call(name, *args)
+        ev[1].record()
+        TIMING.append((name, ev[0], ev[1]))
+        return rc
+    return _call(name, *args)
+
+
+def _call(name, *args):
     lib = _load()
     ret, spec = _protos[name]
     fn = getattr(lib, name)

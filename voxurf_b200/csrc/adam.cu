@@ -177,8 +177,10 @@ VX_API int vx_adam_step(float* param, float* grad, float* exp_avg, float* exp_av
                         float sqrt_bias_correction2, float eps, int skip_zero_grad, int zero_grad,
                         const uint32_t* touched, const uint32_t* live, int group, const float* step_dev, cudaStream_t st) {
   if (N <= 0) return 0;
-  VX_REQUIRE(!touched || (group >= 1 && N % 4 == 0 && N < ((int64_t)1 << 32)), "vx_adam_step",
-             "touched bitmap needs group >= 1, numel % 4 == 0 and numel < 2^32");
+  // a float4 of 4 consecutive elements spans at most two voxels only when a voxel has >= 3 elements: the bitmap tests
+  // look at the voxels of its first and last element
+  VX_REQUIRE(!touched || (group >= 3 && N % 4 == 0 && N < ((int64_t)1 << 32)), "vx_adam_step",
+             "touched bitmap needs group >= 3, numel % 4 == 0 and numel < 2^32");
   VX_REQUIRE(!live || touched, "vx_adam_step", "a live bitmap needs a touched bitmap");
   AdamCoef c;
   c.beta1 = beta1; c.beta2 = beta2; c.omb1 = one_minus_beta1; c.omb2 = one_minus_beta2; c.eps = eps;

@@ -39,7 +39,7 @@ from .optim import _storage
 class FusedFineStep:
     def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0,
                  tensor_core=True, sparse_k0_exchange=True, sparse_adam=True, use_graph=False,
-                 graph_multi_gpu=False):
+                 graph_multi_gpu=True, dense_exchange=False):
         if model.k0_dim not in (6, 12):
             raise NotImplementedError('fused step: k0 channels must be 6 or 12')
         if model.k_center_sdf or not model.center_sdf or not model.k_res:
@@ -96,6 +96,11 @@ class FusedFineStep:
         self.weight, self.T = f32(cap2), f32(cap2)
         self.d_w, self.d_alpha, self.d_sdf_s, self.d_grad_s = f32(cap2), f32(cap2), f32(cap2), f32(cap2, 3)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        # row-capacity overflow is polled without a sync: every `overflow_check_every` steps the counter is copied to
+        # pinned memory behind an event, and the copy is inspected once the event has completed (a step or two later)
+        self.overflow_check_every = 16
+        self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._ovf_event, self._ovf_pending, self._ovf_calls = torch.cuda.Event(), False, 0
         self._alloc_rows(int(row_capacity))
         # MLPs on flat parameter / gradient storage (one Adam launch per network)
         self.mlp1 = FlatMLP(m.rgbnet, self.ld1, self.D1, tensor_core)
@@ -131,6 +136,8 @@ class FusedFineStep:
         if self.use_graph:
             self.consts = torch.zeros(16, dtype=torch.float32, device=dev)
             self.in_o, self.in_d, self.in_v, self.in_t = (torch.zeros(n_rays, 3, dtype=torch.float32, device=dev) for _ in range(4))
+        self.force_eager = False   # bench.py: launch the kernels of the step one by one even when use_graph is set
+        self.sharded = False
         self.bitmap_probe = None   # bench.py: list collecting copies of (touched, live) as the k0 Adam launch sees them
         self.timings = None   # bench.py: list collecting (group, (start, end) CUDA events) around the k0 / sdf Adam launches
         if self.cfg is not None:
@@ -220,6 +227,7 @@ class FusedFineStep:
         """Inference forward (run.py:123-126 calls model(...) per 8192-ray chunk): -> dict of (N, .) tensors.
         Buffers are reused by the next call: clone what you keep."""
         s_val, n2, n4 = self._forward(rays_o, rays_d, viewdirs, None, train=False)
+        self.poll_overflow()
         call('vx_fused_composite_loss', self.logit1, self.k_out, 3, self.idx4, self.off4, self.cap4, self.weight,
              self.alphainv_last, None, self.N, 0.0, 0.0, 0.0, 0.0, float(self.rk.get('bg', 0.0)), 0, self.rgb_marched,
              self.rgb_marched0, None, None, None, None, None)
@@ -424,6 +432,55 @@ class FusedFineStep:
                     ev[1].record()
                     self.timings.append((name, ev))
 
+    def state_dict(self):
+        """Optimizer state of the fused step (the model's own state_dict holds the parameters): Adam moments per
+        group, step count, decayed learning rates, the k0 `live` bitmap.  Mirrors what run.py:786-793 saves as
+        optimizer_state_dict."""
+        self.sync_s_val()
+        st = {'adam_steps': self.adam_steps, 'lr': dict(self.lr), 'moments': {}}
+        for name, params, _ in self.groups:
+            m = self.adam_state.get(id(params[0]))
+            if m is not None:
+                st['moments'][name] = (m[0].detach().clone(), m[1].detach().clone())
+        if self.k0_live is not None:
+            st['k0_live'] = self.k0_live.clone()
+        return st
+
+    def load_state_dict(self, st):
+        self.adam_steps = int(st['adam_steps'])
+        self.lr.update(st['lr'])
+        for name, params, _ in self.groups:
+            if name in st['moments']:
+                p = params[0]
+                cur = self.adam_state.get(id(p))
+                if cur is None:
+                    cur = (torch.zeros_like(p, memory_format=torch.preserve_format), torch.zeros_like(p, memory_format=torch.preserve_format))
+                    self.adam_state[id(p)] = cur
+                for dst, src in zip(cur, st['moments'][name]):     # in place: captured graphs keep their pointers
+                    _storage(dst).copy_(_storage(src.to(dst.device)) if src.shape == dst.shape else src.to(dst.device).reshape(_storage(dst).shape))
+        if self.k0_live is not None:
+            if 'k0_live' in st:
+                self.k0_live.copy_(st['k0_live'])
+            else:
+                self.mark_all_live()    # moments of unknown sparsity: every voxel may hold non-zero exp_avg / exp_avg_sq
+        self.m._refresh_derived()
+
+    def warm_up(self, batches, global_step):
+        """Run real training steps from `global_step` until every execution variant of the step (TV / non-TV iteration)
+        has had its eager first occurrence and -- with use_graph -- its CUDA graph captured, so that later steps are
+        pure replays.  `batches`: list of (rays_o, rays_d, viewdirs, target).  Returns the next global_step."""
+        c = self.cfg
+        want = {self.tv_flags(global_step + i) for i in range(2 * max(1, c['tv_every']) + 2)}
+        done = (lambda: set(self._graphs) >= want) if self.use_graph else (lambda: self._eager_seen >= want)
+        i = 0
+        while not done() and i < 8 * max(1, c['tv_every']):
+            b = batches[i % len(batches)]
+            if not self.use_graph:
+                self._eager_seen.add(self.tv_flags(global_step + i))
+            self.step(*b, global_step + i)
+            i += 1
+        return global_step + i
+
     def mark_all_live(self):
         """Call after loading optimizer moments from elsewhere: every voxel may then hold non-zero exp_avg / exp_avg_sq."""
         if self.k0_live is not None:
@@ -503,14 +560,44 @@ class FusedFineStep:
         self.launches_replayed += self._graph_launches[flags]
         return self.loss
 
+    def release_graphs(self):
+        """Drop the captured CUDA graphs (they hold NCCL work at world > 1: release them before the process group)."""
+        self._graphs.clear()
+        self._graph_launches.clear()
+        torch.cuda.synchronize()
+
     def sync_s_val(self):
         """Write the host-side NeuS s_val into the model's s_val parameter (graph replays keep it on the host only)."""
         if hasattr(self.m, '_s_val_host'):
             self.m.s_val.data.fill_(self.m._s_val_host)
 
+    def poll_overflow(self, force=False):
+        """Raise if an earlier step dropped MLP rows (M4 > row_capacity: its loss and gradients were wrong).  Without
+        `force` this never waits for the GPU: see overflow_check_every.  force=True syncs (end of training / of a view)."""
+        if self._ovf_pending and (force or self._ovf_event.query()):
+            self._ovf_event.synchronize()
+            self._ovf_pending = False
+            if int(self._ovf_host[0]) > 0:
+                raise RuntimeError(f'FusedFineStep: {int(self._ovf_host[0])} MLP rows exceeded row_capacity={self.cap4} in an earlier '
+                                   'step (rows were dropped: loss and gradients of that step are wrong); call calibrate() '
+                                   'with a representative batch at the current global_step, or raise row_capacity')
+        self._ovf_calls += 1
+        if not self._ovf_pending and (force or self._ovf_calls % self.overflow_check_every == 0):
+            self._ovf_host.copy_(self.overflow, non_blocking=True)
+            self._ovf_event.record()
+            self._ovf_pending = True
+            if force:
+                self.poll_overflow(force=True)
+
     def step(self, rays_o, rays_d, viewdirs, target, global_step, grad_sync=None):
-        """One training iteration (run.py:600-659).  grad_sync: optional callable run between backward and TV/Adam."""
-        if self.use_graph and grad_sync is None and self.timings is None and self.bitmap_probe is None:
+        """One training iteration (run.py:600-659).  grad_sync: optional callable run between backward and TV/Adam.
+        calibrate() sizes the MLP row buffers; an overflow of that capacity is detected asynchronously (poll_overflow)."""
+        loss = self._step(rays_o, rays_d, viewdirs, target, global_step, grad_sync)
+        self.poll_overflow()
+        return loss
+
+    def _step(self, rays_o, rays_d, viewdirs, target, global_step, grad_sync=None):
+        if self.use_graph and grad_sync is None and self.timings is None and self.bitmap_probe is None and not self.force_eager:
             return self._step_graph(rays_o, rays_d, viewdirs, target, global_step)
         if grad_sync is None and self.world > 1:
             return self._step_body(rays_o, rays_d, viewdirs, target, global_step, self.tv_flags(global_step))

@@ -80,6 +80,8 @@ class Adam(torch.optim.Optimizer):
                 call('vx_adam_step', _storage(p.data), _storage(g), _storage(state['exp_avg']),
                      _storage(state['exp_avg_sq']), per_lr, p.numel(), beta1, beta2, 1 - beta1, 1 - beta2, step_size,
                      math.sqrt(bias_correction2), group['eps'], 0, int(self.zero_grad_in_step), None, None, 1, None)
+                if self.zero_grad_in_step and g is not p.grad:
+                    p.grad.zero_()   # the kernel zeroed the dense copy, not the strided gradient autograd accumulates into
                 if timed:
                     ev[1].record()
                     self.timings.append(ev)

@@ -67,8 +67,12 @@ class Voxurf(VoxurfBase):
         return None if self.nonempty_mask is None else self.nonempty_mask[0, 0]
 
     def _counts(self):
+        """Normaliser of lib/voxurf_coarse.py:702-715: the three masked L1 sums are divided by 3 * mask.sum() -- the
+        number of masked VOXELS (times C through the repeated mask), the same for every axis -- unlike the fine file's
+        per-axis pair means (lib/voxurf_fine.py:956-969)."""
         if self._pair_counts is None or self._pair_counts[0] is not self.nonempty_mask:
-            self._pair_counts = (self.nonempty_mask, ops.tv_pair_counts(self._mask3(), tuple(self.sdf.grid.shape[2:])))
+            n = self._n_nonempty if self.nonempty_mask is not None else int(self.sdf.grid[0, 0].numel())
+            self._pair_counts = (self.nonempty_mask, [n, n, n])
         return self._pair_counts[1]
 
     def density_total_variation(self, sdf_tv=0, smooth_grad_tv=0, sdf_thrd=0.999):
