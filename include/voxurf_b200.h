@@ -279,13 +279,28 @@ int vx_mlp_prep(const float* W, int N, int K, int ldw, int Np, int Kp, int trans
  * dims_host[j*6..] = N, K, ldw, Np, Kp, transpose */
 int vx_mlp_prep_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, cudaStream_t stream);
 /* Y = chain of up to 4 layers y = act(x W^T + b) [* (mask > 0)] on 128-row tiles.  Packed host arrays (csrc/mlp_tc.cu):
- * ptrs_host[l*5..] = W_hi, W_lo, bias, row image out, mask row image (device addresses, 0 = none);
+ * ptrs_host[l*5..] = W_hi, W_lo, bias, row image out, ReLU-gate bitmap in (device addresses, 0 = none; see vx_mlp_chain_batch);
  * dims_host[l*4..] = Kp, Np, N, relu.  Row images ACT(F) (raw fp32, r = MLP row, F = feature count padded to 32; byte offset
  * (r/4)*16F + (f/32)*512 + (r%4)*128 + (((f%32)/8) ^ (r%4))*32 + (f%8)*4 -- the MN-major TF32 UMMA operand layout) feed
  * vx_mlp_dw; x_img is the ACT(pad32(Kp[0])) image of the input. */
 int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, int capacity, int n_layers,
                  const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* x_img,
                  cudaStream_t stream);
+/* Up to 2 layer chains ("jobs": the forward chains of both colour networks, or both dX chains) in ONE launch: the 128-row
+ * tiles of all jobs share the SMs.  A forward job may end in a tiny last layer evaluated in exact fp32 on the CUDA cores
+ * (Wf / bias_f, n_out <= 4 -- lib/voxurf_fine.py:132-149 ends every colour MLP in Linear(width, 3)), and may take some input
+ * columns from an earlier job's output rows (k_rgbnet reads rgb_logit.detach(), lib/voxurf_fine.py:741-751).  Per job j:
+ *   ptrs_host[j*30 + {0..5}]            = X, x_img, Y, Wf, bias_f, patch           (device addresses, 0 = none)
+ *   ptrs_host[j*30 + 6 + l*6 + {0..5}]  = layer l: W_hi, W_lo, bias, row image out, ReLU-gate words in (dX chains: four
+ *                                         uint64 per row, feature 64c + 16g + j <-> bit 16c + j of word [4r + g], 1 = pass),
+ *                                         ReLU-gate words out (forward chains)
+ *   dims_host[j*26 + {0..9}]            = ldx, K0, n_layers, ldy, n_out, ldwf, patch_col, patch_n, patch_ld, dep (-1 = none)
+ *   dims_host[j*26 + 10 + l*4 + {0..3}] = layer l: Kp, Np, N, relu
+ * done_flags: n_jobs * ceil(capacity / 128) ints (only needed when a job has dep >= 0); zeroed by the call. */
+/* development hook: event log of CTA 0 (only in -DMC_TRACE builds of csrc/mlp_tc.cu) */
+int vx_mlp_trace_set(int64_t* buf);
+int vx_mlp_chain_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
+                       int* done_flags, cudaStream_t stream);
 /* split-K weight gradient on the row images: C[m][n] += sum_r A[r][m] B[r][n], c_bias[m] += sum_r A[r][m]
  * (r < *n_rows_dev, m < M_out <= FA, n < N_in <= FB; FA, FB multiples of 32; image rows past *n_rows_dev up to the next
  * multiple of 16 must hold zeros) */

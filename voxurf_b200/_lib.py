@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'voxurf_b200.h')
-SO_PATH = os.path.join(_HERE, 'libvoxurf_b200.so')
+SO_PATH = os.environ.get('VX_SO') or os.path.join(_HERE, 'libvoxurf_b200.so')   # VX_SO: development builds (e.g. -DMC_TRACE)
 
 _PTR_DTYPES = {
     'float': (torch.float32,), 'int': (torch.int32,), 'int64_t': (torch.int64,), 'bool': (torch.bool, torch.uint8),

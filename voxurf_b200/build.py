@@ -10,9 +10,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(HERE, 'csrc', '_obj')
-SO = os.path.join(HERE, 'libvoxurf_b200.so')
+OBJ = os.path.join(HERE, 'csrc', os.environ.get('VX_OBJ_DIR', '_obj'))
+SO = os.environ.get('VX_SO') or os.path.join(HERE, 'libvoxurf_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+EXTRA = os.environ.get('VX_NVCC_FLAGS', '').split()   # development, e.g. VX_NVCC_FLAGS=-DMC_TRACE
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 
@@ -36,7 +37,7 @@ def build(force=False, verbose=False):
 
     def cc(job):
         s, o = job
-        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
+        cmd = [NVCC] + FLAGS + EXTRA + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (s, r.stdout, r.stderr))

@@ -24,10 +24,7 @@
 #define MLP_STAGES 2
 #define MLP_SLICE_K 32        // K extent of one weight slice in the bulk-copy ring (4 MMA K-steps); a 5 x K=16 ring measured 10 % slower
 #define MLP_MAX_LAYERS 4
-#define MLP_TMEM_COLS 512     // D accumulator at column 0, A (hi) operand at column 256
-#define MLP_TMEM_A 256
-#define MLP_ROW_THREADS 256   // warps 0-7: thread = row (TMEM lane = tid % 128); warps 0-3 / 4-7 take alternate column blocks
-#define MLP_THREADS 288       // + warp 8: weight producer
+#define MLP_TMEM_COLS 512     // chain kernel: accumulators at columns 0 / 128 (alternating), A (hi) operand at 320
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -243,217 +240,536 @@ VX_API int vx_mlp_prep(const float* W, int N, int K, int ldw, int Np, int Kp, in
 
 // ---------------------------------------------------------------------------------------------
 // the chain kernel
+//
+// One persistent CTA per SM walks a queue of (job, 128-row tile) items; a job is a layer chain of one network (the
+// forward chain of rgbnet, the forward chain of k_rgbnet, or one of the two dX chains), up to MLP_MAX_JOBS jobs per
+// launch so that the tiles of both networks fill the 148 SMs in one go (706 tile items = 4.8 waves instead of 2 x 3).
+//
+// Warp roles (576 threads):
+//   warps 0-15  row warps.  TMEM lane quarter = warp % 4 (a warp may only touch lanes 32 * (warp % 4) ..), column group
+//               cg = warp / 4: thread (row, cg) owns the 16 columns [64 c + 16 cg, +16) of every 64-column chunk c.
+//   warp 16     weight producer: lane 0 streams the K = 32 weight slices (hi and lo images) with bulk copies through a
+//               2-slot ring, in exactly the order the MMA warp consumes them.
+//   warp 17     MMA issuer: lane 0 issues tcgen05.mma (TF32 x 3) and commits.
+//
+// Pipelining inside a tile.  TMEM (512 columns): A operand (hi part, K <= 192 columns) at 320; the accumulator of MMA
+// layer q (a per-CTA running count) at column 0 for even q and 128 for odd q.  Consecutive accumulators overlap only in
+// columns [128, 192).  The epilogue of layer q walks its three 64-column chunks starting with the one inside that
+// overlap; as soon as a chunk is done -- accumulator columns read, bias / ReLU (or the ReLU gate of the dX chain)
+// applied, the hi part written to TMEM A and the lo part to shared memory, the raw values to the HBM row image -- the
+// row warps arrive on that chunk's mbarrier and the MMA warp issues the 8 K-steps of layer q + 1 that consume it, into
+// the OTHER accumulator, while the row warps work on the next chunk.  So a layer costs ~ (epilogue / 3 + MMAs) instead
+// of (epilogue + MMAs).  The same hand-over happens across tiles: in the epilogue of a tile's last MMA layer, right
+// after the first chunk, the row warps stage the input rows of the CTA's next tile (prefetched into registers before
+// the accumulator wait) into the A operand, so the next tile's first layer runs under the rest of that epilogue.
+//
+// Forward chains end in a tiny N = 3 layer: 72 MMAs at the 96-clock floor of tcgen05.mma (as much tensor time as a
+// 192-wide layer) for 0.2 % of the flops.  It runs on the CUDA cores instead, inside the epilogue of the last hidden
+// layer: every thread accumulates its 48 columns' share of the three dot products in exact fp32 (weights broadcast from
+// shared memory), the four column groups meet through shared memory.
+//
+// k_rgbnet's input carries rgbnet's output for the same row (rgb_logit.detach(), lib/voxurf_fine.py:741-751): job 1
+// declares `dep = 0` and patches those input columns from job 0's output.  Job 0's tiles come first in the queue and set
+// a per-tile flag (release) when their output rows are in memory; the consumer tile spins on it (acquire).  All CTAs are
+// co-resident (grid <= #SMs, one CTA per SM) and every CTA handles its job-0 items before its job-1 items: no deadlock.
 // ---------------------------------------------------------------------------------------------
+#define MC_ROW_WARPS 16
+#define MC_ROW_THREADS (MC_ROW_WARPS * 32)
+#define MC_THREADS (MC_ROW_THREADS + 96)     // + producer warp, MMA warp, publisher warp
+#define MC_TMEM_A 320
+#define MLP_MAX_JOBS 2
+#define MC_MAX_FINAL 4          // outputs of the CUDA-core final layer
+
 struct MlpLayer {
   const float* W_hi;    // CH(Np) image, Kp/4 chunks
   const float* W_lo;
   const float* bias;    // [N] or nullptr
   float* img;           // ACT(Np) row image of this layer's output, or nullptr
-  const float* mask;    // ACT(Np) row image of the forward activation: output *= (mask > 0), or nullptr
+  const unsigned long long* gate;  // ReLU gates applied to this layer's output (dX chains), one 64-bit word per (row, column
+                        //   group cg): feature f = 64 c + 16 cg + j <-> bit 16 c + j of gate[r * 4 + cg] (1 = pass); nullptr = none
+  unsigned long long* gate_out;    // the same words written for this layer's own output (forward chains: output > 0), or nullptr
   int Kp, Np, N, relu;
 };
-struct MlpChain {
-  int n_layers;
+struct MlpJob {
+  const float* X;       // (capacity, ldx) input rows, K0 valid columns
+  float* x_img;         // ACT(pad32(K0p)) row image of the input, or nullptr
+  float* Y;             // (capacity, ldy) output rows, n_out columns
+  const float* Wf;      // final layer on the CUDA cores: Y[r][o] = bias_f[o] + sum_k act[r][k] * Wf[o * ldwf + k]; nullptr = none
+  const float* bias_f;  //   (then the last MMA layer's output is Y itself)
+  const float* patch;   // input columns [patch_col, patch_col + patch_n) are read from patch[r * patch_ld + j] instead of X
+  int ldx, K0, K0p, ldy, n_out, ldwf, patch_col, patch_n, patch_ld, dep, n_layers;
   MlpLayer L[MLP_MAX_LAYERS];
 };
+struct MlpBatch {
+  int n_jobs;
+  int* done;            // per (job with dependents, tile) completion flags, zeroed by the launcher; may be nullptr
+  long long* trace;     // development (-DMC_TRACE builds): CTA 0 logs (clock64 << 8 | code) of its pipeline events, else nullptr
+  MlpJob job[MLP_MAX_JOBS];
+};
+#ifdef MC_TRACE
+#define MC_T(base, idx, code) do { if (batch.trace && blockIdx.x == 0 && lane == 0 && (idx) < 2040) batch.trace[(base) + (idx)++] = (clock64() << 8) | (code); } while (0)
+#else
+#define MC_T(base, idx, code) do { } while (0)
+#endif
+static long long* g_mc_trace = nullptr;
 
 struct __align__(16) MlpSmem {
   float A_lo[MLP_MAXW / 4 * MLP_ROWS * 4];                           // 96 KB  [K/4][128][4]
   float B[MLP_STAGES][2][MLP_SLICE_K / 4 * MLP_MAXW * 4];            // stages x {hi,lo} x [8 chunks][192][4] = 2 x 48 KB
-  float bias[MLP_MAX_LAYERS][MLP_MAXW];
+  float bias[MLP_MAX_JOBS][MLP_MAX_LAYERS][MLP_MAXW];
+  float Wf[MLP_MAX_JOBS][MC_MAX_FINAL][MLP_MAXW];
+  float bias_f[MLP_MAX_JOBS][MC_MAX_FINAL];
+  float red[4][MLP_ROWS][MC_MAX_FINAL];                               // final-layer partial sums of the 4 column groups
   uint64_t bar_full[MLP_STAGES];
   uint64_t bar_empty[MLP_STAGES];
+  uint64_t bar_chunk[3];
   uint64_t bar_acc;
+  uint64_t bar_pub;
   uint32_t tmem_base;
 };
 
-// 8 consecutive features [c0, c0+8) of this thread's row: hi -> TMEM (A operand), lo -> smem tile; optional HBM row image
-__device__ __forceinline__ void store_a8(MlpSmem& s, uint32_t tmem_a_lane, int row_in_tile, int c0, const float* v,
-                                         float* __restrict__ img, int F, int64_t row) {
-  float hi[8], lo[8];
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_rows16() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 512 row threads only
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                 "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+// TMEM load split into issue and wait so that the next chunk's accumulator columns fly while this chunk is processed;
+// the wait names the destination registers as in/out operands, which orders every later use of them behind it
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
+// chunk visiting order of an epilogue whose accumulator sits at column 0 (even) / 128 (odd): the chunk shared with the
+// next accumulator first
+__device__ __forceinline__ int mc_chunk(int odd, int i) { return odd ? i : (i == 0 ? 2 : i - 1); }
+
+// 16 consecutive features [c0, c0 + 16) of this thread's row become A-operand columns: hi -> TMEM, lo -> smem tile; the
+// raw values optionally go to the HBM row image (two aligned 32-byte pieces = one contiguous 64-byte run)
+__device__ __forceinline__ void mc_store_a16(MlpSmem& s, uint32_t tmem_a_lane, int rt, int c0, const float* v,
+                                             float* __restrict__ img, int F, int64_t row) {
+  // The A operand's hi part is x itself: tcgen05.mma.kind::tf32 reads the upper 19 bits of each 32-bit element, i.e. x
+  // truncated to TF32, and lo = x - trunc(x) is exact in fp32 (it is truncated to TF32 in turn: |error| <= 2^-21 |x|, the
+  // same order as the lo * lo term the 3-product split drops; tests/test_gpu_mlp.py holds the 5e-6 / 2e-5 bars).  Two
+  // instructions per element instead of five for the round-to-nearest split.
+#ifndef EXP_NO_TMEMST
+  tmem_st16(tmem_a_lane + c0, v);
+#endif
+  float lo[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { hi[j] = tf32_rn(v[j]); lo[j] = tf32_rn(v[j] - hi[j]); }
-  tmem_st8(tmem_a_lane + c0, hi);
+  for (int j = 0; j < 16; ++j) lo[j] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
+#ifndef EXP_NO_LO
 #pragma unroll
-  for (int q = 0; q < 2; ++q)
-    reinterpret_cast<float4*>(s.A_lo)[((c0 >> 2) + q) * MLP_ROWS + row_in_tile] = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-  if (img) {   // one aligned 32-byte piece, one 256-bit store
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(img + act_offset(row, c0, F)), "f"(v[0]),
-                 "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+  for (int q = 0; q < 4; ++q)
+    reinterpret_cast<float4*>(s.A_lo)[((c0 >> 2) + q) * MLP_ROWS + rt] = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+#endif
+#ifdef EXP_NO_IMG
+  img = nullptr;
+#endif
+  if (img) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(img + act_offset(row, c0 + 8 * h, F)),
+                   "f"(v[8 * h]), "f"(v[8 * h + 1]), "f"(v[8 * h + 2]), "f"(v[8 * h + 3]), "f"(v[8 * h + 4]), "f"(v[8 * h + 5]),
+                   "f"(v[8 * h + 6]), "f"(v[8 * h + 7]) : "memory");
   }
 }
 
-__global__ void __launch_bounds__(MLP_THREADS, 1)
-k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __restrict__ n_rows_dev, int capacity, MlpChain ch,
-            float* __restrict__ Y, int ldy, int n_out, float* __restrict__ x_img) {
+// this thread's pieces of an input row: piece u covers columns [16 cg + 64 u, +16), u = 0, 1 (K0p <= 128).  Piece 0 is
+// prefetched into registers one layer ahead; piece 1 (only the 79-wide rgbnet input has one, for cg = 0) is loaded when
+// it is staged -- holding it too costs 16 more live registers in the busiest loop, and 576 threads leave 96 per thread.
+struct McRowRegs { float v[16]; };
+
+__device__ __forceinline__ void mc_load_piece(const MlpJob& J, int64_t row, int n_rows, int c0, float* v, bool patch_ready) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  if (c0 >= J.K0p || row >= n_rows) return;
+  const float* src = J.X + row * J.ldx;
+  if ((J.ldx & 3) == 0 && c0 + 16 <= J.K0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + c0 + 4 * q));
+      v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < J.K0) v[j] = __ldg(src + c0 + j);
+  }
+  (void)patch_ready;
+}
+
+// columns produced by another job of this launch (after its completion flag was acquired): plain L2 loads, never the
+// read-only path
+__device__ __forceinline__ void mc_patch_piece(const MlpJob& J, int64_t row, int n_rows, int c0, float* v) {
+  if (!J.patch || row >= n_rows || c0 >= J.K0p) return;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int p = c0 + j - J.patch_col;
+    if (p >= 0 && p < J.patch_n) {
+      float x;
+      asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(x) : "l"(J.patch + row * J.patch_ld + p));
+      v[j] = x;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MC_THREADS, 1)
+k_mlp_chain(const __grid_constant__ MlpBatch batch, const int* __restrict__ n_rows_dev, int capacity) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   MlpSmem& s = *reinterpret_cast<MlpSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_rows = min(*n_rows_dev, capacity);
   const int n_tiles = (n_rows + MLP_ROWS - 1) / MLP_ROWS;
+  const int n_items = n_tiles * batch.n_jobs;      // item u: job u / n_tiles, tile u % n_tiles
 
   if (tid == 0) {
     for (int i = 0; i < MLP_STAGES; ++i) { mbar_init(&s.bar_full[i], 1); mbar_init(&s.bar_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) mbar_init(&s.bar_chunk[i], MC_ROW_WARPS);
     mbar_init(&s.bar_acc, 1);
+    mbar_init(&s.bar_pub, 4);
     fence_barrier_init();
   }
-  for (int l = 0; l < ch.n_layers; ++l)
-    for (int c = tid; c < MLP_MAXW; c += MLP_THREADS) s.bias[l][c] = (ch.L[l].bias && c < ch.L[l].N) ? ch.L[l].bias[c] : 0.f;
+  for (int j = 0; j < batch.n_jobs; ++j) {
+    const MlpJob& J = batch.job[j];
+    for (int l = 0; l < J.n_layers; ++l)
+      for (int c = tid; c < MLP_MAXW; c += MC_THREADS) s.bias[j][l][c] = (J.L[l].bias && c < J.L[l].N) ? J.L[l].bias[c] : 0.f;
+    if (J.Wf) {
+      const int Kf = J.L[J.n_layers - 1].N;
+      for (int i = tid; i < MC_MAX_FINAL * MLP_MAXW; i += MC_THREADS) {
+        const int o = i / MLP_MAXW, k = i % MLP_MAXW;
+        s.Wf[j][o][k] = (o < J.n_out && k < Kf) ? J.Wf[(int64_t)o * J.ldwf + k] : 0.f;
+      }
+      if (tid < MC_MAX_FINAL) s.bias_f[j][tid] = (J.bias_f && tid < J.n_out) ? J.bias_f[tid] : 0.f;
+    }
+  }
   if (warp == 0) tmem_alloc(&s.tmem_base, MLP_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
 
-  if (warp == MLP_ROW_THREADS / 32) {
-    // ===== weight producer: one thread streams every (tile, layer, slice) weight block, two slices ahead at most =====
+  if (warp == MC_ROW_WARPS) {
+    // ===== weight producer: every (item, layer, slice) weight block in consumption order, two slices ahead at most =====
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int l = 0; l < ch.n_layers; ++l) {
-          const MlpLayer& L = ch.L[l];
+      uint32_t it = 0, q = 0;
+      for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
+        const MlpJob& J = batch.job[u / n_tiles];
+        for (int l = 0; l < J.n_layers; ++l, ++q) {
+          const MlpLayer& L = J.L[l];
           const int NSL = (L.Kp + MLP_SLICE_K - 1) / MLP_SLICE_K;
-          for (int sl = 0; sl < NSL; ++sl, ++it) {
-            const int slot = it % MLP_STAGES;
-            const uint32_t use = it / MLP_STAGES;
-            if (use > 0) mbar_wait(&s.bar_empty[slot], (use - 1) & 1);
-            const int kchunks = min(MLP_SLICE_K, L.Kp - sl * MLP_SLICE_K) / 4;
-            const uint32_t bytes = (uint32_t)kchunks * L.Np * 16;
-            mbar_expect_tx(&s.bar_full[slot], 2 * bytes);
-            const int64_t off = (int64_t)sl * (MLP_SLICE_K / 4) * L.Np * 4;
-            bulk_g2s(&s.B[slot][0][0], L.W_hi + off, bytes, &s.bar_full[slot]);
-            bulk_g2s(&s.B[slot][1][0], L.W_lo + off, bytes, &s.bar_full[slot]);
+          const int prev_odd = (int)((q - 1) & 1);     // order of the chunks of the A operand = order the previous epilogue made them
+          for (int i = 0; i < 3; ++i) {
+            const int c = (l == 0) ? i : mc_chunk(prev_odd, i);
+            for (int sl = 2 * c; sl < 2 * c + 2 && sl < NSL; ++sl, ++it) {
+              const int slot = it % MLP_STAGES;
+              const uint32_t use = it / MLP_STAGES;
+              if (use > 0) mbar_wait(&s.bar_empty[slot], (use - 1) & 1);
+              const int kchunks = min(MLP_SLICE_K, L.Kp - sl * MLP_SLICE_K) / 4;
+              const uint32_t bytes = (uint32_t)kchunks * L.Np * 16;
+              mbar_expect_tx(&s.bar_full[slot], 2 * bytes);
+              const int64_t off = (int64_t)sl * (MLP_SLICE_K / 4) * L.Np * 4;
+              bulk_g2s(&s.B[slot][0][0], L.W_hi + off, bytes, &s.bar_full[slot]);
+              bulk_g2s(&s.B[slot][1][0], L.W_lo + off, bytes, &s.bar_full[slot]);
+            }
           }
         }
+      }
+    }
+  } else if (warp == MC_ROW_WARPS + 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t it = 0, q = 0;
+      int ti = 0; (void)ti;
+      for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
+        const MlpJob& J = batch.job[u / n_tiles];
+        for (int l = 0; l < J.n_layers; ++l, ++q) {
+          const MlpLayer& L = J.L[l];
+          const int KS = L.Kp / 8, Np = L.Np;
+          const int NSL = (L.Kp + MLP_SLICE_K - 1) / MLP_SLICE_K;
+          const uint32_t d_tm = tmem + ((q & 1) ? 128u : 0u);
+          const uint32_t idesc = make_idesc_tf32(MLP_ROWS, Np);
+          const int prev_odd = (int)((q - 1) & 1);
+          uint32_t first = 1;
+          for (int i = 0; i < 3; ++i) {
+            const int c = (l == 0) ? i : mc_chunk(prev_odd, i);
+            mbar_wait(&s.bar_chunk[c], q & 1);        // A columns [64 c, 64 c + 64) are in place (and the accumulator
+            tc_fence_after();                         // columns this layer shares with the previous one have been read)
+            MC_T(2048, ti, 40 + i);
+            for (int sl = 2 * c; sl < 2 * c + 2 && sl < NSL; ++sl, ++it) {
+              const int slot = it % MLP_STAGES;
+              MC_T(2048, ti, 60);
+              mbar_wait(&s.bar_full[slot], (it / MLP_STAGES) & 1);
+              tc_fence_after();
+              MC_T(2048, ti, 61);
+              const int k_steps = min(MLP_SLICE_K / 8, KS - sl * (MLP_SLICE_K / 8));
+              for (int kk = 0; kk < k_steps; ++kk) {
+                const int ks = sl * (MLP_SLICE_K / 8) + kk;
+                const uint32_t a_tm = tmem + MC_TMEM_A + ks * 8;
+                const uint64_t da_lo = make_desc(smem_u32(s.A_lo) + (uint32_t)(ks * 2) * MLP_ROWS * 16, MLP_ROWS * 16, 128);
+                const uint32_t b_off = (uint32_t)(kk * 2) * Np * 16;
+                const uint64_t db_hi = make_desc(smem_u32(&s.B[slot][0][0]) + b_off, Np * 16, 128);
+                const uint64_t db_lo = make_desc(smem_u32(&s.B[slot][1][0]) + b_off, Np * 16, 128);
+                umma_tf32_ts(d_tm, a_tm, db_hi, idesc, first ^ 1u);
+                umma_tf32_ts(d_tm, a_tm, db_lo, idesc, 1);
+                umma_tf32_ss(d_tm, da_lo, db_hi, idesc, 1);
+                first = 0;
+              }
+              umma_commit(&s.bar_empty[slot]);
+            }
+          }
+          umma_commit(&s.bar_acc);
+          MC_T(2048, ti, 50);
+        }
+      }
+    }
+  } else if (warp == MC_ROW_WARPS + 2) {
+    // ===== publisher: releases the completion flag of every tile whose output rows other jobs read.  The four warps
+    // that write a tile's output rows arrive on bar_pub (release.cta); the gpu-scope release store then happens here,
+    // so that no row warp sits behind a memory fence =====
+    if (lane == 0 && batch.done) {
+      uint32_t n_pub = 0;
+      for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
+        const int ji = u / n_tiles, tile = u % n_tiles;
+        if (ji + 1 >= batch.n_jobs) continue;
+        mbar_wait(&s.bar_pub, n_pub & 1);
+        ++n_pub;
+        int one = 1;
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(batch.done + ji * n_tiles + tile), "r"(one) : "memory");
+      }
     }
   } else {
-    // ===== row threads: stage inputs, (thread 0) issue MMAs, epilogues =====
-    const int rt = tid & (MLP_ROWS - 1);        // row within the tile == TMEM lane
-    const int half = tid >> 7;                  // 0: even column blocks, 1: odd column blocks
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp may only touch TMEM lanes 32*(warp%4)..
-    uint32_t acc_phase = 0, it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int row = tile * MLP_ROWS + rt;
-      {
-        const bool vec = (ldx % 4 == 0);
-        const float* src = X + (int64_t)row * ldx;
-        // this thread's share of the row, six 8-float pieces at a time: all loads are issued before the first use, so
-        // the tile pays one memory latency instead of one per piece
-        for (int cbase = half * 8; cbase < K0p; cbase += 16 * 6) {
-          float v[6][8];
+    // ===== row warps =====
+    const int rt = (warp & 3) * 32 + lane;       // row within the tile == TMEM lane
+    const int cg = warp >> 2;                    // column group
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t a_lane = lane_addr + MC_TMEM_A;
+    uint32_t q = 0;
+    int ti = 0; (void)ti;
+
+    // stage the input rows of item u as the A operand of its first layer and release the three chunk barriers
+    auto stage = [&](int u, McRowRegs& R, bool loaded) {
+      const int ji = u / n_tiles, tile = u % n_tiles;
+      const MlpJob& J = batch.job[ji];
+      const int64_t row = (int64_t)tile * MLP_ROWS + rt;
+      const int F = (J.K0p + 31) & ~31;
+      // every load first (piece 0 unless it was prefetched, piece 1 if the row is wider than 64, the patched columns), then
+      // the stores: one memory latency instead of three
+      const bool two = 16 * cg + 64 < J.K0p;          // warp-uniform
+      float w[16];
+      if (!loaded) mc_load_piece(J, row, n_rows, 16 * cg, R.v, false);
+      if (two) mc_load_piece(J, row, n_rows, 16 * cg + 64, w, false);
+      if (J.patch) {
+        if (J.dep >= 0 && batch.done) {
+          if (tid == 0) {
+            const int* flag = batch.done + J.dep * n_tiles + tile;
+            int f;
+            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory"); } while (f == 0);
+          }
+          bar_rows16();
+        }
+        mc_patch_piece(J, row, n_rows, 16 * cg, R.v);
+        if (two) mc_patch_piece(J, row, n_rows, 16 * cg + 64, w);
+      }
+      if (16 * cg < J.K0p) mc_store_a16(s, a_lane, rt, 16 * cg, R.v, J.x_img, F, row);
+      if (two) mc_store_a16(s, a_lane, rt, 16 * cg + 64, w, J.x_img, F, row);
+      tmem_st_wait();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive_cta(&s.bar_chunk[0]); mbar_arrive_cta(&s.bar_chunk[1]); mbar_arrive_cta(&s.bar_chunk[2]); }
+      if (warp == 0) MC_T(0, ti, 20);
+    };
+
+    McRowRegs R;
+    if ((int)blockIdx.x < n_items) stage(blockIdx.x, R, false);
+    for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
+      const int ji = u / n_tiles, tile = u % n_tiles;
+      const MlpJob& J = batch.job[ji];
+      const int64_t row = (int64_t)tile * MLP_ROWS + rt;
+      const bool valid = row < n_rows;
+      const int u_next = u + gridDim.x;
+      for (int l = 0; l < J.n_layers; ++l, ++q) {
+        const MlpLayer& L = J.L[l];
+        const int Np = L.Np;
+        const bool last = (l == J.n_layers - 1);
+        const int odd = (int)(q & 1);
+        const uint32_t d_lane = lane_addr + (odd ? 128u : 0u);
+        if (last && u_next < n_items) {
+          // prefetch the next item's input rows: the loads fly while this layer's MMAs finish
+          const MlpJob& Jn = batch.job[u_next / n_tiles];
+          const int64_t rown = (int64_t)(u_next % n_tiles) * MLP_ROWS + rt;
+          mc_load_piece(Jn, rown, n_rows, 16 * cg, R.v, false);
+        }
+        // ReLU gates of the dX chain: 16 bits per chunk visit, fetched while the MMAs run (the forward chain left them as a
+        // 192-bit bitmap per row: 24 bytes instead of the 768-byte activation row)
+        unsigned long long gbits = ~0ull, gout = 0;    // 16 bits per chunk c
+        if (L.gate && valid) gbits = __ldg(L.gate + row * 4 + cg);
+        if (warp == 0) MC_T(0, ti, 2);
+        mbar_wait(&s.bar_acc, q & 1);
+        tc_fence_after();
+        if (warp == 0) MC_T(0, ti, 1);
+        float acc[MC_MAX_FINAL];
 #pragma unroll
-          for (int u = 0; u < 6; ++u) {
-            const int c0 = cbase + 16 * u;
+        for (int o = 0; o < MC_MAX_FINAL; ++o) acc[o] = 0.f;
+        // per-layer constants out of the (dynamically indexed) kernel-parameter structs
+        float* const img = L.img;
+        unsigned long long* const gate_out = L.gate_out;
+        const bool has_gate = L.gate != nullptr, relu = L.relu != 0, has_bias = L.bias != nullptr, has_wf = J.Wf != nullptr;
+        const float validf = valid ? 1.f : 0.f;      // rows past n_rows: zero A rows give zero accumulators; only the bias must go
+        const float* const bias_s = s.bias[ji][l];
+        const int c00 = 64 * mc_chunk(odd, 0) + 16 * cg, c01 = 64 * mc_chunk(odd, 1) + 16 * cg, c02 = 64 * mc_chunk(odd, 2) + 16 * cg;
+        // Last layer of the item: the next item's first layer may start as soon as the accumulator columns it shares with
+        // this one ([128, 192): the first chunk in visiting order) have been READ -- so read them, stage the next item's
+        // input rows as the A operand (the MMA warp takes over from there), and only then do the arithmetic on them.
+        float vn[16];
+        const bool early = last && u_next < n_items;
+        bool pend = false;                           // a TMEM load into vn is in flight
+        if (c00 < Np) { tmem_ld16_issue(d_lane + c00, vn); pend = true; }
+        if (early) {
+          if (c00 < Np) tmem_ld16_wait(vn);
+          tc_fence_before();
+          stage(u_next, R, true);
+        }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
-            if (c0 < K0p && row < n_rows) {
-              if (vec && c0 + 8 <= K0) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(src + c0));
-                const float4 b2 = __ldg(reinterpret_cast<const float4*>(src + c0 + 4));
-                v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
-                v[u][4] = b2.x; v[u][5] = b2.y; v[u][6] = b2.z; v[u][7] = b2.w;
-              } else {
+        for (int i = 0; i < 3; ++i) {
+          const int c0 = (i == 0) ? c00 : (i == 1 ? c01 : c02);
+          if (c0 < Np) {                       // warp-uniform
+            float v[16];
+            if (warp == 0) MC_T(0, ti, 70);
+            if (!pend) tmem_ld16_issue(d_lane + c0, vn);
+            tmem_ld16_wait(vn);
+            pend = false;
+            if (warp == 0) MC_T(0, ti, 71);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (c0 + j < K0) v[u][j] = __ldg(src + c0 + j);
+            for (int j = 0; j < 16; ++j) v[j] = vn[j];
+            if (i < 2) {                       // next visit's accumulator columns fly while this visit is processed
+              const int c1 = (i == 0) ? c01 : c02;
+              if (c1 < Np) { tmem_ld16_issue(d_lane + c1, vn); pend = true; }
+            }
+#ifdef EXP_NO_BIAS
+            if (false) {
+#else
+            if (has_bias) {
+#endif
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * q4);
+                v[4 * q4] = fmaf(b4.x, validf, v[4 * q4]); v[4 * q4 + 1] = fmaf(b4.y, validf, v[4 * q4 + 1]);
+                v[4 * q4 + 2] = fmaf(b4.z, validf, v[4 * q4 + 2]); v[4 * q4 + 3] = fmaf(b4.w, validf, v[4 * q4 + 3]);
+              }
+            }
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (has_gate) {
+              const uint32_t gb = (uint32_t)(gbits >> (c0 >> 2 & 0x30));     // chunk c = c0 / 64 -> bits 16 c ..
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = (gb & (1u << j)) ? v[j] : 0.f;
+            }
+#ifdef EXP_NO_GATE
+            if (false) {
+#else
+            if (gate_out) {
+#endif
+              // bit j = (v[j] > 0); v >= 0 here (post-ReLU), so v > 0 <=> its bit pattern is non-zero: adding 0x7fffffff carries
+              // into bit 31 exactly then, and a funnel shift collects that bit
+              uint32_t gb = 0;
+#pragma unroll
+              for (int j = 15; j >= 0; --j) gb = __funnelshift_l(__float_as_uint(v[j]) + 0x7fffffffu, gb, 1);
+              gout |= (unsigned long long)gb << (c0 >> 2 & 0x30);
+            }
+            if (warp == 0) MC_T(0, ti, 72);
+            if (!last) {
+              mc_store_a16(s, a_lane, rt, c0, v, img, Np, row);
+              if (warp == 0) MC_T(0, ti, 73);
+            } else {
+              if (img) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(img + act_offset(row, c0 + 8 * h, Np)),
+                               "f"(v[8 * h]), "f"(v[8 * h + 1]), "f"(v[8 * h + 2]), "f"(v[8 * h + 3]), "f"(v[8 * h + 4]), "f"(v[8 * h + 5]),
+                               "f"(v[8 * h + 6]), "f"(v[8 * h + 7]) : "memory");
+              }
+              if (has_wf) {
+#pragma unroll
+                for (int o = 0; o < MC_MAX_FINAL; ++o) {
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(&s.Wf[ji][o][c0 + 4 * q4]);
+                    acc[o] = fmaf(v[4 * q4], w4.x, acc[o]); acc[o] = fmaf(v[4 * q4 + 1], w4.y, acc[o]);
+                    acc[o] = fmaf(v[4 * q4 + 2], w4.z, acc[o]); acc[o] = fmaf(v[4 * q4 + 3], w4.w, acc[o]);
+                  }
+                }
+              } else if (valid) {
+                float* dst = J.Y + row * J.ldy + c0;
+                if ((J.ldy & 3) == 0 && c0 + 16 <= J.n_out) {
+#pragma unroll
+                  for (int qv = 0; qv < 4; ++qv)
+                    reinterpret_cast<float4*>(dst)[qv] = make_float4(v[4 * qv], v[4 * qv + 1], v[4 * qv + 2], v[4 * qv + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (c0 + j < J.n_out) dst[j] = v[j];
+                }
               }
             }
           }
-#pragma unroll
-          for (int u = 0; u < 6; ++u) {
-            const int c0 = cbase + 16 * u;
-            if (c0 < K0p) store_a8(s, lane_addr + MLP_TMEM_A, rt, c0, v[u], x_img, (K0p + 31) & ~31, row);
+          if (!last) {
+            // this chunk of the next layer's A operand is complete (and this chunk of the accumulator has been read)
+#ifndef EXP_NO_FENCE
+            tmem_st_wait();
+            if (warp == 0) MC_T(0, ti, 74);
+            fence_proxy_async();
+#endif
+            tc_fence_before();
+            if (warp == 0) MC_T(0, ti, 75);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&s.bar_chunk[(i == 0) ? mc_chunk(odd, 0) : (i == 1 ? mc_chunk(odd, 1) : mc_chunk(odd, 2))]);
+            if (warp == 0) MC_T(0, ti, 10 + i);
           }
         }
-        tmem_st_wait();
-      }
-      for (int l = 0; l < ch.n_layers; ++l) {
-        const MlpLayer& L = ch.L[l];
-        const int KS = L.Kp / 8;
-        const int NSL = (L.Kp + MLP_SLICE_K - 1) / MLP_SLICE_K;
-        const int Np = L.Np;
-        fence_proxy_async();   // this thread's A_lo stores -> async proxy
-        tc_fence_before();     // this thread's tcgen05.st of the A (hi) operand
-        bar_rows();
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t idesc = make_idesc_tf32(MLP_ROWS, Np);
-          for (int sl = 0; sl < NSL; ++sl) {
-            const uint32_t cur = it + sl;
-            const int slot = cur % MLP_STAGES;
-            mbar_wait(&s.bar_full[slot], (cur / MLP_STAGES) & 1);
-            tc_fence_after();
-            const int k_steps = min(MLP_SLICE_K / 8, KS - sl * (MLP_SLICE_K / 8));
-            for (int kk = 0; kk < k_steps; ++kk) {
-              const int ks = sl * (MLP_SLICE_K / 8) + kk;
-              const uint32_t a_tm = tmem + MLP_TMEM_A + ks * 8;
-              const uint64_t da_lo = make_desc(smem_u32(s.A_lo) + (uint32_t)(ks * 2) * MLP_ROWS * 16, MLP_ROWS * 16, 128);
-              const uint32_t b_off = (uint32_t)(kk * 2) * Np * 16;
-              const uint64_t db_hi = make_desc(smem_u32(&s.B[slot][0][0]) + b_off, Np * 16, 128);
-              const uint64_t db_lo = make_desc(smem_u32(&s.B[slot][1][0]) + b_off, Np * 16, 128);
-              umma_tf32_ts(tmem, a_tm, db_hi, idesc, ks > 0);
-              umma_tf32_ts(tmem, a_tm, db_lo, idesc, 1);
-              umma_tf32_ss(tmem, da_lo, db_hi, idesc, 1);
+#ifndef EXP_NO_GSTORE
+        if (gate_out) gate_out[row * 4 + cg] = gout;      // one 8-byte store per thread and layer
+#endif
+        if (last && J.Wf) {
+          // CUDA-core final layer: the four column groups of a row meet in shared memory
+#pragma unroll
+          for (int o = 0; o < MC_MAX_FINAL; ++o) s.red[cg][rt][o] = acc[o];
+          bar_rows16();
+          if (cg == 0) {
+            if (valid) {
+              for (int o = 0; o < J.n_out; ++o)
+                J.Y[row * J.ldy + o] = ((s.red[0][rt][o] + s.red[1][rt][o]) + (s.red[2][rt][o] + s.red[3][rt][o])) + s.bias_f[ji][o];
             }
-            umma_commit(&s.bar_empty[slot]);
+            if (batch.done && ji + 1 < batch.n_jobs) {   // this tile's output rows are written: hand the flag to the publisher
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cta(&s.bar_pub);
+            }
           }
-          umma_commit(&s.bar_acc);
+          bar_rows16();     // s.red is reused by the next item
         }
-        it += NSL;
-        // ---- epilogue: accumulator -> registers -> (+bias, ReLU / mask) -> next A operand (+ HBM images)
-        mbar_wait(&s.bar_acc, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        const bool last = (l == ch.n_layers - 1);
-        if (!last) {
-          for (int c0 = half * 32; c0 < Np; c0 += 64) {
-            float v[32], mk[32];
-            const bool gate = L.mask && row < n_rows;
-            if (gate) {
-              // ReLU gates of the 32 features [c0, c0 + 32) of this row: one 128-byte line of the forward row image
-              // (32-byte pieces permuted), four 256-bit loads issued ahead of the TMEM load they are applied to
-              const float* line = L.mask + act_offset(row, c0, Np) - ((((c0 & 31) >> 3) ^ (row & 3)) << 3);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                             : "=f"(mk[8 * q]), "=f"(mk[8 * q + 1]), "=f"(mk[8 * q + 2]), "=f"(mk[8 * q + 3]), "=f"(mk[8 * q + 4]),
-                               "=f"(mk[8 * q + 5]), "=f"(mk[8 * q + 6]), "=f"(mk[8 * q + 7])
-                             : "l"(line + ((q ^ (row & 3)) << 3)));
-            }
-            tmem_ld32(lane_addr + c0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float y = v[j] + s.bias[l][c0 + j];
-              if (L.relu) y = fmaxf(y, 0.f);
-              v[j] = y;
-            }
-            if (gate) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (!(mk[j] > 0.f)) v[j] = 0.f;
-            }
-            if (row >= n_rows) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              store_a8(s, lane_addr + MLP_TMEM_A, rt, c0 + 8 * q, v + 8 * q, L.img, Np, row);
-          }
-          tmem_st_wait();
-        } else {
-          for (int c0 = half * 16; c0 < Np; c0 += 32) {
-            float v[16];
-            tmem_ld16(lane_addr + c0, v);
-            if (row < n_rows) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < n_out) Y[(int64_t)row * ldy + c0 + j] = v[j] + s.bias[l][c0 + j];
-            }
-          }
-          tc_fence_before();
-          bar_rows();   // every TMEM read of this tile done before the next tile's first MMA overwrites the accumulator
-        }
+        if (last && warp == 0) MC_T(0, ti, 30);
       }
     }
   }
@@ -462,46 +778,113 @@ k_mlp_chain(const float* __restrict__ X, int ldx, int K0, int K0p, const int* __
   if (warp == 0) tmem_dealloc(tmem, MLP_TMEM_COLS);
 }
 
-// Layers are described by two packed HOST arrays so the C ABI stays plain:
-//   ptrs_host[l*5 + {0..4}] = device addresses of W_hi, W_lo (CH(Np) images from vx_mlp_prep), bias, row image out,
-//                             mask row image (0 = none)
-//   dims_host[l*4 + {0..3}] = Kp, Np, N, relu
-// X (capacity, ldx) with K0 valid columns; Y (capacity, ldy) receives the first n_out columns of the last layer;
-// x_img: optional ACT(K0p) row image of the input.  Every row image needs 128 * ceil(capacity / 128) rows.
-VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, int capacity, int n_layers,
-                        const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* x_img,
-                        cudaStream_t st) {
-  VX_REQUIRE(n_layers >= 1 && n_layers <= MLP_MAX_LAYERS, "vx_mlp_chain", "1..4 layers");
-  VX_REQUIRE(n_rows_dev != nullptr, "vx_mlp_chain", "n_rows_dev required");
-  MlpChain ch;
-  ch.n_layers = n_layers;
-  for (int l = 0; l < n_layers; ++l) {
-    MlpLayer& L = ch.L[l];
-    L.W_hi = reinterpret_cast<const float*>(ptrs_host[l * 5 + 0]);
-    L.W_lo = reinterpret_cast<const float*>(ptrs_host[l * 5 + 1]);
-    L.bias = reinterpret_cast<const float*>(ptrs_host[l * 5 + 2]);
-    L.img = reinterpret_cast<float*>(ptrs_host[l * 5 + 3]);
-    L.mask = reinterpret_cast<const float*>(ptrs_host[l * 5 + 4]);
-    L.Kp = dims_host[l * 4 + 0]; L.Np = dims_host[l * 4 + 1]; L.N = dims_host[l * 4 + 2]; L.relu = dims_host[l * 4 + 3];
-    VX_REQUIRE(L.Kp % 8 == 0 && L.Kp >= 8 && L.Kp <= MLP_MAXW && L.Np % 16 == 0 && L.Np >= 16 && L.Np <= MLP_MAXW,
-               "vx_mlp_chain", "layer shape");
-    if (l + 1 < n_layers)
-      VX_REQUIRE(L.Np % 32 == 0 && L.Np == dims_host[(l + 1) * 4 + 0], "vx_mlp_chain", "hidden widths must chain and be multiples of 32");
+// Jobs are described by packed HOST arrays so the C ABI stays plain.  Per job j:
+//   ptrs_host[j*30 + {0..5}]  = X, x_img, Y, Wf, bias_f, patch                       (device addresses, 0 = none)
+//   ptrs_host[j*30 + 6 + l*6 + {0..5}] = layer l: W_hi, W_lo (CH(Np) images from vx_mlp_prep), bias, row image out,
+//                                        gate bitmap in, gate bitmap out
+//   dims_host[j*26 + {0..9}]  = ldx, K0, n_layers, ldy, n_out, ldwf, patch_col, patch_n, patch_ld, dep (-1 = none)
+//   dims_host[j*26 + 10 + l*4 + {0..3}] = layer l: Kp, Np, N, relu
+// done_flags: device int array of n_jobs * ceil(capacity / 128) entries (needed when a job has dep >= 0), zeroed here.
+// Every row image needs 128 * ceil(capacity / 128) rows.
+#define MC_JOB_STRIDE 26      // dims per job
+#define MC_PTR_STRIDE 30      // pointers per job
+VX_API int vx_mlp_chain_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
+                              int* done_flags, cudaStream_t st) {
+  VX_REQUIRE(n_jobs >= 1 && n_jobs <= MLP_MAX_JOBS, "vx_mlp_chain_batch", "1..2 jobs");
+  VX_REQUIRE(n_rows_dev != nullptr, "vx_mlp_chain_batch", "n_rows_dev required");
+  MlpBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n_jobs = n_jobs;
+  b.trace = g_mc_trace;
+  bool any_dep = false;
+  for (int j = 0; j < n_jobs; ++j) {
+    MlpJob& J = b.job[j];
+    const int64_t* P = ptrs_host + j * MC_PTR_STRIDE;
+    const int* D = dims_host + j * MC_JOB_STRIDE;
+    J.X = reinterpret_cast<const float*>(P[0]);
+    J.x_img = reinterpret_cast<float*>(P[1]);
+    J.Y = reinterpret_cast<float*>(P[2]);
+    J.Wf = reinterpret_cast<const float*>(P[3]);
+    J.bias_f = reinterpret_cast<const float*>(P[4]);
+    J.patch = reinterpret_cast<const float*>(P[5]);
+    J.ldx = D[0]; J.K0 = D[1]; J.n_layers = D[2]; J.ldy = D[3]; J.n_out = D[4]; J.ldwf = D[5];
+    J.patch_col = D[6]; J.patch_n = D[7]; J.patch_ld = D[8]; J.dep = D[9];
+    VX_REQUIRE(J.n_layers >= 1 && J.n_layers <= MLP_MAX_LAYERS, "vx_mlp_chain_batch", "1..4 MMA layers");
+    VX_REQUIRE(J.X && J.Y, "vx_mlp_chain_batch", "X / Y required");
+    for (int l = 0; l < J.n_layers; ++l) {
+      MlpLayer& L = J.L[l];
+      L.W_hi = reinterpret_cast<const float*>(P[6 + l * 6 + 0]);
+      L.W_lo = reinterpret_cast<const float*>(P[6 + l * 6 + 1]);
+      L.bias = reinterpret_cast<const float*>(P[6 + l * 6 + 2]);
+      L.img = reinterpret_cast<float*>(P[6 + l * 6 + 3]);
+      L.gate = reinterpret_cast<const unsigned long long*>(P[6 + l * 6 + 4]);
+      L.gate_out = reinterpret_cast<unsigned long long*>(P[6 + l * 6 + 5]);
+      L.Kp = D[10 + l * 4 + 0]; L.Np = D[10 + l * 4 + 1]; L.N = D[10 + l * 4 + 2]; L.relu = D[10 + l * 4 + 3];
+      VX_REQUIRE(L.W_hi && L.W_lo, "vx_mlp_chain_batch", "weight images required");
+      VX_REQUIRE(L.Kp % 8 == 0 && L.Kp >= 8 && L.Kp <= MLP_MAXW && L.Np % 16 == 0 && L.Np >= 16 && L.Np <= MLP_MAXW,
+                 "vx_mlp_chain_batch", "layer shape");
+      if (l + 1 < J.n_layers)
+        VX_REQUIRE(L.Np % 32 == 0 && L.Np == D[10 + (l + 1) * 4 + 0], "vx_mlp_chain_batch", "hidden widths must chain and be multiples of 32");
+      VX_REQUIRE(!L.img || L.Np % 32 == 0, "vx_mlp_chain_batch", "a row image needs a width that is a multiple of 32");
+      VX_REQUIRE(!(L.gate || L.gate_out) || L.Np % 16 == 0, "vx_mlp_chain_batch", "gate words need a width that is a multiple of 16");
+    }
+    J.K0p = J.L[0].Kp;
+    const MlpLayer& LL = J.L[J.n_layers - 1];
+    VX_REQUIRE(J.K0 <= J.K0p && J.K0 <= J.ldx && J.K0p <= 128, "vx_mlp_chain_batch", "K0");
+    if (J.Wf) VX_REQUIRE(J.n_out >= 1 && J.n_out <= MC_MAX_FINAL && J.ldwf >= LL.N, "vx_mlp_chain_batch", "final layer: 1..4 outputs");
+    else VX_REQUIRE(J.n_out <= LL.Np, "vx_mlp_chain_batch", "n_out");
+    if (J.patch) {
+      VX_REQUIRE(J.patch_n >= 1 && J.patch_col >= 0 && J.patch_col + J.patch_n <= J.K0 && J.dep < j, "vx_mlp_chain_batch", "patch");
+      if (J.dep >= 0) {
+        any_dep = true;
+        VX_REQUIRE(b.job[J.dep].Wf != nullptr && J.dep + 1 < n_jobs, "vx_mlp_chain_batch", "a job others patch from must end in the CUDA-core final layer");
+      }
+    }
   }
-  const int K0p = dims_host[0];
-  VX_REQUIRE(K0 <= K0p && K0 <= ldx && n_out <= dims_host[(n_layers - 1) * 4 + 1], "vx_mlp_chain", "K0 / n_out");
   const int tiles_cap = (capacity + MLP_ROWS - 1) / MLP_ROWS;
+  if (tiles_cap <= 0) return 0;
+  if (any_dep) {
+    VX_REQUIRE(done_flags != nullptr, "vx_mlp_chain_batch", "done_flags required when a job patches its input from another");
+    b.done = done_flags;
+    cudaError_t e = cudaMemsetAsync(done_flags, 0, sizeof(int) * (size_t)n_jobs * tiles_cap, st);
+    if (e != cudaSuccess) { vx_set_error("vx_mlp_chain_batch", cudaGetErrorString(e)); return (int)e; }
+  }
   static bool attr_set = false;
   const int smem = (int)sizeof(MlpSmem) + 1024;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_mlp_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { vx_set_error("vx_mlp_chain", cudaGetErrorString(e)); return (int)e; }
+    if (e != cudaSuccess) { vx_set_error("vx_mlp_chain_batch", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  if (tiles_cap <= 0) return 0;
-  const int blocks = min(tiles_cap, vx_num_sms());
-  k_mlp_chain<<<blocks, MLP_THREADS, smem, st>>>(X, ldx, K0, K0p, n_rows_dev, capacity, ch, Y, ldy, n_out, x_img);
-  return vx_check_launch("vx_mlp_chain");
+  const int blocks = min(tiles_cap * n_jobs, vx_num_sms());
+  k_mlp_chain<<<blocks, MC_THREADS, smem, st>>>(b, n_rows_dev, capacity);
+  return vx_check_launch("vx_mlp_chain_batch");
+}
+
+// development: device buffer of 4096 int64 that CTA 0 of the next chain launches logs its pipeline events into (only in
+// -DMC_TRACE builds; nullptr switches it off)
+VX_API int vx_mlp_trace_set(int64_t* buf) {
+  g_mc_trace = reinterpret_cast<long long*>(buf);
+  return 0;
+}
+
+// One chain, every layer on the tensor cores (tests, generic callers): layer l described by
+//   ptrs_host[l*5 + {0..4}] = W_hi, W_lo, bias, row image out, gate bitmap in;  dims_host[l*4 + {0..3}] = Kp, Np, N, relu
+VX_API int vx_mlp_chain(const float* X, int ldx, int K0, const int* n_rows_dev, int capacity, int n_layers,
+                        const int64_t* ptrs_host, const int* dims_host, float* Y, int ldy, int n_out, float* x_img,
+                        cudaStream_t st) {
+  VX_REQUIRE(n_layers >= 1 && n_layers <= MLP_MAX_LAYERS, "vx_mlp_chain", "1..4 layers");
+  int64_t P[MC_PTR_STRIDE];
+  int D[MC_JOB_STRIDE];
+  memset(P, 0, sizeof(P));
+  memset(D, 0, sizeof(D));
+  P[0] = (int64_t)(uintptr_t)X; P[1] = (int64_t)(uintptr_t)x_img; P[2] = (int64_t)(uintptr_t)Y;
+  D[0] = ldx; D[1] = K0; D[2] = n_layers; D[3] = ldy; D[4] = n_out; D[9] = -1;
+  for (int l = 0; l < n_layers; ++l) {
+    for (int k = 0; k < 5; ++k) P[6 + l * 6 + k] = ptrs_host[l * 5 + k];
+    for (int k = 0; k < 4; ++k) D[10 + l * 4 + k] = dims_host[l * 4 + k];
+  }
+  return vx_mlp_chain_batch(1, P, D, n_rows_dev, capacity, nullptr, st);
 }
 
 // ---------------------------------------------------------------------------------------------

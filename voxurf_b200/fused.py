@@ -32,7 +32,7 @@ import torch
 import torch.nn.functional as F
 
 from ._lib import call
-from .mlp import FlatMLP, prepare_chains, run_dw_batch
+from .mlp import FlatMLP, prepare_chains, run_chain_jobs, run_dw_batch
 from .optim import _storage
 
 
@@ -105,6 +105,7 @@ class FusedFineStep:
         # MLPs on flat parameter / gradient storage (one Adam launch per network)
         self.mlp1 = FlatMLP(m.rgbnet, self.ld1, self.D1, tensor_core)
         self.mlp2 = FlatMLP(m.k_rgbnet, self.ld2, self.D2, tensor_core)
+        self.mlp1.alloc(self.cap4), self.mlp2.alloc(self.cap4)
         # persistent gradient buffers for the grids (zeroed by the Adam kernel itself)
         self.sdf_grad = torch.zeros_like(m.sdf.grid)
         self.k0_grad = torch.zeros_like(m.k0.grid, memory_format=torch.preserve_format)
@@ -208,9 +209,17 @@ class FusedFineStep:
              self.P, self.Vp, self.P2, self.V2, self.disp, self.L, self.ld1, self.ld2, self.X1, self.X2)
         if self.tensor_core:   # all weight images of both networks (forward + transposed dX chains) in one launch
             prepare_chains(self.mlp1.chains(train) + self.mlp2.chains(train))
-        self.mlp1.forward(self.X1, self.logit1, keep_activations=train, n_rows_dev=n4 if self.tensor_core else None, prepared=True)
-        call('vx_fused_fill_logit_cols', self.logit1, 3, n4, self.cap4, self.col_logit, self.ld2, self.X2)
-        self.mlp2.forward(self.X2, self.k_out, keep_activations=train, n_rows_dev=n4 if self.tensor_core else None, prepared=True)
+        if self.tensor_core:
+            # both forward chains in one launch: rgbnet's tiles first, k_rgbnet's tiles take their rgb_logit.detach() input
+            # columns (lib/voxurf_fine.py:741-751) straight from rgbnet's output rows behind a per-tile flag
+            self.mlp1._n = self.mlp2._n = n4
+            run_chain_jobs([self.mlp1.forward_job(self.X1, self.logit1, train),
+                            self.mlp2.forward_job(self.X2, self.k_out, train, patch=(self.logit1, self.col_logit, 3, 0))],
+                           n4, self.cap4, self.mlp1.done)
+        else:
+            self.mlp1.forward(self.X1, self.logit1, keep_activations=train, n_rows_dev=None, prepared=True)
+            call('vx_fused_fill_logit_cols', self.logit1, 3, n4, self.cap4, self.col_logit, self.ld2, self.X2)
+            self.mlp2.forward(self.X2, self.k_out, keep_activations=train, n_rows_dev=None, prepared=True)
         return s_val, n2, n4
 
     def _loss_cfg(self):
@@ -250,11 +259,11 @@ class FusedFineStep:
              self.rgb_marched, self.rgb_marched0, self.d_logit1, self.d_kout, self.d_w, self.d_last, self.loss_ray)
         call('vx_sum_f32', self.loss_ray, N, self.loss)
         sparse_dp = self.world > 1 and self.sparse_k0_exchange
-        if self.tensor_core:   # both dX chains, then the 8 weight-gradient GEMMs of both networks in one launch
-            self.mlp2.backward(self.d_kout, self.dX2, defer_dw=True)
+        if self.tensor_core:   # both dX chains in one launch, then the 8 weight-gradient GEMMs of both networks in one launch
+            run_chain_jobs([self.mlp2.backward_job(self.d_kout, self.dX2), self.mlp1.backward_job(self.d_logit1, self.dX1)],
+                           n4, self.cap4, None)
             if sparse_dp:      # dL/dk0 of this rank's rows is final here: its all-gather runs under the rest of the backward
                 self._start_k0_exchange(n4)
-            self.mlp1.backward(self.d_logit1, self.dX1, defer_dw=True)
             # The weight-gradient launch (one persistent CTA per SM, tensor / latency bound, ~220 us) only feeds the
             # optimizer; the scatter kernels below (atomics / ALU bound, independent inputs) run beside it on the main
             # stream.  Fork here, join at the end of this method; inside a CUDA-graph capture the side stream joins
@@ -571,23 +580,29 @@ class FusedFineStep:
         if hasattr(self.m, '_s_val_host'):
             self.m.s_val.data.fill_(self.m._s_val_host)
 
+    def _overflow_error(self, n):
+        return RuntimeError(f'FusedFineStep: {n} MLP rows exceeded row_capacity={self.cap4} in an earlier step (rows were '
+                            'dropped: loss and gradients of that step are wrong); call calibrate() with a representative '
+                            'batch at the current global_step, or raise row_capacity')
+
     def poll_overflow(self, force=False):
         """Raise if an earlier step dropped MLP rows (M4 > row_capacity: its loss and gradients were wrong).  Without
         `force` this never waits for the GPU: see overflow_check_every.  force=True syncs (end of training / of a view)."""
-        if self._ovf_pending and (force or self._ovf_event.query()):
-            self._ovf_event.synchronize()
+        if force:
+            self._ovf_pending = False
+            n = int(self.overflow.item())
+            if n > 0:
+                raise self._overflow_error(n)
+            return
+        if self._ovf_pending and self._ovf_event.query():
             self._ovf_pending = False
             if int(self._ovf_host[0]) > 0:
-                raise RuntimeError(f'FusedFineStep: {int(self._ovf_host[0])} MLP rows exceeded row_capacity={self.cap4} in an earlier '
-                                   'step (rows were dropped: loss and gradients of that step are wrong); call calibrate() '
-                                   'with a representative batch at the current global_step, or raise row_capacity')
+                raise self._overflow_error(int(self._ovf_host[0]))
         self._ovf_calls += 1
-        if not self._ovf_pending and (force or self._ovf_calls % self.overflow_check_every == 0):
+        if not self._ovf_pending and self._ovf_calls % self.overflow_check_every == 0:
             self._ovf_host.copy_(self.overflow, non_blocking=True)
             self._ovf_event.record()
             self._ovf_pending = True
-            if force:
-                self.poll_overflow(force=True)
 
     def step(self, rays_o, rays_d, viewdirs, target, global_step, grad_sync=None):
         """One training iteration (run.py:600-659).  grad_sync: optional callable run between backward and TV/Adam.

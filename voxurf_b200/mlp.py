@@ -51,7 +51,10 @@ class FlatMLP:
         self.tc_fwd = self.tc_bwd = None
         if tensor_core:
             n = len(self.W)
-            self.tc_fwd = TensorCoreChain([dict(W=self.W[i], bias=self.b[i], relu=(i + 1 < n)) for i in range(n)])
+            # forward chain: the hidden layers on the tensor cores, the tiny last layer (N = 3) in exact fp32 on the CUDA
+            # cores inside the last hidden layer's epilogue (csrc/mlp_tc.cu)
+            self.tc_fwd = TensorCoreChain([dict(W=self.W[i], bias=self.b[i], relu=True) for i in range(n - 1)],
+                                          final=(self.W[-1], self.b[-1]))
             # dX chain: dH_{l-1} = (dH_l W_l) * (H_{l-1} > 0), i.e. the same kernel on the transposed weights, last layer first
             self.tc_bwd = TensorCoreChain([dict(W=self.W[i], bias=None, relu=False) for i in range(n - 1, -1, -1)], transpose=True)
 
@@ -67,9 +70,12 @@ class FlatMLP:
             assert all(l.out_features % 32 == 0 for l in self.linears[:-1]), 'hidden widths must be multiples of 32'
             self.F_in = _pad(self.tc_fwd.Kp[0], 32)
             self.F_out = _pad(self.tc_bwd.Kp[0], 32)
+            self.done = torch.zeros(2 * (self.R // 128), dtype=torch.int32, device=dev)   # vx_mlp_chain_batch tile flags
             self.X_img = img(self.F_in)
             self.H_img = [img(l.out_features) for l in self.linears[:-1]]
             self.dH_img = [img(l.out_features) for l in self.linears[:-1]]
+            # ReLU gates of the hidden activations, one bit per (row, feature): written by the forward chain, read by the dX chain
+            self.G_img = [torch.zeros(self.R * 4, dtype=torch.int64, device=dev) for l in self.linears[:-1]]
             self.dY_img = img(self.F_out)
             self.H = self.dH = []
             return
@@ -90,10 +96,7 @@ class FlatMLP:
             self._n = n_rows_dev
             if not prepared:   # the optimizer changed the weights since the last step
                 prepare_chains(self.chains(keep_activations))
-            if keep_activations:
-                self.tc_fwd.run(X, self.ld_in, n_rows_dev, out, out.shape[1], imgs=self.H_img, x_img=self.X_img)
-            else:
-                self.tc_fwd.run(X, self.ld_in, n_rows_dev, out, out.shape[1])
+            run_chain_jobs([self.forward_job(X, out, keep_activations)], n_rows_dev, X.shape[0], None)
             return out
         h = X
         for i in range(len(self.linears) - 1):
@@ -103,6 +106,21 @@ class FlatMLP:
         torch.addmm(self.b[-1], h, self.W[-1].t(), out=out)
         self._X = X
         return out
+
+    def forward_job(self, X, out, keep_activations=True, patch=None):
+        """Job descriptor of this network's forward chain for run_chain_jobs.  patch = (tensor (cap, ld), col0, n, dep):
+        input columns [col0, col0 + n) are read from `tensor` (written by job `dep` of the same launch) instead of X."""
+        self._X = X
+        if keep_activations:
+            return self.tc_fwd.job(X, self.ld_in, out, out.shape[1], imgs=self.H_img, x_img=self.X_img, patch=patch, gates_out=self.G_img)
+        return self.tc_fwd.job(X, self.ld_in, out, out.shape[1], patch=patch)
+
+    def backward_job(self, d_out, dX):
+        """Job descriptor of the dX chain: chain layer j <-> network layer n-1-j, ReLU gates from the forward row images."""
+        n = len(self.linears)
+        rev = list(range(n - 2, -1, -1))
+        return self.tc_bwd.job(d_out, d_out.shape[1], dX, dX.shape[1], imgs=[self.dH_img[i] for i in rev],
+                               masks=[self.G_img[i] for i in rev], x_img=self.dY_img)
 
     def dw_jobs(self):
         """(ptrs, dims) of this network's weight-gradient GEMMs for vx_mlp_dw_batch: dW_i = dY_i^T H_{i-1}, db_i = dY_i^T 1
@@ -123,9 +141,7 @@ class FlatMLP:
         n = len(self.linears)
         if self.tensor_core:
             # dX chain (one launch): chain layer j <-> network layer n-1-j; hidden gradients land feature-major in dHT
-            rev = list(range(n - 2, -1, -1))
-            self.tc_bwd.run(d_out, d_out.shape[1], self._n, dX, dX.shape[1], imgs=[self.dH_img[i] for i in rev],
-                            masks=[self.H_img[i] for i in rev], x_img=self.dY_img)
+            run_chain_jobs([self.backward_job(d_out, dX)], self._n, d_out.shape[0], None)
             if not defer_dw:
                 run_dw_batch([self])
             return dX
@@ -163,6 +179,26 @@ def run_dw_batch(mlps):
         call('vx_mlp_dw_batch', n, ptrs[4 * j:4 * (j + n)], dims[5 * j:5 * (j + n)], mlps[0]._n, mlps[0].cap)
 
 
+JOB_STRIDE, PTR_STRIDE = 26, 30   # csrc/mlp_tc.cu MC_JOB_STRIDE (dims per job), MC_PTR_STRIDE (pointers per job)
+
+
+def run_chain_jobs(jobs, n_rows_dev, capacity, done_flags):
+    """Up to two layer chains (e.g. both networks' forward chains, or both dX chains) in ONE vx_mlp_chain_batch launch:
+    their 128-row tiles share the SMs, so 2 x 353 tiles take 4.8 waves instead of 2 x 3."""
+    from ._lib import call
+    ptrs, dims = [], []
+    for p, d in jobs:
+        ptrs += p; dims += d
+    timed = CHAIN_TIMINGS is not None
+    if timed:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    call('vx_mlp_chain_batch', len(jobs), ptrs, dims, n_rows_dev, capacity, done_flags)
+    if timed:
+        ev[1].record()
+        CHAIN_TIMINGS.append((ev, sum(d.flops for _, d in jobs)))
+
+
 def prepare_chains(chains):
     """(Re)write the hi/lo TF32 weight images of several chains with one launch per 16 layers (vx_mlp_prep_batch)."""
     from ._lib import call
@@ -175,17 +211,27 @@ def prepare_chains(chains):
         call('vx_mlp_prep_batch', n, ptrs[3 * j:3 * (j + n)], dims[6 * j:6 * (j + n)])
 
 
+class _Dims(list):
+    """dims list of a chain job that also remembers the chain's flops per row (bench.py roofline bookkeeping)"""
+
+    def __init__(self, v, flops):
+        super().__init__(v)
+        self.flops = flops
+
+
 class TensorCoreChain:
     """A chain of up to 4 dense layers executed by one fused tcgen05 kernel launch (vx_mlp_chain).
 
     layers: list of dicts {W: (N,K) tensor view (row stride ldw), bias: (N,) or None, relu: bool}.  `prepare()` must
     be called whenever the weights changed (it writes the hi/lo TF32 split images, zero-padded)."""
 
-    def __init__(self, layers, transpose=False):
+    def __init__(self, layers, transpose=False, final=None):
+        """final = (W (n_out, K) view, bias (n_out,)): an extra last layer computed on the CUDA cores (vx_mlp_chain_batch)."""
         from ._lib import call
         self._call = call
         self.layers = layers
         self.transpose = transpose
+        self.final = final
         dev = layers[0]['W'].device
         self.Kp, self.Np, self.N, self.K = [], [], [], []
         n = len(layers)
@@ -194,6 +240,8 @@ class TensorCoreChain:
             self.N.append(N); self.K.append(K)
             self.Kp.append(_pad(K, 8))
             self.Np.append(_pad(N, 32) if i + 1 < n else _pad(N, 16))
+        if final is not None:
+            self.Np[-1] = _pad(self.N[-1], 32)
         for i in range(n - 1):
             assert self.Np[i] == self.Kp[i + 1], 'hidden widths must be multiples of 32 and chain'
         self.W_hi = [torch.zeros(self.Np[i], self.Kp[i], dtype=torch.float32, device=dev) for i in range(n)]
@@ -211,9 +259,34 @@ class TensorCoreChain:
     def prepare(self):
         prepare_chains([self])
 
+    def flops_per_row(self):
+        f = 2 * sum(k * n_ for k, n_ in zip(self.K, self.N))
+        if self.final is not None:
+            f += 2 * self.final[0].shape[0] * self.final[0].shape[1]
+        return f
+
+    def job(self, X, k0, Y, n_out, imgs=None, masks=None, x_img=None, patch=None, gates_out=None):
+        """(ptrs, dims) of this chain as a vx_mlp_chain_batch job (see csrc/mlp_tc.cu for the packing)."""
+        pick = lambda lst, i: lst[i] if (lst is not None and i < len(lst)) else None
+        addr = lambda t: t.data_ptr() if t is not None else 0
+        Wf, bf = self.final if self.final is not None else (None, None)
+        pt, pcol, pn, dep = patch if patch is not None else (None, 0, 0, -1)
+        ptrs = [X.data_ptr(), addr(x_img), Y.data_ptr(), addr(Wf), addr(bf), addr(pt)]
+        dims = [X.stride(0), k0, len(self.layers), Y.stride(0), n_out, Wf.stride(0) if Wf is not None else 0, pcol, pn,
+                pt.stride(0) if pt is not None else 0, dep]
+        for i, L in enumerate(self.layers):
+            ptrs += [self.W_hi[i].data_ptr(), self.W_lo[i].data_ptr(), addr(L.get('bias')), addr(pick(imgs, i)), addr(pick(masks, i)),
+                     addr(pick(gates_out, i))]
+            dims += [self.Kp[i], self.Np[i], self.N[i], int(bool(L.get('relu', False)))]
+        ptrs += [0] * (PTR_STRIDE - len(ptrs))
+        dims += [0] * (JOB_STRIDE - len(dims))
+        return ptrs, _Dims(dims, self.flops_per_row())
+
     def run(self, X, k0, n_rows_dev, Y, n_out, imgs=None, masks=None, x_img=None):
         """X (cap, ldx) with k0 valid columns -> Y (cap, ldy)[:, :n_out].  imgs[l] = (hi, lo) CH(Np) images written for
-        layer l's output (ACT row image), masks[l] = row image gating layer l's output (ReLU backward), x_img = row image of X."""
+        layer l's output (ACT row image), masks[l] = ReLU-gate words (int64 x 4 per row, csrc/mlp_tc.cu MlpLayer.gate) applied to layer l's output (ReLU backward), x_img = row image of X."""
+        if self.final is not None:
+            return run_chain_jobs([self.job(X, k0, Y, n_out, imgs, masks, x_img)], n_rows_dev, X.shape[0], None)
         n = len(self.layers)
         ptrs, dims = [], []
         pick = lambda lst, i: lst[i] if (lst is not None and i < len(lst)) else None
