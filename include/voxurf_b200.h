@@ -160,6 +160,11 @@ int vx_fd_gradient_active(const float* sdf, int X, int Y, int Z, float voxel_siz
  * active (optional): voxels outside it have dgrad == 0 at all six neighbours, their FD part is skipped */
 int vx_sdf_regularisers_backward(const float* dgrad, const float* param, int X, int Y, int Z, float voxel_size,
                                  float wx, float wy, float wz, float* grad, const bool* active, cudaStream_t stream);
+/* the same, restricted to the X-slab [x0, x1) of grad (dgrad may be NULL: TV add-grad only); dgrad / param are full grids.
+ * reduce-scatter -> TV + Adam on the owned X-slab -> all-gather of the parameters */
+int vx_sdf_regularisers_backward_slab(const float* dgrad, const float* param, int X, int Y, int Z, float voxel_size,
+                                      float wx, float wy, float wz, float* grad, const bool* active, int x0, int x1,
+                                      cudaStream_t stream);
 /* _gaussian_3dconv / tv_smooth_conv: Conv3d(1,1,k,padding=k//2,'replicate')  lib/voxurf_fine.py:236-258 ;
  * B independent volumes; weight_host is (k,k,k) on the HOST, k in {1,3,5} */
 int vx_conv3d_replicate(const float* in, int B, int X, int Y, int Z, const float* weight_host, int ksize,

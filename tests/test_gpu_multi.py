@@ -29,7 +29,7 @@ def _batches(world, n_rays):
     return out
 
 
-def _worker(rank, world, port, n_rays, step, sparse, ret):
+def _worker(rank, world, port, n_rays, step, sparse, ret, dense_exchange=False, graph=False):
     import torch.distributed as dist
     from voxurf_b200.fused import FusedFineStep
     from voxurf_b200.parallel import GradSync
@@ -39,22 +39,40 @@ def _worker(rank, world, port, n_rays, step, sparse, ret):
     dev = torch.device('cuda', rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     m = _build(dev)
-    fs = FusedFineStep(m, n_rays, FINE_TRAIN, RK, row_capacity=8192, world=world, rank=rank, sparse_k0_exchange=sparse)
+    fs = FusedFineStep(m, n_rays, FINE_TRAIN, RK, row_capacity=8192, world=world, rank=rank, sparse_k0_exchange=sparse,
+                       dense_exchange=dense_exchange, use_graph=graph)
+    assert fs.sharded == (not dense_exchange)
     b = [t.to(dev) for t in _batches(world, n_rays)[rank]]
+    if graph:
+        # whole steps (CUDA-graph capture and replay of the step including its NCCL collectives): parameters only
+        for it in range(7):
+            fs.step(*b, step + it)
+        fs.sync_params()
+        fs.poll_overflow(force=True)
+        assert len(fs._graphs) == 2
+        ret[rank] = ({}, {'sdf': m.sdf.grid.detach().cpu(), 'k0': m.k0.grid.detach().contiguous().cpu(), 'mlp1': fs.mlp1.flat.detach().cpu()})
+        fs.release_graphs()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     fs.forward_backward(*b, step)
     fs.grad_sync()
+    if fs.sharded:     # the reduce-scatter left every rank with its X-slab of the averaged sdf gradient
+        flat = m.sdf.grid.grad.view(-1)
+        dist.all_gather_into_tensor(flat, flat[fs.slab[0]:fs.slab[1]].clone())
     grads = {'sdf': m.sdf.grid.grad.clone().cpu(), 'k0': m.k0.grid.grad.contiguous().clone().cpu(),
              'mlp1': fs.mlp1.flat.grad.clone().cpu(), 'mlp2': fs.mlp2.flat.grad.clone().cpu()}
     fs.regularise(step)
     fs.optimizer_step()
+    fs.sync_params()
     params = {'sdf': m.sdf.grid.detach().cpu(), 'k0': m.k0.grid.detach().contiguous().cpu(), 'mlp1': fs.mlp1.flat.detach().cpu()}
     fs.counts()
     ret[rank] = (grads, params)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('sparse', [True, False])
-def test_two_gpu_gradients_equal_single_gpu_on_concatenated_batch(sparse):
+@pytest.mark.parametrize('sparse,dense_exchange', [(True, False), (False, False), (True, True)])
+def test_two_gpu_gradients_equal_single_gpu_on_concatenated_batch(sparse, dense_exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
@@ -63,7 +81,7 @@ def test_two_gpu_gradients_equal_single_gpu_on_concatenated_batch(sparse):
     world, n_rays, step = 2, 512, 15003
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, n_rays, step, sparse, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n_rays, step, sparse, ret, dense_exchange), nprocs=world, join=True)
     # single GPU, concatenated batch
     dev = torch.device('cuda', 0)
     m = _build(dev)
@@ -88,3 +106,30 @@ def test_two_gpu_gradients_equal_single_gpu_on_concatenated_batch(sparse):
     for k in ('sdf', 'mlp1') + (() if sparse else ('k0',)):
         assert torch.equal(ret[0][1][k], ret[1][1][k]), k
     np.testing.assert_allclose(ret[0][1]['k0'].numpy(), ret[1][1]['k0'].numpy(), rtol=1e-4, atol=2e-3)
+
+
+def test_two_gpu_graph_replayed_steps_follow_single_gpu():
+    """Seven whole steps (TV iterations included) as CUDA-graph replays with the slab-sharded exchange captured inside,
+    against a single GPU stepping on the concatenated batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from voxurf_b200.fused import FusedFineStep
+    from voxurf_b200.trainer import FINE_TRAIN
+    world, n_rays, step = 2, 512, 15001
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, n_rays, step, True, ret, False, True), nprocs=world, join=True)
+    dev = torch.device('cuda', 0)
+    m = _build(dev)
+    fs = FusedFineStep(m, n_rays * world, FINE_TRAIN, RK, row_capacity=16384)
+    bs = _batches(world, n_rays)
+    cat = [torch.cat([b[i] for b in bs]).to(dev) for i in range(4)]
+    for it in range(7):
+        fs.step(*cat, step + it)
+    refp = {'sdf': m.sdf.grid.detach().cpu(), 'k0': m.k0.grid.detach().contiguous().cpu(), 'mlp1': fs.mlp1.flat.detach().cpu()}
+    for r in range(world):
+        for k, lr in (('sdf', 5e-3), ('k0', 1e-1), ('mlp1', 3e-3)):
+            d = (ret[r][1][k] - refp[k]).abs()
+            assert float((d > 2e-2 * lr).float().mean()) < 1e-3 and float(d.max()) <= 8 * lr, (r, k, float(d.max()))
+    assert torch.equal(ret[0][1]['sdf'], ret[1][1]['sdf']) and torch.equal(ret[0][1]['mlp1'], ret[1][1]['mlp1'])

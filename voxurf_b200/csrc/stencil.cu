@@ -90,9 +90,13 @@ template <bool kFd, bool kTv>
 __global__ void __launch_bounds__(256) k_sdf_reg_backward_v4(const float* __restrict__ dgrad, const float* __restrict__ param,
                                                              uint32_t X, uint32_t Y, uint32_t Z, float vs, float w_fast,
                                                              float w_mid, float w_slow, float* __restrict__ grad,
-                                                             const bool* __restrict__ active) {
-  const uint32_t Z4 = Z >> 2, n4 = X * Y * Z4, V = X * Y * Z, sX = Y * Z;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
+                                                             const bool* __restrict__ active, uint32_t x_begin = 0,
+                                                             uint32_t x_end = 0xffffffffu) {
+  // [x_begin, x_end): the X-slab of grad to update (data-parallel training: every rank regularises and steps only the
+  // slab it owns; dgrad / param are the full grids, the one-plane halo is local)
+  const uint32_t Z4 = Z >> 2, V = X * Y * Z, sX = Y * Z;
+  const uint32_t t0 = x_begin * Y * Z4, n4 = min(x_end, X) * Y * Z4;
+  for (uint32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += gridDim.x * blockDim.x) {
     const uint32_t k4 = t % Z4, ij = t / Z4, j = ij % Y, i = ij / Y, v = t << 2, k = k4 << 2;
     const bool fd_here = kFd && !(active && __ldg(reinterpret_cast<const uint32_t*>(active) + t) == 0u);
     if (!kTv && !fd_here) continue;
@@ -578,6 +582,26 @@ VX_API int vx_sdf_regularisers_backward(const float* dgrad, const float* param, 
   int rc = vx_fd_gradient_backward(dgrad, X, Y, Z, voxel_size, grad, st);
   if (rc) return rc;
   return vx_total_variation_add_grad(param, grad, nullptr, wx, wy, wz, 1, X, Y, Z, V, st);
+}
+
+// The same two regularisers restricted to the X-slab [x0, x1) of grad (dgrad may be nullptr: TV add-grad only).  dgrad and
+// param are full grids: the stencils reach one plane outside the slab.  Used by the slab-sharded data-parallel step
+// (reduce-scatter -> TV + Adam on the owned slab -> all-gather of the parameters).
+VX_API int vx_sdf_regularisers_backward_slab(const float* dgrad, const float* param, int X, int Y, int Z, float voxel_size,
+                                             float wx, float wy, float wz, float* grad, const bool* active, int x0, int x1,
+                                             cudaStream_t st) {
+  VX_REQUIRE(0 <= x0 && x0 <= x1 && x1 <= X, "vx_sdf_regularisers_backward_slab", "0 <= x0 <= x1 <= X");
+  VX_REQUIRE(Z % 4 == 0 && (reinterpret_cast<uintptr_t>(param) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0 &&
+             (!dgrad || (reinterpret_cast<uintptr_t>(dgrad) & 15) == 0) && (reinterpret_cast<uintptr_t>(active) & 3) == 0 &&
+             (int64_t)X * Y * Z < ((int64_t)1 << 32), "vx_sdf_regularisers_backward_slab", "Z % 4 == 0, 16-byte aligned grids, < 2^32 voxels");
+  if (x0 == x1) return 0;
+  (void)wx;
+  const int64_t n4 = (int64_t)(x1 - x0) * Y * (Z / 4);
+  if (dgrad)
+    k_sdf_reg_backward_v4<true, true><<<grid_blocks(n4), 256, 0, st>>>(dgrad, param, X, Y, Z, voxel_size, wz / 6, wy / 6, wz / 6, grad, active, x0, x1);
+  else
+    k_sdf_reg_backward_v4<false, true><<<grid_blocks(n4), 256, 0, st>>>(nullptr, param, X, Y, Z, 1.f, wz / 6, wy / 6, wz / 6, grad, nullptr, x0, x1);
+  return vx_check_launch("vx_sdf_regularisers_backward_slab");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -138,7 +138,17 @@ class FusedFineStep:
             self.consts = torch.zeros(16, dtype=torch.float32, device=dev)
             self.in_o, self.in_d, self.in_v, self.in_t = (torch.zeros(n_rays, 3, dtype=torch.float32, device=dev) for _ in range(4))
         self.force_eager = False   # bench.py: launch the kernels of the step one by one even when use_graph is set
-        self.sharded = False
+        # Slab-sharded data-parallel exchange (SURVEY.md 8e "preferred form"): reduce-scatter of the sdf gradient over X-slabs,
+        # regularisers + Adam on the owned slab only, all-gather of the updated sdf PARAMETERS at the start of the next step
+        # (it overlaps ray set-up and the march, which read rays and the mask cache only).  Non-owned slabs of this rank's sdf
+        # grid / moments are stale between a step and the next all-gather: sync_params() / unshard() bring them up to date.
+        self.sharded = world > 1 and not dense_exchange and self.X % world == 0 and not m.smooth_sdf
+        self._params_dirty = False
+        self._ag_work = None
+        if self.sharded:
+            per = self.X // world * self.Y * self.Z
+            self.slab_x = (rank * (self.X // world), (rank + 1) * (self.X // world))
+            self.slab = (rank * per, (rank + 1) * per)
         self.bitmap_probe = None   # bench.py: list collecting copies of (touched, live) as the k0 Adam launch sees them
         self.timings = None   # bench.py: list collecting (group, (start, end) CUDA events) around the k0 / sdf Adam launches
         if self.cfg is not None:
@@ -180,6 +190,7 @@ class FusedFineStep:
         self.inv_s, self._inv_s_dev = inv_s, inv_s_dev
         X, Y, Z, mn, mx = self._geom()
         near = self.rk['near']
+        self._begin_param_gather()      # (sharded data-parallel step) runs under ray set-up and the march
         call('vx_ray_setup', rays_o, rays_d, m.xyz_min, m.xyz_max, near, 1e9, self.stepdist, N, self.t_min, self.t_max,
              self.n_steps, self.start, self.dirs, self.offsets)
         mc = m.mask_cache.march_args() if m.mask_cache is not None else (None, 1, 1, 1, [0., 0., 0.], [1., 1., 1.], 0., 1., 0.)
@@ -187,6 +198,7 @@ class FusedFineStep:
              self.bits_in, self.bits_keep, self.keep_count, self.keep_off)
         call('vx_march_emit', self.offsets, N, self.bits_keep, self.keep_off, self.cap2, self.ray_id, self.step_id, None)
         n2 = self.keep_off[N:]
+        self._finish_param_gather()     # first read of the sdf grid follows
         if m.smooth_sdf:
             if self.conv_scratch is None:
                 self.conv_scratch = torch.empty(2 * m.sdf.grid.numel(), dtype=torch.float32, device=self.dev)
@@ -311,10 +323,48 @@ class FusedFineStep:
         call('vx_fused_export_k0_rows', *self._pts(), self.idx4, n4, cap, self.dX2, self.ld2, C, 1.0 / W, *self._k0_send)
         self._k0_work = [dist.all_gather_into_tensor(self._k0_recv[i], self._k0_send[i], async_op=True) for i in range(2)]
 
+    def _begin_param_gather(self):
+        """Sharded step: all-gather (in place) of the sdf slabs the ranks updated in the previous step."""
+        if self.sharded and self._params_dirty and self._ag_work is None:
+            import torch.distributed as dist
+            flat = self.m.sdf.grid.data.view(-1)
+            self._ag_work = dist.all_gather_into_tensor(flat, flat[self.slab[0]:self.slab[1]], async_op=True)
+
+    def _finish_param_gather(self):
+        if self._ag_work is not None:
+            self._ag_work.wait()
+            self._ag_work, self._params_dirty = None, False
+
+    def sync_params(self):
+        """Make this rank's copy of the sdf grid current (sharded step: the slabs other ranks own are stale between a
+        step and the next step's all-gather).  Call before reading parameters: rendering, checkpoints, evaluation."""
+        self._begin_param_gather()
+        self._finish_param_gather()
+
+    def unshard(self):
+        """Leave the slab-sharded mode: parameters and Adam moments of the sdf grid are all-gathered so that every rank
+        holds the full optimizer state again (checkpoints; regulariser combinations the slab kernels do not cover)."""
+        if not self.sharded:
+            return
+        import torch.distributed as dist
+        self.sync_params()
+        st = self.adam_state.get(id(self.m.sdf.grid))
+        if st is not None:
+            for t in st:
+                flat = t.view(-1)
+                dist.all_gather_into_tensor(flat, flat[self.slab[0]:self.slab[1]])
+        self.sharded = False
+        self.release_graphs()
+
     def _sync_begin(self):
         import torch.distributed as dist
-        self._works = [dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True)
-                       for t in (self.sdf_grad, self.mlp1.flat.grad, self.mlp2.flat.grad)]
+        AVG = dist.ReduceOp.AVG
+        if self.sharded:
+            flat = self.sdf_grad.view(-1)      # in place: the owned slab of this buffer receives the rank-averaged gradient
+            self._works = [dist.reduce_scatter_tensor(flat[self.slab[0]:self.slab[1]], flat, op=AVG, async_op=True)]
+        else:
+            self._works = [dist.all_reduce(self.sdf_grad, op=AVG, async_op=True)]
+        self._works += [dist.all_reduce(t, op=AVG, async_op=True) for t in (self.mlp1.flat.grad, self.mlp2.flat.grad)]
 
     def _sync_k0(self):
         import torch.distributed as dist
@@ -391,6 +441,10 @@ class FusedFineStep:
             self.loss.add_(self.tv_loss)   # run.py:622-625 adds the regulariser to the reported loss
         n_batch = global_batch or self.N * self.world
         wt = c['weight_tv_density'] * tv['sdf_tv'] / n_batch * max(X, Y, Z) / 128
+        if self.sharded:    # only the owned X-slab of the gradient is regularised (and stepped); _slab_covers(flags) holds
+            call('vx_sdf_regularisers_backward_slab', self.dG if tv['smooth_grad_tv'] > 0 else None, m.sdf.grid, X, Y, Z,
+                 m._voxel_size_host, wt, wt, wt, self.sdf_grad, self.tv_active if tv['smooth_grad_tv'] > 0 else None, *self.slab_x)
+            return
         if tv['smooth_grad_tv'] > 0 and tv['sdf_tv'] > 0 and dense:
             # both regularisers land in the sdf gradient with one read-modify-write
             call('vx_sdf_regularisers_backward', self.dG, m.sdf.grid, X, Y, Z, m._voxel_size_host, wt, wt, wt, self.sdf_grad,
@@ -401,6 +455,14 @@ class FusedFineStep:
         if tv['sdf_tv'] > 0:
             call('vx_total_variation_add_grad', m.sdf.grid, self.sdf_grad, None, wt, wt, wt,
                  int(dense), X, Y, Z, m.sdf.grid.numel())
+
+    def _slab_covers(self, flags):
+        """Regulariser combinations the slab kernel implements: dense TV add-grad with or without the smooth-gradient TV."""
+        is_tv, dense = flags
+        if not is_tv:
+            return True
+        tv = self.cfg['tv_terms']
+        return dense and tv['sdf_tv'] > 0 and self.X * self.Y * self.Z < 2 ** 32 and self.Z % 4 == 0
 
     def regularise(self, global_step, global_batch=None, flags=None):
         """run.py:612-625 (smooth-grad TV through the full-grid FD gradient) and run.py:641-655 (TV add-grad)."""
@@ -432,7 +494,16 @@ class FusedFineStep:
                 touched, live = (self.k0_touched, self.k0_live) if name == 'k0' else (None, None)
                 if touched is not None and self.bitmap_probe is not None:
                     self.bitmap_probe.append((touched.clone(), live.clone()))
-                call('vx_adam_step', _storage(p.data), _storage(p.grad), _storage(st[0]), _storage(st[1]), None, p.numel(),
+                tensors = [_storage(p.data), _storage(p.grad), _storage(st[0]), _storage(st[1])]
+                if name == 'sdf' and self.sharded:
+                    # the owned X-slab only; the other slabs of the gradient buffer still hold this rank's local
+                    # (un-reduced) gradient and are cleared here, the Adam pass clears the slab itself
+                    lo, hi = self.slab
+                    g = tensors[1].view(-1)
+                    g[:lo].zero_(); g[hi:].zero_()
+                    tensors = [t.view(-1)[lo:hi] for t in tensors]
+                    self._params_dirty = True
+                call('vx_adam_step', *tensors, None, tensors[0].numel(),
                      beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1, touched, live, self.C,
                      None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
                 if touched is not None:
@@ -446,6 +517,12 @@ class FusedFineStep:
         group, step count, decayed learning rates, the k0 `live` bitmap.  Mirrors what run.py:786-793 saves as
         optimizer_state_dict."""
         self.sync_s_val()
+        if self.sharded:      # every rank saves the full sdf parameters and moments
+            import torch.distributed as dist
+            self.sync_params()
+            mom = self.adam_state.get(id(self.m.sdf.grid))
+            for t in (mom or ()):
+                dist.all_gather_into_tensor(t.view(-1), t.view(-1)[self.slab[0]:self.slab[1]])
         st = {'adam_steps': self.adam_steps, 'lr': dict(self.lr), 'moments': {}}
         for name, params, _ in self.groups:
             m = self.adam_state.get(id(params[0]))
@@ -502,13 +579,18 @@ class FusedFineStep:
             self.lr[k] *= f
 
     def _step_body(self, rays_o, rays_d, viewdirs, target, global_step, flags):
-        if flags[0] and self.tensor_core and self.world == 1:   # (multi-GPU keeps the order its tests were run with)
+        if self.sharded and not self._slab_covers(flags):
+            self.unshard()      # e.g. sparse TV after tv_dense_before: back to the dense exchange, full optimizer state everywhere
+        if flags[0] and self.tensor_core:
             # the first half of the TV regulariser depends on the parameters only: it runs on the side stream (ahead of
             # the weight-gradient launch that is forked onto the same stream later) beside the forward / backward pass
             if self._dw_stream is None:
                 self._dw_stream = torch.cuda.Stream(device=self.dev)
+            self._begin_param_gather()
             self._dw_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._dw_stream):
+                if self._ag_work is not None:
+                    self._ag_work.wait()     # the FD gradient reads the whole sdf grid
                 self.regularise_prepare(flags)
             early_tv = True
         else:
@@ -519,7 +601,8 @@ class FusedFineStep:
         else:
             reg = lambda: self.regularise(global_step, flags=flags)
         if self.world > 1:
-            # overlap: the sdf / MLP all-reduces run on the NCCL stream while k0 is re-scattered and updated
+            # overlap: the sdf reduce-scatter (or all-reduce) and the MLP all-reduces run on the NCCL stream while k0 is
+            # re-scattered and updated
             self._sync_begin()
             self._sync_k0()
             self.optimizer_step(only=('k0',))
@@ -566,8 +649,71 @@ class FusedFineStep:
             self._graphs[flags] = g
             self._graph_launches[flags] = launch_count() - l0
         g.replay()
+        self._params_dirty = self.sharded      # (host flags do not move during a replay)
         self.launches_replayed += self._graph_launches[flags]
         return self.loss
+
+    @torch.no_grad()
+    def parity_check(self, batch, global_step, rtol=1e-4):
+        """Untimed proof for multi-GPU runs (bench.py prints it as `parity_check`): (a) the replicas agree -- float64
+        checksums of the sdf grid and both MLPs identical on every rank (bit-for-bit: they see the same reduced gradients),
+        k0 to rounding (its row re-scatter is atomic-ordered per rank); (b) the exchanged gradients of one step on this
+        rank's `batch` equal the gradients a single GPU computes on the concatenated batch of all ranks.  Leaves gradient
+        buffers cleared; call it after the timed region.  -> dict (same on every rank)"""
+        import copy
+        import torch.distributed as dist
+        W, m = self.world, self.m
+        self.sync_params()
+        sums = torch.stack([m.sdf.grid.double().sum(), m.sdf.grid.double().abs().sum(), self.mlp1.flat.double().sum(),
+                            self.mlp2.flat.double().sum(), _storage(m.k0.grid).double().sum()])
+        allsums = [torch.zeros_like(sums) for _ in range(W)]
+        dist.all_gather(allsums, sums)
+        identical = all(torch.equal(allsums[0][:4], a[:4]) for a in allsums)
+        k0_spread = max(float((a[4] - allsums[0][4]).abs() / allsums[0][4].abs().clamp_min(1e-300)) for a in allsums)
+        # (b) one step's gradients through the exchange
+        was_eager = self.force_eager
+        self.force_eager = True
+        self.forward_backward(*batch, global_step)
+        self._sync_begin()
+        self._sync_k0()
+        self._sync_end()
+        if self.sharded:      # put the reduced slabs of all ranks together (untimed)
+            flat = self.sdf_grad.view(-1)
+            dist.all_gather_into_tensor(flat, flat[self.slab[0]:self.slab[1]].clone())
+        self.force_eager = was_eager
+        cat = []
+        for t in batch:
+            parts = [torch.empty_like(t) for _ in range(W)]
+            dist.all_gather(parts, t.contiguous())
+            cat.append(torch.cat(parts))
+        res = torch.zeros(5, dtype=torch.float64, device=self.dev)
+        if self.rank == 0:
+            m2 = copy.deepcopy(m)
+            ref = FusedFineStep(m2, self.N * W, self.cfg, self.rk, row_capacity=self.cap4 * W, world=1, rank=0)
+            ref.forward_backward(*cat, global_step)
+            pairs = [(self.sdf_grad, ref.sdf_grad), (_storage(self.k0_grad), _storage(ref.k0_grad)),
+                     (self.mlp1.flat.grad, ref.mlp1.flat.grad), (self.mlp2.flat.grad, ref.mlp2.flat.grad)]
+            ok = 1.0
+            for i, (a, b) in enumerate(pairs):
+                scale = float(b.abs().max().clamp_min(1e-30))
+                d = (a - b).abs()
+                bad = d > (rtol * b.abs() + rtol * scale)
+                res[i] = float(d.max()) / scale
+                # (a handful of ReLU gates of pre-activations within 1e-6 of zero may flip between the two runs: DESIGN.md 6)
+                if int(bad.sum()) > max(2, 1e-5 * bad.numel()) or res[i] > 5e-2:
+                    ok = 0.0
+            res[4] = ok
+            del ref, m2
+        dist.broadcast(res, 0)
+        # leave clean gradient buffers behind
+        self.sdf_grad.zero_(); _storage(self.k0_grad).zero_(); self.mlp1.flat.grad.zero_(); self.mlp2.flat.grad.zero_()
+        if self.k0_touched is not None:
+            self.k0_touched.zero_()
+        r = [float(v) for v in res.cpu()]
+        return {'ok': bool(identical and r[4] == 1.0 and k0_spread < 1e-6), 'replicas_identical_sdf_mlps': bool(identical),
+                'k0_checksum_rel_spread': k0_spread, 'exchange': 'slab reduce-scatter + sharded Adam + param all-gather' if self.sharded else 'dense all-reduce',
+                'grad_vs_single_gpu_max_err_over_max': {'sdf': r[0], 'k0': r[1], 'rgbnet': r[2], 'k_rgbnet': r[3]},
+                'tolerance': f'|d| <= {rtol} |g| + {rtol} max|g| (all but <= 1e-5 of the elements: ReLU-gate flips)', 'world': W}
 
     def release_graphs(self):
         """Drop the captured CUDA graphs (they hold NCCL work at world > 1: release them before the process group)."""
