@@ -136,6 +136,12 @@ int vx_sdf_taps_backward(const float* grid, int X, int Y, int Z, const float* xy
                          int64_t n_host, const float* displace_host, int L, float voxel_size, int use_grad_norm,
                          int xyz_order, const float* grad_sdf, const float* grad_feat, const float* grad_grad,
                          float* grad_grid, cudaStream_t stream);
+/* Mesh field query (lib/voxurf_fine.py:894-910, lib/dvgo_ori.py:679-693): out_u[i][j][k] = (negate ? -1 : 1) * trilinear
+ * value of the single-channel grid at (xs[i], ys[j], zs[k]); out_grad (optional, (nx,ny,nz,3), x,y,z order) = the 6-tap
+ * gradient of Voxurf.grid_sampler(sample_grad=True), lib/voxurf_fine.py:502-534.  xs may be an X-slab of the lattice axis. */
+int vx_sdf_lattice(const float* grid, int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
+                   const float* xs, const float* ys, const float* zs, int nx, int ny, int nz, float voxel_size,
+                   int negate, float* out_u, float* out_grad, cudaStream_t stream);
 /* neus_alpha_from_sdf_scatter  lib/voxurf_fine.py:463-500 (== lib/voxurf_coarse.py:348-382); give ray_id (int32)
  * or ray_id64 */
 int vx_neus_alpha(const float* viewdirs, const int* ray_id, const int64_t* ray_id64, const float* sdf,

@@ -119,6 +119,15 @@ def test_fused_render_matches_dropin_forward():
     out = fs.render(ro, rd, vd)
     for k in ['rgb_marched', 'rgb_marched0', 'normal_marched', 'depth', 'alphainv_cum']:
         close(out[k], ref[k], 1e-5, 3e-6, k)
+    # the same chunk as one CUDA-graph replay (what bench.py --workload render times), on two different ray sets
+    fg = FusedFineStep(m, n_rays, None, rk, row_capacity=fs.cap4, use_graph=True)
+    for seed in (5, 6, 7):
+        ro2, rd2, vd2 = (T(x).to(DEV) for x in S.make_rays(n_rays, seed=seed))
+        a = {k: v.clone() for k, v in fs.render(ro2, rd2, vd2).items() if torch.is_tensor(v)}
+        b = fg.render_chunk(ro2, rd2, vd2)
+        for k in ['rgb_marched', 'rgb_marched0', 'normal_marched', 'depth', 'alphainv_cum']:
+            assert torch.equal(a[k], b[k]), k
+    assert fg.launches_replayed > 0
 
 
 def test_fused_step_cuda_graph_replay_matches_eager():

@@ -158,21 +158,36 @@ def test_coarse_model_matches_oracle_with_regularisers(G, n_rays, cl):
         grad_close(l.weight.grad, W.grad); grad_close(l.bias.grad, b.grad)
 
 
-def test_query_sdf_field_matches_oracle_and_shards_by_slab():
-    """Mesh field query (SURVEY 8d config 5 shape at small size): the smoothed -sdf on a lattice, whole and as X-slabs."""
+def test_query_sdf_field_matches_reference_and_shards_by_slab():
+    """Mesh field query (BASELINE config 5 at small size): the smoothed -sdf and its gradient on a lattice, whole and as
+    X-slabs, against the vectors of the reference's own extract_fields / grid_sampler (tests/golden/r2_extras.npz) and
+    against the oracle at a lattice size that does not divide the grid."""
+    g = load_golden('r2_extras.npz')
     sc = S.make_fine_scene(24, 6, 32, seed=5, mask_G=12)
     m = product_fine_model(sc)
     om = oracle_fine_model(sc, requires_grad=False)
+    u, gr = m.query_sdf_field(24, smooth=True, sigma=0.5, with_gradient=True)
+    close(u, g['field_u'], 1e-5, 2e-6, 'u vs extract_fields'); close(-u, g['field_sdf'], 1e-5, 2e-6)
+    close(gr, g['field_grad'], 1e-5, 1e-5, 'gradient field vs grid_sampler(sample_grad=True)')
+    close(m.query_sdf_field(24, smooth=False), g['field_u_raw'], 1e-5, 2e-6)
     res = 37
     ref = R.sdf_field(om['sdf'], om['xyz_min'], om['xyz_max'], res, smooth=True, sigma=0.5)
-    u = m.query_sdf_field(res, smooth=True, sigma=0.5, chunk=res * res * 5)
+    u = m.query_sdf_field(res, smooth=True, sigma=0.5)
     assert u.shape == (res, res, res)
     close(u, ref, 1e-5, 2e-6)
-    slabs = [m.query_sdf_field(res, x_range=(a, min(a + 10, res))) for a in range(0, res, 10)]
-    assert torch.equal(torch.cat(slabs, 0), m.query_sdf_field(res))
-    close(m.query_sdf_field(res, smooth=False), R.sdf_field(om['sdf'], om['xyz_min'], om['xyz_max'], res, smooth=False), 1e-5, 2e-6)
+    sref, gref = R.sdf_gradient_field(om['sdf'], om['xyz_min'], om['xyz_max'], om['voxel_size'], res, smooth=True, sigma=0.5)
     u2, g2 = m.query_sdf_field(res, with_gradient=True)
-    assert torch.equal(u2, m.query_sdf_field(res)) and g2.shape == (res, res, res, 3)
+    assert torch.equal(u2, u)
+    close(g2, gref, 1e-5, 1e-5, 'gradient field')
+    # identical to the chunked meshgrid -> grid_sampler path, bit for bit
+    grid = m.mesh_query_grid(True, 0.5)
+    ax = [torch.linspace(-1., 1., res) for _ in range(3)]
+    pts = torch.stack(torch.meshgrid(*ax, indexing='ij'), -1).reshape(-1, 3).to(DEV)
+    s_, gs_, _ = m.grid_sampler(pts, grid, sample_ret=True, sample_grad=True)
+    assert torch.equal(-s_.reshape(res, res, res), u) and torch.equal(gs_.reshape(res, res, res, 3), g2)
+    slabs = [m.query_sdf_field(res, x_range=(a, min(a + 10, res)), with_gradient=True, sdf_grid=grid) for a in range(0, res, 10)]
+    assert torch.equal(torch.cat([s[0] for s in slabs], 0), u) and torch.equal(torch.cat([s[1] for s in slabs], 0), g2)
+    close(m.query_sdf_field(res, smooth=False), R.sdf_field(om['sdf'], om['xyz_min'], om['xyz_max'], res, smooth=False), 1e-5, 2e-6)
 
 
 @pytest.mark.parametrize('cl', [False, True])
@@ -182,7 +197,7 @@ def test_scale_volume_grid_matches_oracle(cl):
     sc = S.make_fine_scene(20, 6, 32, seed=3, mask_G=12)
     m = product_fine_model(sc, k0_channels_last=cl)
     om = oracle_fine_model(sc, requires_grad=False)
-    new_voxels = 28 ** 3
+    new_voxels = 23000   # 28.4^3: clear of the float32 pow / floor edge at exact cubes (the golden vector uses the same)
     m.scale_volume_grid(new_voxels)
     ws = tuple(int(w) for w in m.world_size)
     assert ws == (28, 28, 28) and m.sdf.grid.shape == (1, 1) + ws and m.k0.grid.shape == (1, 6) + ws
@@ -192,6 +207,9 @@ def test_scale_volume_grid_matches_oracle(cl):
     sdf[~nonempty] = 1
     close(m.sdf.grid, sdf, 1e-5, 1e-6)
     close(m.k0.grid, R.scale_volume(om['k0'], ws), 1e-5, 1e-6)
+    g = load_golden('r2_extras.npz')      # the reference's own scale_volume_grid (lib/voxurf_fine.py:384-397)
+    assert tuple(int(w) for w in g['sv_world_size']) == ws and (m.nonempty_mask.cpu().numpy() == g['sv_nonempty']).all()
+    close(m.sdf.grid, g['sv_sdf'], 1e-5, 1e-6, 'sdf vs reference'); close(m.k0.grid, g['sv_k0'], 1e-5, 1e-6, 'k0 vs reference')
     assert m.k0.grid.is_contiguous(memory_format=torch.channels_last_3d) == cl or not cl
     voxel_size = ((om['xyz_max'] - om['xyz_min']).prod() / new_voxels).pow(1 / 3)
     close(m.voxel_size, voxel_size, 1e-6, 0)
@@ -199,3 +217,20 @@ def test_scale_volume_grid_matches_oracle(cl):
     ro, rd, vd = (T(x).to(DEV) for x in S.make_rays(64, seed=3))
     ret = m(ro, rd, vd, global_step=100, near=0.3, far=6.0, bg=0.0, stepsize=0.5)
     assert torch.isfinite(ret['rgb_marched']).all()
+
+
+def test_coarse_regularisers_match_reference_formula():
+    """lib/voxurf_coarse.py:300-320,702-715 (sum / 3 / mask.sum(), not the fine file's per-axis means): values and gradients of
+    density_total_variation(sdf_tv, smooth_grad_tv) and k0_total_variation against the reference's own functions."""
+    g = load_golden('r2_extras.npz')
+    sc = S.make_coarse_scene(16, 12, 32, seed=4, mask_G=12)
+    m = product_coarse_model(sc)
+    m.gradient = m.neus_sdf_gradient(sdf=m.sdf.grid)
+    tv = m.density_total_variation(sdf_tv=0.1, smooth_grad_tv=0.2)
+    close(tv, g['ctv_density_value'], 1e-5, 1e-8)
+    tv.backward()
+    close(m.sdf.grid.grad, g['ctv_density_grad'], 1e-4, 1e-7)
+    k0l = m.k0_total_variation()
+    close(k0l, g['ctv_k0_value'], 1e-5, 1e-8)
+    k0l.backward()
+    close(m.k0.grid.grad, g['ctv_k0_grad'], 1e-4, 1e-9)

@@ -379,6 +379,57 @@ VX_API int vx_sdf_taps_backward(const float* grid, int X, int Y, int Z, const fl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Mesh field query (lib/voxurf_fine.py:894-910 + lib/dvgo_ori.py:679-693): the trilinear value of a single-channel grid,
+// optionally negated (extract_geometry queries -sdf), and optionally its 6-tap gradient (Voxurf.grid_sampler with
+// sample_grad=True, displace 1.0: lib/voxurf_fine.py:502-534) on the lattice xs[i] x ys[j] x zs[k] -- the three
+// torch.linspace axes of extract_fields, xs already restricted to an X-slab.  One thread per lattice point; the
+// arithmetic per point is k_sdf_taps's (L = 1, xyz order), so results are bit-identical to the chunked
+// meshgrid -> grid_sampler path, without materialising the (P,3) points.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sdf_lattice(VxGrid g, const float* __restrict__ grid, const float* __restrict__ xs, const float* __restrict__ ys,
+                              const float* __restrict__ zs, int nx, int ny, int nz, float voxel_size, float sign,
+                              float* __restrict__ out_u, float* __restrict__ out_grad) {
+  const int64_t n = (int64_t)nx * ny * nz;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(p % nz), j = (int)((p / nz) % ny), i = (int)(p / ((int64_t)nz * ny));
+    const float px = __ldg(xs + i), py = __ldg(ys + j), pz = __ldg(zs + k);
+    VxTap t;
+    {
+      float ix, iy, iz;
+      point_to_index(g, px, py, pz, ix, iy, iz);
+      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+      out_u[p] = sign * vx_tap_eval(grid, t);
+    }
+    if (!out_grad) continue;
+    SdfTapCoords s;
+    sdf_tap_setup(g, px, py, pz, s);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float ix, iy, iz;
+      const float cm = sdf_tap_coords(g, s, a, -1.f, ix, iy, iz);
+      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+      const float fm = vx_tap_eval(grid, t);
+      const float cp = sdf_tap_coords(g, s, a, 1.f, ix, iy, iz);
+      vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+      const float fp = vx_tap_eval(grid, t);
+      out_grad[p * 3 + (2 - a)] = __fdiv_rn(__fdiv_rn(__fsub_rn(fp, fm), __fsub_rn(cp, cm)), voxel_size);
+    }
+  }
+}
+
+VX_API int vx_sdf_lattice(const float* grid, int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
+                          const float* xs, const float* ys, const float* zs, int nx, int ny, int nz, float voxel_size,
+                          int negate, float* out_u, float* out_grad, cudaStream_t st) {
+  const int64_t n = (int64_t)nx * ny * nz;
+  if (n <= 0) return 0;
+  VX_REQUIRE(grid && xs && ys && zs && out_u, "vx_sdf_lattice", "null pointer");
+  const VxGrid g = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
+  k_sdf_lattice<<<(int)min((int64_t)vx_blocks(n, 256), (int64_t)vx_num_sms() * 32), 256, 0, st>>>(
+      g, grid, xs, ys, zs, nx, ny, nz, voxel_size, negate ? -1.f : 1.f, out_u, out_grad);
+  return vx_check_launch("vx_sdf_lattice");
+}
+
+// ---------------------------------------------------------------------------------------------
 // NeuS alpha (lib/voxurf_fine.py:463-500), forward and backward, one thread per sample.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_neus_alpha(const float* __restrict__ viewdirs, const int* __restrict__ ray_id,

@@ -248,7 +248,8 @@ class FusedFineStep:
         """Inference forward (run.py:123-126 calls model(...) per 8192-ray chunk): -> dict of (N, .) tensors.
         Buffers are reused by the next call: clone what you keep."""
         s_val, n2, n4 = self._forward(rays_o, rays_d, viewdirs, None, train=False)
-        self.poll_overflow()
+        if not torch.cuda.is_current_stream_capturing():
+            self.poll_overflow()
         call('vx_fused_composite_loss', self.logit1, self.k_out, 3, self.idx4, self.off4, self.cap4, self.weight,
              self.alphainv_last, None, self.N, 0.0, 0.0, 0.0, 0.0, float(self.rk.get('bg', 0.0)), 0, self.rgb_marched,
              self.rgb_marched0, None, None, None, None, None)
@@ -258,6 +259,30 @@ class FusedFineStep:
         return {'rgb_marched': self.rgb_marched, 'rgb_marched0': self.rgb_marched0, 'alphainv_cum': self.alphainv_last,
                 'normal_marched': self.normal_marched if render_grad else None, 'depth': self.depth if render_depth else None,
                 'disp': (1 / self.depth) if render_depth else 0, 's_val': s_val}
+
+    @torch.no_grad()
+    def render_chunk(self, rays_o, rays_d, viewdirs, render_grad=True, render_depth=True):
+        """render() of one chunk as ONE CUDA-graph replay (use_graph=True; run.py:123-126 renders a view as ~79 such
+        chunks): static input buffers, results in the persistent output buffers (clone what you keep).  The NeuS
+        sharpness is a launch constant of the captured kernels: the graph is re-captured if s_val changed."""
+        if not self.use_graph or self.world > 1 and self.sharded and self._params_dirty:
+            return self.render(rays_o, rays_d, viewdirs, render_grad, render_depth)
+        key = (bool(render_grad), bool(render_depth), float(self.m._s_val_host) if hasattr(self.m, '_s_val_host') else None)
+        rg = getattr(self, '_render_graph', None)
+        if rg is None or rg[0] != key:
+            self.render(rays_o, rays_d, viewdirs, render_grad, render_depth)     # eager once: lazy allocations, kernel attributes
+            torch._foreach_copy_([self.in_o, self.in_d, self.in_v], [rays_o, rays_d, viewdirs])
+            from ._lib import launch_count
+            g = torch.cuda.CUDAGraph()
+            l0 = launch_count()
+            with torch.cuda.graph(g):
+                out = self.render(self.in_o, self.in_d, self.in_v, render_grad, render_depth)
+            self._render_graph = rg = (key, g, out, launch_count() - l0)
+        torch._foreach_copy_([self.in_o, self.in_d, self.in_v], [rays_o, rays_d, viewdirs])
+        rg[1].replay()
+        self.launches_replayed += rg[3]
+        self.poll_overflow()
+        return rg[2]
 
     @torch.no_grad()
     def forward_backward(self, rays_o, rays_d, viewdirs, target, global_step):
@@ -719,6 +744,7 @@ class FusedFineStep:
         """Drop the captured CUDA graphs (they hold NCCL work at world > 1: release them before the process group)."""
         self._graphs.clear()
         self._graph_launches.clear()
+        self._render_graph = None
         torch.cuda.synchronize()
 
     def sync_s_val(self):

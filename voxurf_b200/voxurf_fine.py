@@ -237,32 +237,33 @@ class Voxurf(VoxurfBase):
 
     # ------------------------------------------------------------------ mesh / field queries
     @torch.no_grad()
-    def query_sdf_field(self, resolution, x_range=None, smooth=True, sigma=0.5, with_gradient=False, chunk=64 ** 3 * 8):
+    def query_sdf_field(self, resolution, x_range=None, smooth=True, sigma=0.5, with_gradient=False, sdf_grid=None):
         """The field part of extract_geometry (lib/voxurf_fine.py:894-910 + lib/dvgo_ori.py:679-693): u = -sdf
         (k=3 Gaussian-smoothed when `smooth`) on a resolution^3 lattice over [xyz_min, xyz_max], restricted to the
-        X-slab x_range=(x0, x1) so the lattice can be sharded across GPUs.  Marching cubes stays on the host."""
+        X-slab x_range=(x0, x1) so the lattice can be sharded across GPUs (grids are replicated, the smoothing halo is
+        local).  with_gradient: also the (.., 3) gradient of the same grid at the lattice points (the 6-tap
+        grid_sampler gradient, lib/voxurf_fine.py:502-534).  One fused launch (vx_sdf_lattice): no points are
+        materialised.  sdf_grid: pass the already smoothed grid when querying several slabs."""
         dev = self.sdf.grid.device
-        if self.smooth_sdf:
-            sdf_grid = self.smooth_conv(self.sdf.grid)
-        elif smooth:
-            sdf_grid = SmoothConv(3, sigma)(self.sdf.grid)
-        else:
-            sdf_grid = self.sdf.grid
+        if sdf_grid is None:
+            sdf_grid = self.mesh_query_grid(smooth, sigma)
         x0, x1 = x_range if x_range is not None else (0, resolution)
-        xs = torch.linspace(self._min_host[0], self._max_host[0], resolution, device=dev)[x0:x1]
-        ys = torch.linspace(self._min_host[1], self._max_host[1], resolution, device=dev)
-        zs = torch.linspace(self._min_host[2], self._max_host[2], resolution, device=dev)
+        # torch.linspace on the host in float32, like extract_fields builds its axes; three tiny uploads
+        ax = [torch.linspace(self._min_host[i], self._max_host[i], resolution) for i in range(3)]
+        xs, ys, zs = ax[0][x0:x1].contiguous().to(dev), ax[1].to(dev), ax[2].to(dev)
         u = torch.empty(x1 - x0, resolution, resolution, dtype=torch.float32, device=dev)
         g = torch.empty(x1 - x0, resolution, resolution, 3, dtype=torch.float32, device=dev) if with_gradient else None
-        planes = max(1, chunk // (resolution * resolution))
-        for a in range(0, x1 - x0, planes):
-            b = min(a + planes, x1 - x0)
-            xx, yy, zz = torch.meshgrid(xs[a:b], ys, zs, indexing='ij')
-            pts = torch.stack([xx, yy, zz], -1).reshape(-1, 3)
-            if with_gradient:
-                s, gr, _ = self.grid_sampler(pts, sdf_grid, sample_ret=True, sample_grad=True)
-                g[a:b] = gr.reshape(b - a, resolution, resolution, 3)
-            else:
-                s = self.grid_sampler(pts, sdf_grid)
-            u[a:b] = -s.reshape(b - a, resolution, resolution)
+        X, Y, Z = (int(w) for w in sdf_grid.shape[2:])
+        call('vx_sdf_lattice', sdf_grid, X, Y, Z, self._min_host, self._max_host, xs, ys, zs, x1 - x0, resolution, resolution,
+             self._voxel_size_host, 1, u, g)
         return (u, g) if with_gradient else u
+
+    @torch.no_grad()
+    def mesh_query_grid(self, smooth=True, sigma=0.5):
+        """The grid extract_geometry queries: the per-iteration smoothed grid if the model has one, else the k=3 Gaussian
+        smoothed grid (init_smooth_conv_test_k3), else the raw grid (lib/voxurf_fine.py:894-903)."""
+        if self.smooth_sdf:
+            return self.smooth_conv(self.sdf.grid)
+        if smooth:
+            return SmoothConv(3, sigma).to(self.sdf.grid.device)(self.sdf.grid)
+        return self.sdf.grid
