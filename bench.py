@@ -402,7 +402,10 @@ def main():
         # to ~1.4 GHz under sustained tensor load)
         sustained = None
         if args.sustain > 0:
-            n_sus = max(args.steps, int(args.sustain / max(ms / args.steps * 1e-3, 1e-6)))
+            t_ = torch.tensor([ms], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)     # every rank must run the same number of steps
+            n_sus = max(args.steps, int(args.sustain / max(float(t_[0]) / args.steps * 1e-3, 1e-6)))
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             ts0 = time.perf_counter()

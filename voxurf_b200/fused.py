@@ -106,6 +106,10 @@ class FusedFineStep:
         self.mlp1 = FlatMLP(m.rgbnet, self.ld1, self.D1, tensor_core)
         self.mlp2 = FlatMLP(m.k_rgbnet, self.ld2, self.D2, tensor_core)
         self.mlp1.alloc(self.cap4), self.mlp2.alloc(self.cap4)
+        # one gradient buffer for both networks: the data-parallel exchange is one all-reduce for both
+        n1, n2 = self.mlp1.flat.numel(), self.mlp2.flat.numel()
+        self.mlp_grads = torch.zeros(n1 + n2, dtype=torch.float32, device=dev)
+        self.mlp1.rebind_grad(self.mlp_grads[:n1]); self.mlp2.rebind_grad(self.mlp_grads[n1:])
         # persistent gradient buffers for the grids (zeroed by the Adam kernel itself)
         self.sdf_grad = torch.zeros_like(m.sdf.grid)
         self.k0_grad = torch.zeros_like(m.k0.grid, memory_format=torch.preserve_format)
@@ -341,12 +345,13 @@ class FusedFineStep:
         the scatter of every rank's rows happens in grad_sync()."""
         import torch.distributed as dist
         W, cap, C = self.world, self.cap4, self.C
-        if getattr(self, '_k0_send', None) is None or self._k0_send[0].shape[0] != cap:
-            f32 = lambda *s_: torch.empty(*s_, dtype=torch.float32, device=self.dev)
-            self._k0_send = (f32(cap, 3), f32(cap, C))
-            self._k0_recv = (f32(W * cap, 3), f32(W * cap, C))
-        call('vx_fused_export_k0_rows', *self._pts(), self.idx4, n4, cap, self.dX2, self.ld2, C, 1.0 / W, *self._k0_send)
-        self._k0_work = [dist.all_gather_into_tensor(self._k0_recv[i], self._k0_send[i], async_op=True) for i in range(2)]
+        if getattr(self, '_k0_send', None) is None or self._k0_send.numel() != cap * (3 + C):
+            # one buffer per rank: [cap x 3 positions | cap x C gradient rows] -> ONE all-gather
+            self._k0_send = torch.empty(cap * (3 + C), dtype=torch.float32, device=self.dev)
+            self._k0_recv = torch.empty(W, cap * (3 + C), dtype=torch.float32, device=self.dev)
+        call('vx_fused_export_k0_rows', *self._pts(), self.idx4, n4, cap, self.dX2, self.ld2, C, 1.0 / W,
+             self._k0_send[:cap * 3].view(cap, 3), self._k0_send[cap * 3:].view(cap, C))
+        self._k0_work = [dist.all_gather_into_tensor(self._k0_recv.view(-1), self._k0_send, async_op=True)]
 
     def _begin_param_gather(self):
         """Sharded step: all-gather (in place) of the sdf slabs the ranks updated in the previous step."""
@@ -389,7 +394,7 @@ class FusedFineStep:
             self._works = [dist.reduce_scatter_tensor(flat[self.slab[0]:self.slab[1]], flat, op=AVG, async_op=True)]
         else:
             self._works = [dist.all_reduce(self.sdf_grad, op=AVG, async_op=True)]
-        self._works += [dist.all_reduce(t, op=AVG, async_op=True) for t in (self.mlp1.flat.grad, self.mlp2.flat.grad)]
+        self._works += [dist.all_reduce(self.mlp_grads, op=AVG, async_op=True)]
 
     def _sync_k0(self):
         import torch.distributed as dist
@@ -397,9 +402,11 @@ class FusedFineStep:
         if self.sparse_k0_exchange:
             for w in self._k0_work:
                 w.wait()
-            xyz, g = self._k0_recv
-            call('vx_grid_gather_backward', self.X, self.Y, self.Z, self.C, self.k0_cl, m._min_host, m._max_host, xyz, None, None,
-                 None, None, 0.0, None, xyz.shape[0], g, _storage(self.k0_grad), self.k0_touched)
+            cap, C = self.cap4, self.C
+            for r in range(self.world):      # every rank's rows (zero rows past its count add nothing)
+                xyz, g = self._k0_recv[r, :cap * 3].view(cap, 3), self._k0_recv[r, cap * 3:].view(cap, C)
+                call('vx_grid_gather_backward', self.X, self.Y, self.Z, self.C, self.k0_cl, m._min_host, m._max_host, xyz, None, None,
+                     None, None, 0.0, None, cap, g, _storage(self.k0_grad), self.k0_touched)
         else:
             dist.all_reduce(_storage(self.k0_grad), op=dist.ReduceOp.AVG)
             if self.k0_touched is not None:

@@ -58,6 +58,22 @@ class FlatMLP:
             # dX chain: dH_{l-1} = (dH_l W_l) * (H_{l-1} > 0), i.e. the same kernel on the transposed weights, last layer first
             self.tc_bwd = TensorCoreChain([dict(W=self.W[i], bias=None, relu=False) for i in range(n - 1, -1, -1)], transpose=True)
 
+    def rebind_grad(self, buf):
+        """Move the flat gradient storage into `buf` (numel == flat.numel()): lets several networks share one buffer so that
+        a data-parallel exchange is ONE collective for all of them."""
+        assert buf.numel() == self.flat.numel() and buf.dtype == torch.float32
+        buf.copy_(self.flat.grad)
+        self.flat.grad = buf
+        o = 0
+        for i, l in enumerate(self.linears):
+            out_f, in_f = self.W[i].shape
+            self.dW[i] = buf[o:o + out_f * in_f].view(out_f, in_f)
+            o += out_f * in_f
+            self.db[i] = buf[o:o + out_f]
+            o += out_f
+            l.weight.grad = self.dW[i][:, :l.in_features]
+            l.bias.grad = self.db[i]
+
     def alloc(self, cap):
         dev = self.flat.device
         self.cap = cap
