@@ -39,6 +39,7 @@ G_FINE, N_RAYS, WIDTH = 256, 8192, 192
 START_STEP = 15001   # right after the 160^3 -> 256^3 growth (configs/dtu_e2e/fine.py:26-27)
 RENDER_KW = dict(near=0.3, far=6.0, bg=0.0, stepsize=0.5)
 METRIC = 'rays/sec fwd+bwd+Adam (fine 256^3, 8192-ray batch)'
+PRE_STEPS = 12       # untimed steps before the --warmup steps: eager first occurrences + CUDA-graph captures of every step variant
 
 
 def parse(argv=None):
@@ -60,6 +61,7 @@ def parse(argv=None):
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--path', default='fused', choices=['fused', 'dropin'], help='fused = sync-free FusedFineStep; dropin = Voxurf.forward + autograd')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel of the step separately (no CUDA-graph replay)')
+    ap.add_argument('--no-defer', action='store_true', help='run the optimizer phase at the end of its own step instead of beside the next step\'s march')
     ap.add_argument('--dense-adam', action='store_true', help='k0 Adam over every voxel (no touched/live bitmaps)')
     ap.add_argument('--dense-exchange', action='store_true', help='multi-GPU: plain dense all-reduces instead of the slab-sharded exchange')
     ap.add_argument('--sustain', type=float, default=2.0, help='seconds of back-to-back steps for the `sustained` figure (0 = skip)')
@@ -335,7 +337,7 @@ def main():
     if args.path == 'fused':
         from voxurf_b200.fused import FusedFineStep
         fused = FusedFineStep(model, rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank, sparse_adam=not args.dense_adam,
-                              use_graph=not args.no_graph, dense_exchange=args.dense_exchange)
+                              use_graph=not args.no_graph, dense_exchange=args.dense_exchange, defer_optimizer=not args.no_defer)
         fused.calibrate(*dev_pool[0][:3], global_step=START_STEP, headroom=1.35)
         step_fn = lambda b, gs: fused.step(*b, gs)
         decay = fused.apply_lr_decay
@@ -372,10 +374,13 @@ def main():
     # ---- warm-up: every execution variant (TV / non-TV) run eagerly once and captured BEFORE anything is timed
     if fused is not None:
         gs_next[0] = fused.warm_up(dev_pool, START_STEP)
+        run(max(0, START_STEP + PRE_STEPS - gs_next[0]))     # the timed window starts at the same global step in every configuration
     run(max(args.warmup, 3))
     barrier()
     graph = fused is not None and fused.use_graph
-    execution = {'path': args.path, 'cuda_graph': bool(graph), 'graphs_captured': len(fused._graphs) if graph else 0}
+    execution = {'path': args.path, 'cuda_graph': bool(graph), 'graphs_captured': len(fused._graphs) if graph else 0,
+                 'optimizer': ('deferred: the Adam / regulariser phase of step k runs beside the march of step k + 1 (one optimizer phase per '
+                               'timed step all the same)') if (fused is not None and fused.defer_optimizer) else 'end of step'}
 
     with ClockSampler(local_rank) as clk:
         # ---- device-resident timing
@@ -462,6 +467,7 @@ def main():
         fused.force_eager = False
         probe, fused.bitmap_probe = fused.bitmap_probe, None
     if fused is not None:
+        fused.sync_params()
         fused.poll_overflow(force=True)
     if rank == 0:
         total_rays = rays * world * args.steps

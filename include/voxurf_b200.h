@@ -267,11 +267,11 @@ int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int C, int
                           const float* dX2, float* d_sdf_s, float* d_grad_s, float* sdf_grad, float* k0_grad,
                           uint32_t* k0_touched, cudaStream_t stream);
 /* data-parallel exchange of the k0 gradient as rows: (xyz, scale * dX2[:, 0:C]) per MLP row, zeros past *n_rows_dev;
- * the gathered rows of all ranks are scattered with vx_grid_gather_backward.  Pass k0_grad = NULL to
- * vx_fused_row_backward to skip the local scatter. */
+ * the gathered rows of all ranks are scattered with vx_grid_gather_backward (n_out, optional: the row count, written
+ * next to the rows so that it travels with them).  Pass k0_grad = NULL to vx_fused_row_backward to skip the local scatter. */
 int vx_fused_export_k0_rows(const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
                             float stepdist, const int* idx4, const int* n_rows_dev, int capacity, const float* dX2,
-                            int ld2, int C, float scale, float* xyz_out, float* g_out, cudaStream_t stream);
+                            int ld2, int C, float scale, float* xyz_out, float* g_out, int* n_out, cudaStream_t stream);
 /* NeuS-alpha backward + the 7-tap scatter of every M2 sample into the sdf gradient grid */
 int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
                                 const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,

@@ -48,7 +48,7 @@ def test_benchmarked_shape_follows_the_oracle_trajectory():
     # 16.7 M lattice points through the mask cache: allow a handful of alpha == thres borderline voxels, then share the mask
     assert int((m.nonempty_mask.cpu() != om['nonempty_mask']).sum()) <= 8
     om['nonempty_mask'] = m.nonempty_mask.cpu()
-    fs = FusedFineStep(m, N, FINE_TRAIN, bench.RENDER_KW, use_graph=True)
+    fs = FusedFineStep(m, N, FINE_TRAIN, bench.RENDER_KW, use_graph=True, defer_optimizer=True)   # as bench.py runs it
     pool = bench.ray_pool(3, N, 0)
     dpool = [tuple(t.to(DEV) for t in b) for b in pool]
     fs.calibrate(*dpool[0][:3], global_step=bench.START_STEP, headroom=1.35)
@@ -76,7 +76,7 @@ def test_benchmarked_shape_follows_the_oracle_trajectory():
     del grads, g_prod
 
     # ---- steps 15002..15006 through step(): first occurrences eager, then capture, then replay of both variants
-    for it in range(1, 6):
+    for it in range(1, 8):
         gs = bench.START_STEP + it
         b = it % len(pool)
         loss = fs.step(*dpool[b], gs).clone()
@@ -84,7 +84,8 @@ def test_benchmarked_shape_follows_the_oracle_trajectory():
         rgb = fs.rgb_marched.clone()
         M0, M2, M4 = fs.counts()
         oloss, oret = bench.oracle_bench_step(om, params, lrs, state, pool[b], gs, it + 1, N, G, lr_scale=decay ** it)
-        assert M0 == oret['mask_outbbox'].shape[0] and M2 == int((~oret['mask_outbbox']).sum())
+        # (a sample whose interpolated mask-cache alpha sits exactly on the threshold may fall on either side: GPU vs CPU exp)
+        assert M0 == oret['mask_outbbox'].shape[0] and abs(M2 - int((~oret['mask_outbbox']).sum())) <= 4
         assert abs(M4 - oret['weights'].shape[0]) <= 16, (M4, oret['weights'].shape[0])   # w > 1e-4 borderline samples
         _close(loss, oloss, 1e-4, 1e-7, f'loss {gs}')
         # two trajectories whose fp32 atomics land in different orders: Adam's first steps are sign-like, so a voxel with a
@@ -92,10 +93,11 @@ def test_benchmarked_shape_follows_the_oracle_trajectory():
         d = (rgb.cpu() - oret['rgb_marched'].detach()).abs()
         assert float((d > 1e-4 * oret['rgb_marched'].detach().abs() + 2e-5).float().mean()) < 5e-3 and float(d.max()) < 5e-3, \
             (gs, float((d > 1e-4).float().mean()), float(d.max()))
-    assert len(fs._graphs) == 2 and fs.launches_replayed > 0
+    assert len(fs._graphs) >= 2 and fs.launches_replayed > 0
+    fs.sync_params()          # the last step's deferred optimizer phase
     fs.poll_overflow(force=True)
     # parameters after six steps (Adam's first steps are sign-like: all but a small fraction within a fraction of lr)
     d = (m.sdf.grid.detach().cpu() - om['sdf'].detach()).abs()
-    assert float((d > 2e-2 * 5e-3).float().mean()) < 1e-4 and float(d.max()) <= 6 * 5e-3 * 1.01, (float((d > 1e-4).float().mean()), float(d.max()))
+    assert float((d > 2e-2 * 5e-3).float().mean()) < 1e-4 and float(d.max()) <= 8 * 5e-3 * 1.01, (float((d > 1e-4).float().mean()), float(d.max()))
     d = (m.k0.grid.detach().cpu() - om['k0'].detach()).abs()
     assert float((d > 2e-2 * 1e-1).float().mean()) < 1e-4, float((d > 2e-3).float().mean())

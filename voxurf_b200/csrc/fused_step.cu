@@ -778,8 +778,9 @@ VX_API int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min
 // ---------------------------------------------------------------------------------------------
 __global__ void k_export_k0_rows(VxPts pts, const int* __restrict__ idx4, const int* __restrict__ n_rows_dev, int capacity,
                                  const float* __restrict__ dX2, int ld2, int C, float scale, float* __restrict__ xyz_out,
-                                 float* __restrict__ g_out) {
+                                 float* __restrict__ g_out, int* __restrict__ n_out) {
   const int n = min(*n_rows_dev, capacity);
+  if (n_out && blockIdx.x == 0 && threadIdx.x == 0) *n_out = n;   // travels with the rows: receivers scatter n rows, not `capacity`
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < capacity; row += gridDim.x * blockDim.x) {
     float p[3] = {0.f, 0.f, 0.f};
     if (row < n) vx_load_pt(pts, idx4[row], p[0], p[1], p[2]);
@@ -790,11 +791,11 @@ __global__ void k_export_k0_rows(VxPts pts, const int* __restrict__ idx4, const 
 
 VX_API int vx_fused_export_k0_rows(const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
                                    float stepdist, const int* idx4, const int* n_rows_dev, int capacity, const float* dX2,
-                                   int ld2, int C, float scale, float* xyz_out, float* g_out, cudaStream_t st) {
+                                   int ld2, int C, float scale, float* xyz_out, float* g_out, int* n_out, cudaStream_t st) {
   if (capacity <= 0) return 0;
   const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
   k_export_k0_rows<<<min(vx_blocks(capacity, 256), vx_num_sms() * 8), 256, 0, st>>>(pts, idx4, n_rows_dev, capacity, dX2, ld2, C,
-                                                                                    scale, xyz_out, g_out);
+                                                                                    scale, xyz_out, g_out, n_out);
   return vx_check_launch("vx_fused_export_k0_rows");
 }
 

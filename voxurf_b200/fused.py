@@ -39,7 +39,7 @@ from .optim import _storage
 class FusedFineStep:
     def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0,
                  tensor_core=True, sparse_k0_exchange=True, sparse_adam=True, use_graph=False,
-                 graph_multi_gpu=True, dense_exchange=False):
+                 graph_multi_gpu=True, dense_exchange=False, defer_optimizer=False):
         if model.k0_dim not in (6, 12):
             raise NotImplementedError('fused step: k0 channels must be 6 or 12')
         if model.k_center_sdf or not model.center_sdf or not model.k_res:
@@ -142,6 +142,14 @@ class FusedFineStep:
             self.consts = torch.zeros(16, dtype=torch.float32, device=dev)
             self.in_o, self.in_d, self.in_v, self.in_t = (torch.zeros(n_rays, 3, dtype=torch.float32, device=dev) for _ in range(4))
         self.force_eager = False   # bench.py: launch the kernels of the step one by one even when use_graph is set
+        # defer_optimizer: the regulariser application, the gradient-exchange completion and the Adam passes of step k run at
+        # the START of step k + 1, on a side stream beside that step's ray set-up and march (which read only the rays and the
+        # mask cache, and are issue-bound while the optimizer is bandwidth / atomics-bound), and are joined before the first
+        # read of the sdf grid.  Same arithmetic in the same order; parameters lag one call behind until the next step() or
+        # flush() / sync_params().
+        self.defer_optimizer = bool(defer_optimizer)
+        self._pending = None
+        self._opt_stream = None
         # Slab-sharded data-parallel exchange (SURVEY.md 8e "preferred form"): reduce-scatter of the sdf gradient over X-slabs,
         # regularisers + Adam on the owned slab only, all-gather of the updated sdf PARAMETERS at the start of the next step
         # (it overlaps ray set-up and the march, which read rays and the mask cache only).  Non-owned slabs of this rank's sdf
@@ -149,6 +157,7 @@ class FusedFineStep:
         self.sharded = world > 1 and not dense_exchange and self.X % world == 0 and not m.smooth_sdf
         self._params_dirty = False
         self._ag_work = None
+        self._opt_forked = False
         if self.sharded:
             per = self.X // world * self.Y * self.Z
             self.slab_x = (rank * (self.X // world), (rank + 1) * (self.X // world))
@@ -202,6 +211,7 @@ class FusedFineStep:
              self.bits_in, self.bits_keep, self.keep_count, self.keep_off)
         call('vx_march_emit', self.offsets, N, self.bits_keep, self.keep_off, self.cap2, self.ray_id, self.step_id, None)
         n2 = self.keep_off[N:]
+        self._join_optimizer()          # (defer_optimizer) the previous step's Adam passes ran beside the march
         self._finish_param_gather()     # first read of the sdf grid follows
         if m.smooth_sdf:
             if self.conv_scratch is None:
@@ -251,6 +261,8 @@ class FusedFineStep:
     def render(self, rays_o, rays_d, viewdirs, render_grad=True, render_depth=True):
         """Inference forward (run.py:123-126 calls model(...) per 8192-ray chunk): -> dict of (N, .) tensors.
         Buffers are reused by the next call: clone what you keep."""
+        if not torch.cuda.is_current_stream_capturing():
+            self.flush()
         s_val, n2, n4 = self._forward(rays_o, rays_d, viewdirs, None, train=False)
         if not torch.cuda.is_current_stream_capturing():
             self.poll_overflow()
@@ -345,12 +357,13 @@ class FusedFineStep:
         the scatter of every rank's rows happens in grad_sync()."""
         import torch.distributed as dist
         W, cap, C = self.world, self.cap4, self.C
-        if getattr(self, '_k0_send', None) is None or self._k0_send.numel() != cap * (3 + C):
-            # one buffer per rank: [cap x 3 positions | cap x C gradient rows] -> ONE all-gather
-            self._k0_send = torch.empty(cap * (3 + C), dtype=torch.float32, device=self.dev)
-            self._k0_recv = torch.empty(W, cap * (3 + C), dtype=torch.float32, device=self.dev)
+        if getattr(self, '_k0_send', None) is None or self._k0_send.numel() != cap * (3 + C) + 4:
+            # one buffer per rank: [cap x 3 positions | cap x C gradient rows | row count] -> ONE all-gather
+            self._k0_send = torch.empty(cap * (3 + C) + 4, dtype=torch.float32, device=self.dev)
+            self._k0_recv = torch.empty(W, cap * (3 + C) + 4, dtype=torch.float32, device=self.dev)
         call('vx_fused_export_k0_rows', *self._pts(), self.idx4, n4, cap, self.dX2, self.ld2, C, 1.0 / W,
-             self._k0_send[:cap * 3].view(cap, 3), self._k0_send[cap * 3:].view(cap, C))
+             self._k0_send[:cap * 3].view(cap, 3), self._k0_send[cap * 3:cap * (3 + C)].view(cap, C),
+             self._k0_send[cap * (3 + C):].view(torch.int32))
         self._k0_work = [dist.all_gather_into_tensor(self._k0_recv.view(-1), self._k0_send, async_op=True)]
 
     def _begin_param_gather(self):
@@ -367,7 +380,9 @@ class FusedFineStep:
 
     def sync_params(self):
         """Make this rank's copy of the sdf grid current (sharded step: the slabs other ranks own are stale between a
-        step and the next step's all-gather).  Call before reading parameters: rendering, checkpoints, evaluation."""
+        step and the next step's all-gather; with defer_optimizer the last step's update is still pending).  Call before
+        reading parameters: rendering, checkpoints, evaluation."""
+        self.flush()
         self._begin_param_gather()
         self._finish_param_gather()
 
@@ -403,10 +418,10 @@ class FusedFineStep:
             for w in self._k0_work:
                 w.wait()
             cap, C = self.cap4, self.C
-            for r in range(self.world):      # every rank's rows (zero rows past its count add nothing)
-                xyz, g = self._k0_recv[r, :cap * 3].view(cap, 3), self._k0_recv[r, cap * 3:].view(cap, C)
+            for r in range(self.world):      # every rank's rows, as many as it sent
+                xyz, g = self._k0_recv[r, :cap * 3].view(cap, 3), self._k0_recv[r, cap * 3:cap * (3 + C)].view(cap, C)
                 call('vx_grid_gather_backward', self.X, self.Y, self.Z, self.C, self.k0_cl, m._min_host, m._max_host, xyz, None, None,
-                     None, None, 0.0, None, cap, g, _storage(self.k0_grad), self.k0_touched)
+                     None, None, 0.0, self._k0_recv[r, cap * (3 + C):].view(torch.int32), cap, g, _storage(self.k0_grad), self.k0_touched)
         else:
             dist.all_reduce(_storage(self.k0_grad), op=dist.ReduceOp.AVG)
             if self.k0_touched is not None:
@@ -461,7 +476,7 @@ class FusedFineStep:
         w = c['weight_tv_density'] * tv['smooth_grad_tv'] / (3.0 * m._n_nonempty)
         call('vx_smooth_grad_tv_masked_writes', self.G, m.nonempty_mask[0, 0], X, Y, Z, m._tv_smooth_w, w, self.dG, self.tv_scratch, self.tv_loss)
 
-    def regularise_apply(self, flags, global_batch=None):
+    def regularise_apply(self, flags, global_batch=None, add_loss=True):
         """Second half: the regularisers' gradients land in the sdf gradient (run.py:622-625, 641-655)."""
         c, m = self.cfg, self.m
         is_tv, dense = flags
@@ -469,7 +484,7 @@ class FusedFineStep:
             return
         X, Y, Z = self.X, self.Y, self.Z
         tv = c['tv_terms']
-        if tv['smooth_grad_tv'] > 0:
+        if tv['smooth_grad_tv'] > 0 and add_loss:
             self.loss.add_(self.tv_loss)   # run.py:622-625 adds the regulariser to the reported loss
         n_batch = global_batch or self.N * self.world
         wt = c['weight_tv_density'] * tv['sdf_tv'] / n_batch * max(X, Y, Z) / 128
@@ -503,17 +518,21 @@ class FusedFineStep:
         self.regularise_apply(flags, global_batch)
 
     @torch.no_grad()
-    def optimizer_step(self, only=None, advance=True):
+    def optimizer_step(self, only=None, advance=True, step=None, lrs=None):
         """lib/utils.py:83-199 with betas (0.9, 0.99), eps 1e-8 (lib/utils.py:229); grads are zeroed in the same pass.
-        only: restrict to these group names (the multi-GPU step updates k0 while the sdf all-reduce is in flight)."""
-        if advance and self._dev_consts is None:
-            self.adam_steps += 1
-        step, beta1, beta2, eps = max(self.adam_steps, 1), 0.9, 0.99, 1e-8
+        only: restrict to these group names (the multi-GPU step updates k0 while the sdf all-reduce is in flight).
+        step / lrs: the Adam step number and learning rates to apply (default: advance the counter, current rates)."""
+        if step is None:
+            if advance and self._dev_consts is None:
+                self.adam_steps += 1
+            step = max(self.adam_steps, 1)
+        lrs = lrs if lrs is not None else self.lr
+        beta1, beta2, eps = 0.9, 0.99, 1e-8
         bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
         for gi, (name, params, _) in enumerate(self.groups):
             if only is not None and name not in only:
                 continue
-            lr = self.lr[name]
+            lr = lrs[name]
             for p in params:
                 st = self.adam_state.get(id(p))
                 if st is None:
@@ -549,6 +568,7 @@ class FusedFineStep:
         group, step count, decayed learning rates, the k0 `live` bitmap.  Mirrors what run.py:786-793 saves as
         optimizer_state_dict."""
         self.sync_s_val()
+        self.flush()
         if self.sharded:      # every rank saves the full sdf parameters and moments
             import torch.distributed as dist
             self.sync_params()
@@ -584,18 +604,18 @@ class FusedFineStep:
         self.m._refresh_derived()
 
     def warm_up(self, batches, global_step):
-        """Run real training steps from `global_step` until every execution variant of the step (TV / non-TV iteration)
-        has had its eager first occurrence and -- with use_graph -- its CUDA graph captured, so that later steps are
-        pure replays.  `batches`: list of (rays_o, rays_d, viewdirs, target).  Returns the next global_step."""
-        c = self.cfg
-        want = {self.tv_flags(global_step + i) for i in range(2 * max(1, c['tv_every']) + 2)}
-        done = (lambda: set(self._graphs) >= want) if self.use_graph else (lambda: self._eager_seen >= want)
+        """Run real training steps from `global_step` until every execution variant of the step (TV / non-TV iteration,
+        and with defer_optimizer the variant of the preceding step) has had its eager first occurrence and -- with
+        use_graph -- its CUDA graph captured, so that later steps are pure replays.  `batches`: list of
+        (rays_o, rays_d, viewdirs, target).  Returns the next global_step."""
+        n_look = 3 * max(1, self.cfg['tv_every']) + 2
+        fl = [self.tv_flags(global_step + i) for i in range(1, n_look)]
+        want = {(b, a if self.defer_optimizer else None) for a, b in zip(fl[:-1], fl[1:])}
+        if not self.defer_optimizer:
+            want = {(f, None) for f in fl}
         i = 0
-        while not done() and i < 8 * max(1, c['tv_every']):
-            b = batches[i % len(batches)]
-            if not self.use_graph:
-                self._eager_seen.add(self.tv_flags(global_step + i))
-            self.step(*b, global_step + i)
+        while not (set(self._graphs) >= want if self.use_graph else i >= 2) and i < 8 * max(1, self.cfg['tv_every']):
+            self.step(*batches[i % len(batches)], global_step + i)
             i += 1
         return global_step + i
 
@@ -610,63 +630,107 @@ class FusedFineStep:
         for k in self.lr:
             self.lr[k] *= f
 
-    def _step_body(self, rays_o, rays_d, viewdirs, target, global_step, flags):
+    def _optimizer_phase(self, pend):
+        """Everything between a step's backward pass and the next forward: completion of the gradient exchange, the k0
+        row re-scatter, the regularisers' gradients, the Adam passes (run.py:641-659).  pend: dict(flags, step, lrs)."""
+        flags, kw = pend['flags'], dict(step=pend['step'], lrs=pend['lrs'])
+        if self.world > 1:
+            self._sync_k0()
+            self.optimizer_step(only=('k0',), **kw)
+            self._sync_end()
+            self.regularise_apply(flags, add_loss=False)
+            self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet'), **kw)
+        else:
+            self.regularise_apply(flags, add_loss=False)
+            self.optimizer_step(**kw)
+
+    def flush(self):
+        """Apply a deferred optimizer phase now (defer_optimizer=True): call before reading parameters."""
+        if self._pending is not None:
+            pend, self._pending = self._pending, None
+            self._optimizer_phase(pend)
+
+    def _join_optimizer(self):
+        """forward pass, right before the first read of a parameter: the deferred optimizer phase must be complete"""
+        if self._opt_forked:
+            torch.cuda.current_stream().wait_stream(self._opt_stream)
+            self._opt_forked = False
+
+    def _step_body(self, rays_o, rays_d, viewdirs, target, global_step, flags, pend_in='own'):
+        """pend_in: the optimizer phase to run at the start of this step ('own': whatever self._pending holds)."""
         if self.sharded and not self._slab_covers(flags):
+            self.flush()
             self.unshard()      # e.g. sparse TV after tv_dense_before: back to the dense exchange, full optimizer state everywhere
-        if flags[0] and self.tensor_core:
+        if pend_in == 'own':
+            pend_in, self._pending = self._pending, None
+        main = torch.cuda.current_stream()
+        if self._dw_stream is None:
+            self._dw_stream = torch.cuda.Stream(device=self.dev)
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream(device=self.dev)
+        self._opt_forked = False
+        if pend_in is not None:
+            # the previous step's optimizer phase, beside this step's ray set-up and march
+            self._opt_stream.wait_stream(main)
+            with torch.cuda.stream(self._opt_stream):
+                self._optimizer_phase(pend_in)
+                self._begin_param_gather()       # (sharded) the all-gather of the updated slabs follows the Adam pass
+            self._opt_forked = True
+        early_tv = bool(flags[0] and self.tensor_core)
+        if early_tv:
             # the first half of the TV regulariser depends on the parameters only: it runs on the side stream (ahead of
             # the weight-gradient launch that is forked onto the same stream later) beside the forward / backward pass
-            if self._dw_stream is None:
-                self._dw_stream = torch.cuda.Stream(device=self.dev)
             self._begin_param_gather()
-            self._dw_stream.wait_stream(torch.cuda.current_stream())
+            self._dw_stream.wait_stream(main)
+            if pend_in is not None:
+                self._dw_stream.wait_stream(self._opt_stream)      # ... on the UPDATED parameters
             with torch.cuda.stream(self._dw_stream):
                 if self._ag_work is not None:
                     self._ag_work.wait()     # the FD gradient reads the whole sdf grid
                 self.regularise_prepare(flags)
-            early_tv = True
-        else:
-            early_tv = False
         loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
-        if early_tv:     # forward_backward joined the side stream at its end
-            reg = lambda: self.regularise_apply(flags)
-        else:
-            reg = lambda: self.regularise(global_step, flags=flags)
+        if not early_tv:
+            self.regularise_prepare(flags)
+        if flags[0] and self.cfg['tv_terms']['smooth_grad_tv'] > 0:
+            self.loss.add_(self.tv_loss)   # run.py:622-625 adds the regulariser to the reported loss
         if self.world > 1:
-            # overlap: the sdf reduce-scatter (or all-reduce) and the MLP all-reduces run on the NCCL stream while k0 is
-            # re-scattered and updated
-            self._sync_begin()
-            self._sync_k0()
-            self.optimizer_step(only=('k0',))
-            self._sync_end()
-            reg()
-            self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet'), advance=False)
-            return loss
-        reg()
-        self.optimizer_step()
+            self._sync_begin()       # the sdf reduce-scatter (or all-reduce) and the MLP all-reduce start right after the backward pass
+        if self._dev_consts is None:
+            self.adam_steps += 1
+        pend = dict(flags=flags, step=max(self.adam_steps, 1), lrs=dict(self.lr))
+        if self.defer_optimizer:
+            self._pending = pend
+        else:
+            self._optimizer_phase(pend)
         return loss
 
     def _step_graph(self, rays_o, rays_d, viewdirs, target, global_step):
-        """The same step as one CUDA-graph launch.  Per (TV iteration?, dense TV?) variant: the first occurrence runs
-        eagerly (lazy allocations, kernel attributes), the second is captured, later ones are replayed.  Host side per
-        step: the NeuS schedule and the Adam scalars (a 64-byte upload) and one fused copy of the batch into the static
-        input buffers."""
+        """The same step as one CUDA-graph launch.  Per variant -- (TV iteration?, dense TV?) of this step and, with
+        defer_optimizer, of the step whose optimizer phase runs inside this launch -- the first occurrence runs eagerly
+        (lazy allocations, kernel attributes), the second is captured, later ones are replayed.  Host side per step: the
+        NeuS schedule and the Adam scalars (a 64-byte upload) and one fused copy of the batch into the static input buffers."""
         m = self.m
         flags = self.tv_flags(global_step)
-        if flags not in self._eager_seen:
-            self._eager_seen.add(flags)
+        pend_in = self._pending
+        key = (flags, pend_in['flags'] if pend_in is not None else None)
+        if key not in self._eager_seen:
+            self._eager_seen.add(key)
             return self._step_body(rays_o, rays_d, viewdirs, target, global_step, flags)
         s_val = 1. / (global_step + m.s_ratio / m.s_start - m.step_start) * m.s_ratio          # lib/voxurf_fine.py:466-473
         m._s_val_host = float(np.float32(s_val))
         self.adam_steps += 1
-        step, beta1, beta2 = self.adam_steps, 0.9, 0.99
-        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        cur = dict(flags=flags, step=self.adam_steps, lrs=dict(self.lr))
+        opt = pend_in if self.defer_optimizer else cur      # the optimizer phase that executes inside this launch
         host = [float(np.float32(1.0) / np.float32(m._s_val_host)), 0.0]
         for name, _, _ in self.groups:
-            host += [self.lr[name] / bc1, math.sqrt(bc2)]
+            if opt is None:
+                host += [0.0, 1.0]
+            else:
+                bc1, bc2 = 1 - 0.9 ** opt['step'], 1 - 0.99 ** opt['step']
+                host += [opt['lrs'][name] / bc1, math.sqrt(bc2)]
         self.consts[:len(host)].copy_(torch.tensor(host, dtype=torch.float32))
         torch._foreach_copy_([self.in_o, self.in_d, self.in_v, self.in_t], [rays_o, rays_d, viewdirs, target])
-        g = self._graphs.get(flags)
+        g = self._graphs.get(key)
         if g is None:
             assert self.timings is None and self.bitmap_probe is None, 'kernel timing hooks need use_graph=False'
             self._dev_consts = self.consts
@@ -675,14 +739,15 @@ class FusedFineStep:
             l0 = launch_count()
             try:
                 with torch.cuda.graph(g):
-                    self._step_body(self.in_o, self.in_d, self.in_v, self.in_t, None, flags)
+                    self._step_body(self.in_o, self.in_d, self.in_v, self.in_t, None, flags, pend_in=pend_in)
             finally:
                 self._dev_consts = None
-            self._graphs[flags] = g
-            self._graph_launches[flags] = launch_count() - l0
+            self._graphs[key] = g
+            self._graph_launches[key] = launch_count() - l0
         g.replay()
+        self._pending = cur if self.defer_optimizer else None
         self._params_dirty = self.sharded      # (host flags do not move during a replay)
-        self.launches_replayed += self._graph_launches[flags]
+        self.launches_replayed += self._graph_launches[key]
         return self.loss
 
     @torch.no_grad()
@@ -695,7 +760,7 @@ class FusedFineStep:
         import copy
         import torch.distributed as dist
         W, m = self.world, self.m
-        self.sync_params()
+        self.sync_params()      # (also applies a deferred optimizer phase)
         sums = torch.stack([m.sdf.grid.double().sum(), m.sdf.grid.double().abs().sum(), self.mlp1.flat.double().sum(),
                             self.mlp2.flat.double().sum(), _storage(m.k0.grid).double().sum()])
         allsums = [torch.zeros_like(sums) for _ in range(W)]
@@ -793,7 +858,7 @@ class FusedFineStep:
     def _step(self, rays_o, rays_d, viewdirs, target, global_step, grad_sync=None):
         if self.use_graph and grad_sync is None and self.timings is None and self.bitmap_probe is None and not self.force_eager:
             return self._step_graph(rays_o, rays_d, viewdirs, target, global_step)
-        if grad_sync is None and self.world > 1:
+        if grad_sync is None:
             return self._step_body(rays_o, rays_d, viewdirs, target, global_step, self.tv_flags(global_step))
         loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
         if grad_sync is not None:
@@ -813,6 +878,7 @@ class FusedFineStep:
         """Size the row buffers from one forward of a representative batch (one-off sync).  Pass the global_step the
         run is at: the NeuS sharpness s_val (and with it the number of MLP rows) depends on it."""
         self.overflow.zero_()
+        self.flush()
         with torch.no_grad():
             self._forward(rays_o, rays_d, viewdirs, global_step, train=False)
         v = torch.stack([self.off4[self.N], self.overflow[0]]).cpu()
