@@ -143,14 +143,14 @@ int vx_sdf_lattice(const float* grid, int X, int Y, int Z, const float* xyz_min_
                    const float* xs, const float* ys, const float* zs, int nx, int ny, int nz, float voxel_size,
                    int negate, float* out_u, float* out_grad, cudaStream_t stream);
 /* neus_alpha_from_sdf_scatter  lib/voxurf_fine.py:463-500 (== lib/voxurf_coarse.py:348-382); give ray_id (int32)
- * or ray_id64 */
+ * or ray_id64; inv_s_dev (optional): 1/s read from device memory instead of the scalar (CUDA-graph replays) */
 int vx_neus_alpha(const float* viewdirs, const int* ray_id, const int64_t* ray_id64, const float* sdf,
                   const float* gradient, float dist, float inv_s, const int* n_dev, int64_t n_host, float* alpha,
-                  cudaStream_t stream);
+                  const float* inv_s_dev, cudaStream_t stream);
 int vx_neus_alpha_backward(const float* viewdirs, const int* ray_id, const int64_t* ray_id64, const float* sdf,
                            const float* gradient, float dist, float inv_s, const int* n_dev, int64_t n_host,
                            const float* grad_alpha, int accumulate, float* grad_sdf, float* grad_gradient,
-                           cudaStream_t stream);
+                           const float* inv_s_dev, cudaStream_t stream);
 
 /* ---- grid-level stencils ------------------------------------------------------------------- */
 /* neus_sdf_gradient('interpolate')  lib/voxurf_fine.py:440-460 ; grad is (3,X,Y,Z); backward accumulates */
@@ -214,6 +214,9 @@ int vx_points_from_steps(const int* ray_id, const int* step_id, const float* ray
                          float stepdist, const int* n_dev, int64_t n_host, float* out, cudaStream_t stream);
 /* alpha2weight over int32 per-ray segments with an optional keep flag (alpha > thres filter applied in place,
  * lib/voxurf_fine.py:647-654) and weight > thres flags / per-ray counts (lib/voxurf_fine.py:668-676) */
+/* ub360_utils_cuda.cumdist_thres(dist (n_rays, n_pts), thres) -> bool mask (lib/cuda/ub360_utils.cpp:17-25, kernel
+ * ub360_utils_kernel.cu:13-33): running distance per ray, restarted where it exceeds thres; bit-identical */
+int vx_cumdist_thres(const float* dist, float thres, int n_rays, int n_pts, bool* mask, cudaStream_t stream);
 int vx_alpha2weight_seg(const float* alpha, const uint8_t* keep, const int* seg_off, int n_rays, float w_thres,
                         float* weight, float* T, float* alphainv_last, int* i_end, uint8_t* w_keep, int* w_count,
                         cudaStream_t stream);
@@ -281,6 +284,29 @@ int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min_host, 
                                 const float* inv_s_dev, cudaStream_t stream);
 
 /* ---- tensor-core MLP (tcgen05, TF32x3 split; lib/voxurf_fine.py:132-187,718,749) ---------------------------- */
+/* ---- fused coarse-stage step (lib/voxurf_coarse.py:513-619; csrc/coarse_step.cu) ---------------------------------- */
+/* MLP input rows [k0 C | xyz 3 | sin 3P | cos 3P | view 3 | sin 3V | cos 3V | normal 3], normal = gradient / (|gradient| + 1e-5)
+ * (lib/voxurf_coarse.py:552-571); rows past *n_rows_dev are zero-filled */
+int vx_coarse_row_features(const float* k0_grid, int X, int Y, int Z, int C, int k0_channels_last,
+                           const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
+                           const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
+                           const int* n_rows_dev, int capacity, const float* viewdirs, const float* grad_s, int P, int V,
+                           int ld, float* Xrows, cudaStream_t stream);
+/* its backward: k0 scatter, and the normal's adjoint ADDED to d_grad_s of each row's sample */
+int vx_coarse_row_backward(int X, int Y, int Z, int C, int k0_channels_last, const float* xyz_min_host,
+                           const float* xyz_max_host, const int* ray_id, const int* step_id, const float* rays_start,
+                           const float* rays_dir, float stepdist, const int* idx4, const int* n_rows_dev, int capacity,
+                           const float* grad_s, int P, int V, int ld, const float* dX, float* d_grad_s, float* k0_grad,
+                           cudaStream_t stream);
+/* rgb_marched = clamp(sum w sigmoid(logit) + (1 - sum w) bg, 0, 1), mse + last-ray entropy, and their backward
+ * (lib/voxurf_coarse.py:573-583, run.py:604-610) */
+int vx_coarse_composite_loss(const float* logit, int ld_out, const int* idx4, const int* off4, int capacity,
+                             const float* weight_s, const float* alphainv_last, const float* target, int n_rays,
+                             float w_main, float w_ent, float ent_scale, float bg, int train, float* rgb_marched,
+                             float* d_logit, float* d_w_s, float* d_last, float* loss_ray, cudaStream_t stream);
+/* y += a * x */
+int vx_axpy(const float* x, float a, int64_t n, float* y, cudaStream_t stream);
+
 /* "chunked K-major image" CH(F): IMG[(k/4)*F + f][k%4] -- the UMMA K-major no-swizzle operand layout; a K=32 slice is one
  * contiguous block, fetched with one bulk copy.  vx_mlp_prep writes the hi/lo weight images (k = input feature), zero padded
  * to (Np, Kp), optionally of the transposed matrix (dX chain). */

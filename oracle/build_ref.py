@@ -20,6 +20,7 @@ MODULES = {
     'render_utils_cuda': ['render_utils.cpp', 'render_utils_kernel.cu'],
     'total_variation_cuda': ['total_variation.cpp', 'total_variation_kernel.cu'],
     'adam_upd_cuda': ['adam_upd.cpp', 'adam_upd_kernel.cu'],
+    'ub360_utils_cuda': ['ub360_utils.cpp', 'ub360_utils_kernel.cu'],
 }
 
 

@@ -174,3 +174,11 @@ def adam_upd(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, eps, mode
         assert t.is_contiguous() and t.dtype == torch.float32
     lib().vxo_adam_upd(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(perlr), ctypes.c_int64(param.numel()),
                        ctypes.c_int(step), _f(beta1), _f(beta2), _f(lr), _f(eps), ctypes.c_int(mode))
+
+
+def cumdist_thres(dist, thres):
+    """ub360_utils_kernel.cu:13-47 -> bool (n_rays, n_pts)"""
+    dist = dist.contiguous().float()
+    mask = torch.zeros(dist.shape, dtype=torch.uint8)
+    lib().vxo_cumdist_thres(_p(dist), ctypes.c_float(thres), ctypes.c_int(dist.shape[0]), ctypes.c_int(dist.shape[1]), _p(mask))
+    return mask.bool()

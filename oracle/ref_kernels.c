@@ -269,3 +269,16 @@ VX_EXPORT void vxo_adam_upd(float* param, const float* grad, float* exp_avg, flo
     param[i] -= s * exp_avg[i] / (sqrtf(exp_avg_sq[i]) + eps);
   }
 }
+
+/* ---- cumdist_thres: ub360_utils_kernel.cu:13-33 -------------------------------------------- */
+VX_EXPORT void vxo_cumdist_thres(const float* dist, float thres, int n_rays, int n_pts, unsigned char* mask) {
+  for (int r = 0; r < n_rays; ++r) {
+    float cum_dist = 0;
+    for (int64_t i = (int64_t)r * n_pts; i < (int64_t)(r + 1) * n_pts; ++i) {
+      cum_dist += dist[i];
+      const int over = (cum_dist > thres);
+      cum_dist *= (float)(!over);
+      mask[i] = (unsigned char)over;
+    }
+  }
+}

@@ -57,8 +57,9 @@ class _Anything(types.ModuleType):
         return None
 
 
-def load_lib(backend):
-    """-> namespace with the reference modules voxurf_fine, voxurf_coarse, grid, utils imported against `backend`."""
+def load_lib(backend, extra=()):
+    """-> namespace with the reference modules voxurf_fine, voxurf_coarse, grid, utils (+ `extra`, e.g.
+    voxurf_womask_fine) imported against `backend`."""
     assert backend in ('ref', 'b200')
     assert available(), 'baseline/_ref/lib is missing: run __graft_entry__.build() in the build container'
     for name in ['cv2', 'matplotlib', 'matplotlib.pyplot', 'matplotlib.cm', 'mcubes', 'plyfile', 'imageio', 'skimage', 'skimage.measure',
@@ -76,10 +77,11 @@ def load_lib(backend):
         from oracle import build_ref
         mods = {n: build_ref.load_ref(n) for n in ('render_utils_cuda', 'total_variation_cuda')}
         assert all(m is not None for m in mods.values()), 'oracle/_ref/*.so missing: run oracle/build_ref.py in the build container'
+        mods['ub360_utils_cuda'] = build_ref.load_ref('ub360_utils_cuda')     # only the womask models load it
     else:
-        from voxurf_b200 import render_utils_cuda, total_variation_cuda, torch_scatter
+        from voxurf_b200 import render_utils_cuda, total_variation_cuda, torch_scatter, ub360_utils_cuda
         ts.segment_coo = torch_scatter.segment_coo
-        mods = {'render_utils_cuda': render_utils_cuda, 'total_variation_cuda': total_variation_cuda}
+        mods = {'render_utils_cuda': render_utils_cuda, 'total_variation_cuda': total_variation_cuda, 'ub360_utils_cuda': ub360_utils_cuda}
     saved_ts = sys.modules.get('torch_scatter')
     sys.modules['torch_scatter'] = ts
     import torch.utils.cpp_extension as ce
@@ -90,7 +92,7 @@ def load_lib(backend):
     sys.path.insert(0, REF_COPY)
     try:
         ns = types.SimpleNamespace(backend=backend)
-        for m in ('grid', 'utils', 'dvgo_ori', 'voxurf_fine', 'voxurf_coarse'):
+        for m in ('grid', 'utils', 'dvgo_ori', 'voxurf_fine', 'voxurf_coarse') + tuple(extra):
             setattr(ns, m, importlib.import_module('lib.' + m))
     finally:
         sys.path.remove(REF_COPY)

@@ -161,3 +161,71 @@ def test_fused_step_cuda_graph_replay_matches_eager(defer):
         close_mostly(lb_.weight, la_.weight, 5e-2 * lr['lrate_rgbnet'], 2 * lr['lrate_rgbnet'], 'rgbnet W', max_frac=1e-3)
     fb.sync_s_val()
     close(mb.s_val, ma.s_val, 1e-6, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused coarse-stage step (voxurf_b200.fused_coarse.FusedCoarseStep; lib/voxurf_coarse.py:513-619, BASELINE config 2)
+# ------------------------------------------------------------------------------------------------
+def _coarse_oracle_loss(om, oret, target, c):
+    import torch.nn.functional as F
+    loss = c['weight_main'] * F.mse_loss(oret['rgb_marched'], target)
+    pout = oret['alphainv_cum'][..., -1].clamp(1e-6, 1 - 1e-6)
+    loss = loss + c['weight_entropy_last'] * (-(pout * torch.log(pout) + (1 - pout) * torch.log(1 - pout)).mean())
+    tv = c['tv_terms']
+    reg = c['weight_tv_density'] * R.smooth_grad_tv(oret['_full_gradient'], om['nonempty_mask'], tv['smooth_grad_tv'])
+    reg = reg + c['weight_tv_density'] * (R.total_variation_coarse(om['sdf'], om['nonempty_mask']) / 2 / om['voxel_size'] * tv['sdf_tv'])
+    reg = reg + c['weight_tv_k0'] * R.total_variation_coarse(om['k0'], om['nonempty_mask'].repeat(1, om['k0'].shape[1], 1, 1, 1))
+    return loss, reg
+
+
+@pytest.mark.parametrize('G,n_rays,bg', [(48, 1024, 0.0), (32, 300, 1.0)])
+def test_fused_coarse_step_matches_oracle(G, n_rays, bg):
+    from tests.helpers import oracle_coarse_model, product_coarse_model
+    from voxurf_b200.fused_coarse import FusedCoarseStep
+    from voxurf_b200.trainer import COARSE_TRAIN
+    sc = S.make_coarse_scene(G, 12, 128, seed=G)
+    m = product_coarse_model(sc)
+    om = oracle_coarse_model(sc)
+    ro, rd, vd = (T(x) for x in S.make_rays(n_rays, seed=G + 1))
+    target = T(S.make_target(vd.numpy()))
+    rk = dict(RK, bg=bg)
+    fs = FusedCoarseStep(m, n_rays, COARSE_TRAIN, rk, row_capacity=8192)
+    step = 1200
+    fs.calibrate(ro.to(DEV), rd.to(DEV), vd.to(DEV), global_step=step)
+    loss = fs.forward_backward(ro.to(DEV), rd.to(DEV), vd.to(DEV), target.to(DEV), step).clone()
+    oret = R.coarse_forward(om, ro, rd, vd, step, near=0.3, stepsize=0.5, bg=bg)
+    oloss, oreg = _coarse_oracle_loss(om, oret, target, COARSE_TRAIN)
+    M0, M2, M4 = fs.counts()
+    assert M0 == oret['mask_outbbox'].shape[0] and M2 == int((~oret['mask_outbbox']).sum()) and M4 == oret['weights'].shape[0]
+    close(loss, oloss, 1e-5, 1e-7)
+    close(fs.rgb_marched, oret['rgb_marched'], 1e-5, 3e-6); close(fs.alphainv_last, oret['alphainv_cum'], 1e-5, 1e-6)
+    fs.regularise(step)
+    close(fs.loss, oloss + oreg, 1e-5, 1e-7)
+    (oloss + oreg).backward()
+    grad_close(m.sdf.grid.grad, om['sdf'].grad, 'grad_sdf'); grad_close(m.k0.grid.grad, om['k0'].grad, 'grad_k0')
+    for l, (W, b) in zip(fs.mlp.linears, om['rgbnet']):
+        grad_close(l.weight.grad, W.grad, 'W'); grad_close(l.bias.grad, b.grad, 'b')
+
+
+def test_fused_coarse_graph_replay_matches_dropin_path():
+    """Six iterations: the CUDA-graph replayed fused coarse step against the drop-in autograd model + Trainer."""
+    from tests.helpers import product_coarse_model
+    from voxurf_b200.fused_coarse import FusedCoarseStep
+    from voxurf_b200.trainer import COARSE_TRAIN, Trainer
+    sc = S.make_coarse_scene(40, 12, 128, seed=7)
+    ma, mb = product_coarse_model(sc), product_coarse_model(sc)
+    n_rays = 512
+    tr = Trainer(ma, COARSE_TRAIN, RK, zero_grad_in_step=False)
+    fs = FusedCoarseStep(mb, n_rays, COARSE_TRAIN, RK, row_capacity=16384, use_graph=True)
+    for it in range(6):
+        step = 1201 + it
+        ro, rd, vd = (T(x).to(DEV) for x in S.make_rays(n_rays, seed=400 + it))
+        target = T(S.make_target(vd.cpu().numpy(), seed=it)).to(DEV)
+        la, _ = tr.step(ro, rd, vd, target, step)
+        lb = fs.step(ro, rd, vd, target, step).clone()
+        close(lb, la, 2e-5, 1e-7, f'loss step {step}')
+        fs.counts()
+    assert fs._graph is not None and fs.launches_replayed > 0
+    lr = COARSE_TRAIN
+    close_mostly(mb.sdf.grid, ma.sdf.grid, 2e-2 * lr['lrate_sdf'], 6 * lr['lrate_sdf'], 'sdf', max_frac=1e-3)
+    close_mostly(mb.k0.grid, ma.k0.grid, 2e-2 * lr['lrate_k0'], 6 * lr['lrate_k0'], 'k0', max_frac=1e-3)

@@ -460,3 +460,22 @@ def test_separable_conv_matches_generic_conv(k, sigma):
         scratch = torch.empty(2 * x.numel(), device=DEV)
         call('vx_conv3d_replicate_separable', go, B, X, Y, Z, sc.weight1d_host, k, 1, 1, scratch, acc)
         close(acc - base, xa.grad, 1e-5, 2e-6)
+
+
+@pytest.mark.parametrize('n_rays,n_pts', [(1, 1), (77, 33), (1000, 257), (8192, 64)])
+def test_cumdist_thres_bit_exact(n_rays, n_pts):
+    """ub360_utils_cuda.cumdist_thres (lib/cuda/ub360_utils_kernel.cu:13-47): warp-per-ray here, thread-per-ray there, same
+    float additions in the same order -> identical masks (C oracle; the reference's compiled kernel when present)."""
+    from voxurf_b200 import ub360_utils_cuda as ub
+    rs = np.random.RandomState(n_rays + n_pts)
+    dist = T(np.abs(rs.standard_normal((n_rays, n_pts))).astype(np.float32) * 0.01)
+    dist[0, 0] = 10.0
+    thres = 0.02
+    out = ub.cumdist_thres(dist.cuda(), thres)
+    ref = K.cumdist_thres(dist, thres)
+    assert out.dtype == torch.bool and torch.equal(out.cpu(), ref)
+    assert 0 < int(ref.sum()) < ref.numel() or n_pts == 1
+    from oracle import build_ref
+    mod = build_ref.load_ref('ub360_utils_cuda')
+    if mod is not None:
+        assert torch.equal(mod.cumdist_thres(dist.cuda(), thres), out)

@@ -435,8 +435,9 @@ VX_API int vx_sdf_lattice(const float* grid, int X, int Y, int Z, const float* x
 __global__ void k_neus_alpha(const float* __restrict__ viewdirs, const int* __restrict__ ray_id,
                              const int64_t* __restrict__ ray_id64, const float* __restrict__ sdf,
                              const float* __restrict__ gradient, float dist, float inv_s, const int* __restrict__ n_dev,
-                             int64_t n_host, float* __restrict__ alpha) {
+                             int64_t n_host, float* __restrict__ alpha, const float* __restrict__ inv_s_dev) {
   const int64_t n = vx_count(n_dev, n_host);
+  if (inv_s_dev) inv_s = __ldg(inv_s_dev);     // CUDA-graph replays: the step-dependent 1/s lives in device memory
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = ray_id ? (int64_t)ray_id[i] : ray_id64[i];
     const float gx = gradient[3 * i], gy = gradient[3 * i + 1], gz = gradient[3 * i + 2];
@@ -455,8 +456,10 @@ __global__ void k_neus_alpha_bwd(const float* __restrict__ viewdirs, const int* 
                                  const int64_t* __restrict__ ray_id64, const float* __restrict__ sdf,
                                  const float* __restrict__ gradient, float dist, float inv_s,
                                  const int* __restrict__ n_dev, int64_t n_host, const float* __restrict__ grad_alpha,
-                                 int accumulate, float* __restrict__ grad_sdf, float* __restrict__ grad_gradient) {
+                                 int accumulate, float* __restrict__ grad_sdf, float* __restrict__ grad_gradient,
+                                 const float* __restrict__ inv_s_dev) {
   const int64_t n = vx_count(n_dev, n_host);
+  if (inv_s_dev) inv_s = __ldg(inv_s_dev);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float ga = grad_alpha[i];
     float ds = 0.f, dgx = 0.f, dgy = 0.f, dgz = 0.f;
@@ -496,24 +499,24 @@ __global__ void k_neus_alpha_bwd(const float* __restrict__ viewdirs, const int* 
 }
 
 VX_API int vx_neus_alpha(const float* viewdirs, const int* ray_id, const int64_t* ray_id64, const float* sdf,
-                         const float* gradient, float dist, float inv_s, const int* n_dev, int64_t n_host, float* alpha,
+                         const float* gradient, float dist, float inv_s, const int* n_dev, int64_t n_host, float* alpha, const float* inv_s_dev,
                          cudaStream_t st) {
   if (!n_dev && n_host <= 0) return 0;
   VX_REQUIRE((ray_id != nullptr) != (ray_id64 != nullptr), "vx_neus_alpha", "give exactly one of ray_id / ray_id64");
   k_neus_alpha<<<launch_blocks(n_dev, n_host), 256, 0, st>>>(viewdirs, ray_id, ray_id64, sdf, gradient, dist, inv_s, n_dev,
-                                                             n_host, alpha);
+                                                             n_host, alpha, inv_s_dev);
   return vx_check_launch("vx_neus_alpha");
 }
 
 VX_API int vx_neus_alpha_backward(const float* viewdirs, const int* ray_id, const int64_t* ray_id64, const float* sdf,
                                   const float* gradient, float dist, float inv_s, const int* n_dev, int64_t n_host,
                                   const float* grad_alpha, int accumulate, float* grad_sdf, float* grad_gradient,
-                                  cudaStream_t st) {
+                                  const float* inv_s_dev, cudaStream_t st) {
   if (!n_dev && n_host <= 0) return 0;
   VX_REQUIRE((ray_id != nullptr) != (ray_id64 != nullptr), "vx_neus_alpha_backward", "give exactly one of ray_id / ray_id64");
   k_neus_alpha_bwd<<<launch_blocks(n_dev, n_host), 256, 0, st>>>(viewdirs, ray_id, ray_id64, sdf, gradient, dist, inv_s,
                                                                  n_dev, n_host, grad_alpha, accumulate, grad_sdf,
-                                                                 grad_gradient);
+                                                                 grad_gradient, inv_s_dev);
   return vx_check_launch("vx_neus_alpha_backward");
 }
 

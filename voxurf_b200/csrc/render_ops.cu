@@ -273,3 +273,40 @@ VX_API int vx_alpha2weight_seg_backward(const float* alpha, const float* weight,
                                              grad_last, grad);
   return vx_check_launch("vx_alpha2weight_seg_backward");
 }
+
+// ---------------------------------------------------------------------------------------------
+// cumdist_thres (lib/cuda/ub360_utils_kernel.cu:13-47, the one native op of the unbounded "womask" models,
+// lib/voxurf_womask_fine.py:867): per ray, walk the inter-sample distances, mark a sample when the running distance
+// exceeds `thres`, and restart the running distance there.  The reference runs one THREAD per ray (strided, uncoalesced
+// reads); here one WARP per ray reads 32 consecutive distances at a time and replays the recurrence in lock-step from
+// shuffled values -- the same float additions in the same order, so the mask is bit-identical.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_cumdist_thres(const float* __restrict__ dist, float thres, int n_rays, int n_pts, bool* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * warps_per_block) {
+    const float* d = dist + (int64_t)r * n_pts;
+    bool* m = mask + (int64_t)r * n_pts;
+    float cum = 0.f;
+    for (int base = 0; base < n_pts; base += 32) {
+      const int i = base + lane;
+      const float v = (i < n_pts) ? __ldg(d + i) : 0.f;
+      bool mine = false;
+      const int n = min(32, n_pts - base);
+      for (int j = 0; j < n; ++j) {
+        cum += __shfl_sync(0xffffffffu, v, j);
+        const bool over = cum > thres;
+        if (over) cum = 0.f;          // cum_dist *= float(!over)
+        if (j == lane) mine = over;
+      }
+      if (i < n_pts) m[i] = mine;
+    }
+  }
+}
+
+VX_API int vx_cumdist_thres(const float* dist, float thres, int n_rays, int n_pts, bool* mask, cudaStream_t st) {
+  if (n_rays <= 0 || n_pts <= 0) return 0;
+  VX_REQUIRE(dist && mask, "vx_cumdist_thres", "null pointer");
+  k_cumdist_thres<<<min(vx_blocks((int64_t)n_rays * 32, 256), vx_num_sms() * 16), 256, 0, st>>>(dist, thres, n_rays, n_pts, mask);
+  return vx_check_launch("vx_cumdist_thres");
+}

@@ -111,7 +111,7 @@ class _NeusAlpha(torch.autograd.Function):
         n = sdf.shape[0]
         alpha = torch.empty_like(sdf)
         r32, r64 = (ray_id, None) if ray_id.dtype == torch.int32 else (None, ray_id)
-        call('vx_neus_alpha', viewdirs, r32, r64, sdf, gradient, dist, inv_s, None, n, alpha)
+        call('vx_neus_alpha', viewdirs, r32, r64, sdf, gradient, dist, inv_s, None, n, alpha, None)
         ctx.save_for_backward(viewdirs, ray_id, sdf, gradient)
         ctx.cfg = (dist, inv_s)
         return alpha
@@ -124,7 +124,7 @@ class _NeusAlpha(torch.autograd.Function):
         g_sdf, g_grad = torch.empty_like(sdf), torch.empty_like(gradient)
         r32, r64 = (ray_id, None) if ray_id.dtype == torch.int32 else (None, ray_id)
         call('vx_neus_alpha_backward', viewdirs, r32, r64, sdf, gradient, dist, inv_s, None, sdf.shape[0],
-             grad_alpha.contiguous(), 0, g_sdf, g_grad)
+             grad_alpha.contiguous(), 0, g_sdf, g_grad, None)
         return None, None, g_sdf, g_grad, None, None
 
 
