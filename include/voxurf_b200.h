@@ -269,6 +269,27 @@ int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int C, int
                           int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
                           const float* dX2, float* d_sdf_s, float* d_grad_s, float* sdf_grad, float* k0_grad,
                           uint32_t* k0_touched, cudaStream_t stream);
+/* ---- bit-reproducible gradients: the scatters into 64-bit fixed-point accumulators (integer sums do not depend on the
+ * order the atomics land in; SURVEY.md 8e "Determinism" -- the reference inherits ATen's fp32 atomics, run.py:279).
+ * acc_scale = accumulator units per 1.0 (2^52: contributions >= 4e-9 keep their fp32 mantissa, |sums| < 2048). */
+int vx_fused_row_backward_fx(const float* sdf_grid, int X, int Y, int Z, int C, int k0_channels_last,
+                             const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
+                             const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
+                             const int* n_rows_dev, int capacity, float voxel_size, int use_grad_norm, int P, int Vp,
+                             int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
+                             const float* dX2, float* d_sdf_s, float* d_grad_s, int64_t* sdf_acc, int64_t* k0_acc,
+                             float acc_scale, uint32_t* k0_touched, cudaStream_t stream);
+int vx_fused_alpha_sdf_backward_fx(int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
+                                   const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
+                                   float stepdist, const int* n_dev, const float* viewdirs, const float* sdf,
+                                   const float* grad, const uint8_t* keep, const float* d_alpha, const float* d_sdf_s,
+                                   const float* d_grad_s, float voxel_size, float dist, float inv_s, int64_t* sdf_acc,
+                                   float acc_scale, const float* inv_s_dev, cudaStream_t stream);
+/* grad[i] += acc[i] / acc_scale and acc[i] = 0 wherever acc[i] != 0; touched (optional): one bit per `group` elements */
+int vx_fx_accumulate(int64_t* acc, int64_t n, float acc_scale, float* grad, const uint32_t* touched, int group,
+                     cudaStream_t stream);
+int vx_mlp_dw_batch_fx(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
+                       int64_t* acc, const float* grad_base, float acc_scale, cudaStream_t stream);
 /* data-parallel exchange of the k0 gradient as rows: (xyz, scale * dX2[:, 0:C]) per MLP row, zeros past *n_rows_dev;
  * the gathered rows of all ranks are scattered with vx_grid_gather_backward (n_out, optional: the row count, written
  * next to the rows so that it travels with them).  Pass k0_grad = NULL to vx_fused_row_backward to skip the local scatter. */
@@ -367,6 +388,15 @@ int vx_rays_hit_mask(const float* rays_o, const float* rays_d, int n_rays, const
 int vx_compact_rows3(const bool* mask, const int* incl, int n, const int64_t* top_in, int64_t* top_out, int64_t capacity,
                      const float* src0, const float* src1, const float* src2, const float* src3, float* dst0, float* dst1,
                      float* dst2, float* dst3, cudaStream_t stream);
+
+
+/* ---- GPU marching cubes (replaces mcubes.marching_cubes(u, threshold), lib/dvgo_ori.py:695-703; csrc/marching.cu) ---- */
+/* edge_flag[3 p + a]: the iso-level crosses the edge from lattice point p along axis a; cell_tris[cell]: triangle count */
+int vx_mc_classify(const float* u, int nx, int ny, int nz, float thr, const int* tri_count, int* cell_tris,
+                   uint8_t* edge_flag, cudaStream_t stream);
+/* tri_off / vert_off: inclusive prefix sums of cell_tris / edge_flag; verts (V,3) lattice-index coordinates, tris (T,3) */
+int vx_mc_emit(const float* u, int nx, int ny, int nz, float thr, const int* tri_table, const int64_t* tri_off,
+               const int* vert_off, const uint8_t* edge_flag, float* verts, int64_t* tris, cudaStream_t stream);
 
 /* development probe: one M = 128, K = 8 TF32 tcgen05.mma on caller-laid-out shared-memory operand images (<= 32 KB each)
  * with caller-chosen descriptor fields; used by tests/test_gpu_mlp.py to pin the operand layouts the kernels rely on */

@@ -235,3 +235,43 @@ def test_fused_coarse_graph_replay_matches_dropin_path():
     lr = COARSE_TRAIN
     close_mostly(mb.sdf.grid, ma.sdf.grid, 2e-2 * lr['lrate_sdf'], 6 * lr['lrate_sdf'], 'sdf', max_frac=1e-3)
     close_mostly(mb.k0.grid, ma.k0.grid, 2e-2 * lr['lrate_k0'], 6 * lr['lrate_k0'], 'k0', max_frac=1e-3)
+
+
+def test_deterministic_mode_gives_bit_identical_gradients_and_trajectories():
+    """deterministic=True (SURVEY.md 8e "Determinism", north_star "deterministic reductions instead of naive atomics"): every
+    backward scatter -- k0 rows, sdf taps, split-K weight gradients -- accumulates in 64-bit fixed point.  The same step run
+    twice gives BIT-IDENTICAL sdf / k0 / MLP gradients; eight training steps run twice give bit-identical parameters; and
+    the gradients agree with the fp32-atomics path to its own tolerance."""
+    from voxurf_b200.fused import FusedFineStep
+    from voxurf_b200.trainer import FINE_TRAIN
+    sc = S.make_fine_scene(48, 12, 64, seed=91)
+    n_rays = 2048
+    ro, rd, vd = (T(x).to(DEV) for x in S.make_rays(n_rays, seed=17))
+    target = T(S.make_target(vd.cpu().numpy())).to(DEV)
+
+    def grads(det):
+        m = product_fine_model(sc, k0_channels_last=True)
+        fs = FusedFineStep(m, n_rays, FINE_TRAIN, RK, row_capacity=32768, deterministic=det)
+        fs.forward_backward(ro, rd, vd, target, 15003)
+        fs.counts()
+        return [m.sdf.grid.grad.clone(), m.k0.grid.grad.clone(), fs.mlp_grads.clone()]
+
+    a, b, c = grads(True), grads(True), grads(False)
+    for x, y, name in zip(a, b, ('sdf', 'k0', 'mlp')):
+        assert torch.equal(x, y), f'{name} gradient differs between two deterministic runs'
+        assert float(x.abs().max()) > 0
+    for x, y, name in zip(a, c, ('sdf', 'k0', 'mlp')):
+        grad_close(x, y, name + ' vs fp32 atomics', tol=2e-5 if name != 'mlp' else 1e-4)
+
+    def train(det):
+        m = product_fine_model(sc, k0_channels_last=True)
+        fs = FusedFineStep(m, n_rays, FINE_TRAIN, RK, row_capacity=32768, deterministic=det, use_graph=True)
+        for it in range(8):
+            o, d, v = (T(x).to(DEV) for x in S.make_rays(n_rays, seed=500 + it))
+            fs.step(o, d, v, T(S.make_target(v.cpu().numpy(), seed=it)).to(DEV), 15001 + it)
+        fs.counts()
+        return [m.sdf.grid.detach().clone(), m.k0.grid.detach().clone(), fs.mlp1.flat.detach().clone(), fs.mlp2.flat.detach().clone()]
+
+    pa, pb = train(True), train(True)
+    for x, y, name in zip(pa, pb, ('sdf', 'k0', 'rgbnet', 'k_rgbnet')):
+        assert torch.equal(x, y), f'{name} parameters differ between two deterministic training runs'

@@ -80,12 +80,33 @@ __device__ __forceinline__ float vx_tap_eval(const float* __restrict__ g, const 
   return acc;
 }
 
+// Scatter targets.  VxAccF: fp32 atomics straight into the gradient grid (the sum depends on the order the atomics land
+// in: the last bits differ from run to run).  VxAccQ: 64-bit fixed-point accumulators -- integer addition is associative,
+// so the sum is the same whatever the order: bit-reproducible gradients (SURVEY.md 8e "Determinism"; the reference
+// inherits ATen's fp32 atomics and says so, run.py:279).  One accumulator unit is 1 / scale; with scale = 2^52 a
+// contribution >= 4e-9 keeps its full fp32 mantissa and sums up to +-2048 fit.
+struct VxAccF {
+  float* p;
+  __device__ __forceinline__ void add(int64_t i, float v) const { atomicAdd(p + i, v); }
+};
+struct VxAccQ {
+  unsigned long long* p;
+  double scale;
+  __device__ __forceinline__ void add(int64_t i, float v) const {
+    atomicAdd(p + i, (unsigned long long)__double2ll_rn((double)v * scale));
+  }
+};
+
 // scatter g * w into grad at the tap's corners; exact zeros are skipped (adding +0 is a no-op)
-__device__ __forceinline__ void vx_tap_scatter(float* __restrict__ grad, const VxTap& t, float g) {
+template <class Acc>
+__device__ __forceinline__ void vx_tap_scatter(const Acc& acc, const VxTap& t, float g) {
   if (g == 0.f) return;
 #pragma unroll
   for (int c = 0; c < 8; ++c)
-    if (t.off[c] >= 0) atomicAdd(grad + t.off[c], g * t.w[c]);
+    if (t.off[c] >= 0) acc.add(t.off[c], g * t.w[c]);
+}
+__device__ __forceinline__ void vx_tap_scatter(float* __restrict__ grad, const VxTap& t, float g) {
+  vx_tap_scatter(VxAccF{grad}, t, g);
 }
 
 // Sample positions are either an explicit (P,3) array or implicit: (ray_id, step_id) into per-ray

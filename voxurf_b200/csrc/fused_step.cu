@@ -555,12 +555,31 @@ VX_API int vx_fused_composite_aux(const int* idx4, const int* off4, int capacity
 // S11: backward of the row features: dX1 -> sdf-grid scatter (all_feat, all_grad) + d_sdf_s (centre sdf);
 //      dX2 -> k0-grid scatter + d_grad_s (gradient feature of k_rgbnet).  One thread per row.
 // ---------------------------------------------------------------------------------------------
+// one corner of a channels-last k0 scatter: kC contiguous channels (vector atomics for fp32, scalar 64-bit adds otherwise)
 template <int kC>
+__device__ __forceinline__ void vx_k0_add(const VxAccF& a, int64_t base, const float* go, float w) {
+  float* dst = a.p + base;
+  if (kC % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < kC; c += 4)
+      atomicAdd(reinterpret_cast<float4*>(dst + c), make_float4(go[c] * w, go[c + 1] * w, go[c + 2] * w, go[c + 3] * w));
+  } else {
+#pragma unroll
+    for (int c = 0; c < kC; c += 2) atomicAdd(reinterpret_cast<float2*>(dst + c), make_float2(go[c] * w, go[c + 1] * w));
+  }
+}
+template <int kC>
+__device__ __forceinline__ void vx_k0_add(const VxAccQ& a, int64_t base, const float* go, float w) {
+#pragma unroll
+  for (int c = 0; c < kC; ++c) a.add(base + c, go[c] * w);
+}
+
+template <int kC, class AccS, class AccK>
 __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, VxGrid gk, VxPts pts,
                                const int* __restrict__ idx4, const int* __restrict__ n_rows_dev, int capacity,
                                float voxel_size, int use_grad_norm, VxRowLayout lay, const float* __restrict__ dX1,
                                const float* __restrict__ dX2, float* __restrict__ d_sdf_s, float* __restrict__ d_grad_s,
-                               float* __restrict__ sdf_grad, float* __restrict__ k0_grad, uint32_t* __restrict__ k0_touched) {
+                               AccS sdf_grad, AccK k0_acc, bool has_k0, uint32_t* __restrict__ k0_touched) {
   const int n = min(*n_rows_dev, capacity);
   const int L = lay.L;
   const int col_sdf = 3 + 6 * lay.P + 3 + 6 * lay.Vp;
@@ -583,7 +602,7 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
       bool any = false;
 #pragma unroll
       for (int c = 0; c < kC; ++c) { go[c] = g2[c]; any |= go[c] != 0.f; }
-      if (any && k0_grad != nullptr) {
+      if (any && has_k0) {
         float ix, iy, iz;
         point_to_index(gk, p[0], p[1], p[2], ix, iy, iz);
         VxTap t;
@@ -594,20 +613,10 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
           if ((k >> 1) != sub || t.off[k] < 0) continue;
           if (k0_touched) atomicOr(k0_touched + (t.off[k] >> 5), 1u << (t.off[k] & 31));
           if (gk.cl) {
-            float* dst = k0_grad + (int64_t)t.off[k] * kC;
-            if (kC % 4 == 0) {
-#pragma unroll
-              for (int c = 0; c < kC; c += 4)
-                atomicAdd(reinterpret_cast<float4*>(dst + c),
-                          make_float4(go[c] * t.w[k], go[c + 1] * t.w[k], go[c + 2] * t.w[k], go[c + 3] * t.w[k]));
-            } else {
-#pragma unroll
-              for (int c = 0; c < kC; c += 2)
-                atomicAdd(reinterpret_cast<float2*>(dst + c), make_float2(go[c] * t.w[k], go[c + 1] * t.w[k]));
-            }
+            vx_k0_add<kC>(k0_acc, (int64_t)t.off[k] * kC, go, t.w[k]);
           } else {
 #pragma unroll
-            for (int c = 0; c < kC; ++c) atomicAdd(k0_grad + c * V + t.off[k], go[c] * t.w[k]);
+            for (int c = 0; c < kC; ++c) k0_acc.add(c * V + t.off[k], go[c] * t.w[k]);
           }
         }
       }
@@ -663,13 +672,14 @@ __global__ void k_row_backward(VxGrid gs, const float* __restrict__ sdf_grid, Vx
   }
 }
 
-VX_API int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int C, int k0_channels_last,
-                                 const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
-                                 const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
-                                 const int* n_rows_dev, int capacity, float voxel_size, int use_grad_norm, int P, int Vp,
-                                 int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
-                                 const float* dX2, float* d_sdf_s, float* d_grad_s, float* sdf_grad, float* k0_grad,
-                                 uint32_t* k0_touched, cudaStream_t st) {
+template <class AccS, class AccK>
+static int row_backward_impl(const float* sdf_grid, int X, int Y, int Z, int C, int k0_channels_last,
+                             const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
+                             const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
+                             const int* n_rows_dev, int capacity, float voxel_size, int use_grad_norm, int P, int Vp,
+                             int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
+                             const float* dX2, float* d_sdf_s, float* d_grad_s, AccS sdf_acc, AccK k0_acc, bool has_k0,
+                             uint32_t* k0_touched, cudaStream_t st) {
   if (capacity <= 0) return 0;
   VxRowLayout lay;
   VX_REQUIRE(fill_layout(lay, P, Vp, P2, V2, L, C, ld1, ld2, displace_host) == 0, "vx_fused_row_backward", "bad layout");
@@ -679,12 +689,40 @@ VX_API int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int
   const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
   const int blocks = min(vx_blocks((int64_t)capacity * 4, 128), vx_num_sms() * 32);
   if (C == 6)
-    k_row_backward<6><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, pts, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm, lay,
-                                              dX1, dX2, d_sdf_s, d_grad_s, sdf_grad, k0_grad, k0_touched);
+    k_row_backward<6, AccS, AccK><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, pts, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm,
+                                                          lay, dX1, dX2, d_sdf_s, d_grad_s, sdf_acc, k0_acc, has_k0, k0_touched);
   else
-    k_row_backward<12><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, pts, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm, lay,
-                                               dX1, dX2, d_sdf_s, d_grad_s, sdf_grad, k0_grad, k0_touched);
+    k_row_backward<12, AccS, AccK><<<blocks, 128, 0, st>>>(gs, sdf_grid, gk, pts, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm,
+                                                           lay, dX1, dX2, d_sdf_s, d_grad_s, sdf_acc, k0_acc, has_k0, k0_touched);
   return vx_check_launch("vx_fused_row_backward");
+}
+
+VX_API int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int C, int k0_channels_last,
+                                 const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
+                                 const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
+                                 const int* n_rows_dev, int capacity, float voxel_size, int use_grad_norm, int P, int Vp,
+                                 int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
+                                 const float* dX2, float* d_sdf_s, float* d_grad_s, float* sdf_grad, float* k0_grad,
+                                 uint32_t* k0_touched, cudaStream_t st) {
+  return row_backward_impl(sdf_grid, X, Y, Z, C, k0_channels_last, xyz_min_host, xyz_max_host, ray_id, step_id, rays_start, rays_dir,
+                           stepdist, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm, P, Vp, P2, V2, displace_host, L, ld1, ld2,
+                           dX1, dX2, d_sdf_s, d_grad_s, VxAccF{sdf_grad}, VxAccF{k0_grad}, k0_grad != nullptr, k0_touched, st);
+}
+
+// the same scatter into 64-bit fixed-point accumulators (order-independent sums: bit-reproducible gradients); acc_scale =
+// accumulator units per 1.0, e.g. 2^52.  vx_fx_accumulate folds the accumulators into the fp32 gradient grids.
+VX_API int vx_fused_row_backward_fx(const float* sdf_grid, int X, int Y, int Z, int C, int k0_channels_last,
+                                    const float* xyz_min_host, const float* xyz_max_host, const int* ray_id, const int* step_id,
+                                    const float* rays_start, const float* rays_dir, float stepdist, const int* idx4,
+                                    const int* n_rows_dev, int capacity, float voxel_size, int use_grad_norm, int P, int Vp,
+                                    int P2, int V2, const float* displace_host, int L, int ld1, int ld2, const float* dX1,
+                                    const float* dX2, float* d_sdf_s, float* d_grad_s, int64_t* sdf_acc, int64_t* k0_acc,
+                                    float acc_scale, uint32_t* k0_touched, cudaStream_t st) {
+  VX_REQUIRE(sdf_acc != nullptr && acc_scale > 0.f, "vx_fused_row_backward_fx", "sdf_acc / acc_scale required");
+  return row_backward_impl(sdf_grid, X, Y, Z, C, k0_channels_last, xyz_min_host, xyz_max_host, ray_id, step_id, rays_start, rays_dir,
+                           stepdist, idx4, n_rows_dev, capacity, voxel_size, use_grad_norm, P, Vp, P2, V2, displace_host, L, ld1, ld2,
+                           dX1, dX2, d_sdf_s, d_grad_s, VxAccQ{reinterpret_cast<unsigned long long*>(sdf_acc), (double)acc_scale},
+                           VxAccQ{reinterpret_cast<unsigned long long*>(k0_acc), (double)acc_scale}, k0_acc != nullptr, k0_touched, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -693,11 +731,12 @@ VX_API int vx_fused_row_backward(const float* sdf_grid, int X, int Y, int Z, int
 // d_sdf_s / d_grad_s carry the MLP-feature gradients of the rows.  Samples whose gradients are all exactly zero
 // (the vast majority late in training) are skipped before any tap is recomputed.
 // ---------------------------------------------------------------------------------------------
+template <class Acc>
 __global__ void k_alpha_sdf_bwd(VxGrid g, VxPts pts, const int* __restrict__ n_dev, const float* __restrict__ viewdirs,
                                 const float* __restrict__ sdf, const float* __restrict__ grad,
                                 const uint8_t* __restrict__ keep, const float* __restrict__ d_alpha,
                                 const float* __restrict__ d_sdf_s, const float* __restrict__ d_grad_s, float voxel_size,
-                                float dist, float inv_s, float* __restrict__ sdf_grad, const float* __restrict__ inv_s_dev) {
+                                float dist, float inv_s, Acc sdf_grad, const float* __restrict__ inv_s_dev) {
   const int64_t n = *n_dev;
   if (inv_s_dev) inv_s = __ldg(inv_s_dev);
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
@@ -765,10 +804,61 @@ VX_API int vx_fused_alpha_sdf_backward(int X, int Y, int Z, const float* xyz_min
   VX_REQUIRE(n_dev != nullptr, "vx_fused_alpha_sdf_backward", "n_dev required");
   const VxGrid g = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
   const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
-  k_alpha_sdf_bwd<<<vx_num_sms() * 8, 256, 0, st>>>(g, pts, n_dev, viewdirs, sdf, grad, keep, d_alpha, d_sdf_s, d_grad_s,
-                                                    voxel_size, dist, inv_s, sdf_grad, inv_s_dev);
+  k_alpha_sdf_bwd<VxAccF><<<vx_num_sms() * 8, 256, 0, st>>>(g, pts, n_dev, viewdirs, sdf, grad, keep, d_alpha, d_sdf_s, d_grad_s,
+                                                            voxel_size, dist, inv_s, VxAccF{sdf_grad}, inv_s_dev);
   return vx_check_launch("vx_fused_alpha_sdf_backward");
 }
+
+VX_API int vx_fused_alpha_sdf_backward_fx(int X, int Y, int Z, const float* xyz_min_host, const float* xyz_max_host,
+                                          const int* ray_id, const int* step_id, const float* rays_start, const float* rays_dir,
+                                          float stepdist, const int* n_dev, const float* viewdirs, const float* sdf,
+                                          const float* grad, const uint8_t* keep, const float* d_alpha, const float* d_sdf_s,
+                                          const float* d_grad_s, float voxel_size, float dist, float inv_s, int64_t* sdf_acc,
+                                          float acc_scale, const float* inv_s_dev, cudaStream_t st) {
+  VX_REQUIRE(n_dev != nullptr && sdf_acc != nullptr && acc_scale > 0.f, "vx_fused_alpha_sdf_backward_fx", "n_dev / sdf_acc / acc_scale required");
+  const VxGrid g = make_grid(X, Y, Z, 1, 0, xyz_min_host, xyz_max_host);
+  const VxPts pts{nullptr, ray_id, step_id, rays_start, rays_dir, stepdist};
+  k_alpha_sdf_bwd<VxAccQ><<<vx_num_sms() * 8, 256, 0, st>>>(g, pts, n_dev, viewdirs, sdf, grad, keep, d_alpha, d_sdf_s, d_grad_s, voxel_size,
+                                                            dist, inv_s, VxAccQ{reinterpret_cast<unsigned long long*>(sdf_acc), (double)acc_scale},
+                                                            inv_s_dev);
+  return vx_check_launch("vx_fused_alpha_sdf_backward_fx");
+}
+
+// grad[i] += acc[i] / scale, acc[i] = 0 where acc[i] != 0 (dense read of the accumulators, sparse writes).  touched
+// (optional, one bit per group of `group` consecutive elements): only the flagged groups are visited.
+__global__ void k_fx_accumulate(long long* __restrict__ acc, int64_t n, double inv_scale, float* __restrict__ grad,
+                                const uint32_t* __restrict__ touched, int group) {
+  if (touched) {
+    const int64_t n_vox = n / group, n_words = (n_vox + 31) >> 5;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int64_t w = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); w < n_words; w += (int64_t)gridDim.x * wpb) {
+      const uint32_t bits = touched[w];
+      if (bits == 0u) continue;
+      for (int64_t e = lane; e < (int64_t)32 * group; e += 32) {
+        const int64_t i = w * 32 * group + e;
+        if (i >= n || !((bits >> (e / group)) & 1u)) continue;
+        const long long a = acc[i];
+        if (a != 0) { grad[i] += (float)((double)a * inv_scale); acc[i] = 0; }
+      }
+    }
+    return;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const long long a = acc[i];
+    if (a != 0) { grad[i] += (float)((double)a * inv_scale); acc[i] = 0; }
+  }
+}
+
+VX_API int vx_fx_accumulate(int64_t* acc, int64_t n, float acc_scale, float* grad, const uint32_t* touched, int group,
+                            cudaStream_t st) {
+  if (n <= 0) return 0;
+  VX_REQUIRE(acc && grad && acc_scale > 0.f && group >= 1, "vx_fx_accumulate", "bad arguments");
+  const int64_t work = touched ? ((n / group + 31) / 32) * 32 : n;
+  k_fx_accumulate<<<(int)min((int64_t)vx_blocks(work, 256), (int64_t)vx_num_sms() * 16), 256, 0, st>>>(
+      reinterpret_cast<long long*>(acc), n, 1.0 / (double)acc_scale, grad, touched, group);
+  return vx_check_launch("vx_fx_accumulate");
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // Ray-sharded data parallelism: instead of all-reducing the dense k0 gradient grid (0.8 GB at 256^3 x 12), every

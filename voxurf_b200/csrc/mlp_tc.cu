@@ -915,6 +915,11 @@ struct DwJob {
 };
 struct DwBatch {
   int n_jobs;
+  // deterministic mode: partial sums go into 64-bit fixed-point accumulators (acc[i] <-> grad_base[i], `scale` units per
+  // 1.0) instead of fp32 atomics on C / c_bias: integer sums do not depend on the order the CTAs finish in
+  unsigned long long* acc;
+  const float* grad_base;
+  double scale;
   DwJob job[DW_MAX_JOBS];
 };
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -1077,7 +1082,16 @@ k_mlp_dw(const __grid_constant__ DwBatch batch, const int* __restrict__ n_rows_d
         for (int c0 = 0; c0 < FB + 16; c0 += 16) {
           float v[16];
           tmem_ld16(lane_addr + mt * 256 + c0, v);   // warp-collective: every thread executes it, only the adds are predicated
-          if (m < J.M_out) {
+          if (m < J.M_out && batch.acc) {
+            if (c0 == FB) {
+              if (J.c_bias) atomicAdd(batch.acc + (J.c_bias + m - batch.grad_base), (unsigned long long)__double2ll_rn((double)v[0] * batch.scale));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < J.N_in)
+                  atomicAdd(batch.acc + (J.C + (int64_t)m * J.ldc + c0 + j - batch.grad_base), (unsigned long long)__double2ll_rn((double)v[j] * batch.scale));
+            }
+          } else if (m < J.M_out) {
             if (c0 == FB) {
               if (J.c_bias) atomicAdd(J.c_bias + m, v[0]);
             } else {
@@ -1104,8 +1118,24 @@ k_mlp_dw(const __grid_constant__ DwBatch batch, const int* __restrict__ n_rows_d
 }
 
 // ptrs_host[j*4..] = A_img, B_img, C, c_bias (device addresses; c_bias may be 0); dims_host[j*5..] = FA, M_out, FB, N_in, ldc
+static int dw_batch_impl(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
+                         int64_t* acc, const float* grad_base, float acc_scale, cudaStream_t st);
+
 VX_API int vx_mlp_dw_batch(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
                            cudaStream_t st) {
+  return dw_batch_impl(n_jobs, ptrs_host, dims_host, n_rows_dev, capacity, nullptr, nullptr, 0.f, st);
+}
+
+// deterministic variant: every C / c_bias of the jobs lies inside one gradient buffer starting at grad_base; its partial
+// sums are added to acc[offset] as 64-bit fixed point (acc_scale units per 1.0); vx_fx_accumulate folds acc into the buffer
+VX_API int vx_mlp_dw_batch_fx(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
+                              int64_t* acc, const float* grad_base, float acc_scale, cudaStream_t st) {
+  VX_REQUIRE(acc && grad_base && acc_scale > 0.f, "vx_mlp_dw_batch_fx", "acc / grad_base / acc_scale required");
+  return dw_batch_impl(n_jobs, ptrs_host, dims_host, n_rows_dev, capacity, acc, grad_base, acc_scale, st);
+}
+
+static int dw_batch_impl(int n_jobs, const int64_t* ptrs_host, const int* dims_host, const int* n_rows_dev, int capacity,
+                         int64_t* acc, const float* grad_base, float acc_scale, cudaStream_t st) {
   VX_REQUIRE(n_rows_dev != nullptr, "vx_mlp_dw_batch", "n_rows_dev required");
   VX_REQUIRE(n_jobs >= 0 && n_jobs <= DW_MAX_JOBS, "vx_mlp_dw_batch", "at most 8 jobs per launch");
   const int slices_cap = (capacity + DW_KC - 1) / DW_KC;
@@ -1113,6 +1143,9 @@ VX_API int vx_mlp_dw_batch(int n_jobs, const int64_t* ptrs_host, const int* dims
   DwBatch b;
   memset(&b, 0, sizeof(b));
   b.n_jobs = n_jobs;
+  b.acc = reinterpret_cast<unsigned long long*>(acc);
+  b.grad_base = grad_base;
+  b.scale = (double)acc_scale;
   double cost[DW_MAX_JOBS], total = 0;
   for (int j = 0; j < n_jobs; ++j) {
     DwJob& J = b.job[j];

@@ -89,7 +89,8 @@ __device__ __forceinline__ float tap_eval_axes(const float* __restrict__ grid, i
   return acc;
 }
 
-__device__ __forceinline__ void tap_scatter_axes(float* __restrict__ grad, int Y, int Z, const AxisTap& az, const AxisTap& ay,
+template <class Acc>
+__device__ __forceinline__ void tap_scatter_axes(const Acc& acc, int Y, int Z, const AxisTap& az, const AxisTap& ay,
                                                  const AxisTap& ax, float g) {
   if (g == 0.f) return;   // adding +0 is a no-op
   const int base = (ax.i0 * Y + ay.i0) * Z + az.i0, sY = Z, sX = Y * Z;
@@ -98,7 +99,7 @@ __device__ __forceinline__ void tap_scatter_axes(float* __restrict__ grad, int Y
     const int bz = c & 1, by = (c >> 1) & 1, bx = (c >> 2) & 1;
     const float w = (bz ? az.w1 : az.w0) * (by ? ay.w1 : ay.w0) * (bx ? ax.w1 : ax.w0);
     const bool valid = (bz ? az.v1 : az.v0) & (by ? ay.v1 : ay.v0) & (bx ? ax.v1 : ax.v0);
-    if (valid) atomicAdd(grad + base + bx * sX + by * sY + bz, g * w);
+    if (valid) acc.add(base + bx * sX + by * sY + bz, g * w);
   }
 }
 

@@ -39,12 +39,13 @@ from .optim import _storage
 class FusedFineStep:
     def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0,
                  tensor_core=True, sparse_k0_exchange=True, sparse_adam=True, use_graph=False,
-                 graph_multi_gpu=True, dense_exchange=False, defer_optimizer=False):
+                 graph_multi_gpu=True, dense_exchange=False, defer_optimizer=False, deterministic=False):
         if model.k0_dim not in (6, 12):
             raise NotImplementedError('fused step: k0 channels must be 6 or 12')
         if model.k_center_sdf or not model.center_sdf or not model.k_res:
             raise NotImplementedError('fused step covers the shipped fine configs (center_sdf, k_res, no k_center_sdf)')
         self.m, self.N = model, int(n_rays)
+        model._fused = self       # (Voxurf.mesh_color_forward reuses this step's flat MLPs and row buffers)
         self.cfg = dict(train_cfg) if train_cfg is not None else None
         self.rk = dict(render_kwargs or {})
         self.world, self.rank = world, rank
@@ -124,6 +125,17 @@ class FusedFineStep:
             n_words = (self.X * self.Y * self.Z + 31) // 32
             self.k0_touched = torch.zeros(n_words, dtype=torch.int32, device=dev)
             self.k0_live = torch.zeros(n_words, dtype=torch.int32, device=dev)
+        # deterministic=True: every scatter of the backward pass (k0 rows, sdf taps, split-K weight gradients) accumulates in
+        # 64-bit fixed point (order-independent integer sums) and is folded into the fp32 gradient buffers afterwards:
+        # gradients -- and with them the whole training trajectory -- are bit-reproducible run to run.  Costs one dense
+        # read of the sdf accumulators per step (~25 us at 256^3) and 64-bit atomics.
+        self.deterministic = bool(deterministic)
+        self.ACC_SCALE, self.ACC_SCALE_MLP = float(2 ** 52), float(2 ** 44)
+        if self.deterministic:
+            assert world == 1, 'deterministic mode: single GPU (the NCCL reductions have their own order)'
+            self.sdf_acc = torch.zeros(m.sdf.grid.numel(), dtype=torch.int64, device=dev)
+            self.k0_acc = torch.zeros(m.k0.grid.numel(), dtype=torch.int64, device=dev)
+            self.mlp_acc = torch.zeros(self.mlp_grads.numel(), dtype=torch.int64, device=dev)
         self.conv_scratch = None
         self._dw_stream = None
         self.G = None       # FD gradient grid + its gradient, allocated on the first TV iteration
@@ -277,6 +289,41 @@ class FusedFineStep:
                 'disp': (1 / self.depth) if render_depth else 0, 's_val': s_val}
 
     @torch.no_grad()
+    def mesh_colors(self, pts):
+        """Vertex colours of an extracted mesh, lib/voxurf_fine.py:804-892 (`mesh_color_forward`; run.py:889-893 feeds it the
+        mesh vertices in chunks): the fine forward's feature build and both colour MLPs at arbitrary points, viewed along the
+        inward surface normal (viewdirs = -normal, normal = gradient / (|gradient| + 1e-5)), no compositing.  Runs on the
+        same kernels as a training step: every point is a one-sample "ray" (start = the point, zero direction), so
+        vx_sdf_taps / vx_fused_row_features / the tcgen05 chains are used unchanged.  pts (P,3) -> rgb (P,3)"""
+        from . import ops
+        m = self.m
+        self.sync_params()
+        pts = pts.reshape(-1, 3).float().contiguous()
+        P = pts.shape[0]
+        out = torch.empty(P, 3, dtype=torch.float32, device=self.dev)
+        X, Y, Z, mn, mx = self._geom()
+        sdf_grid = m.smooth_conv(m.sdf.grid) if m.smooth_sdf else m.sdf.grid
+        prepare_chains(self.mlp1.chains(False) + self.mlp2.chains(False))
+        for a in range(0, P, self.cap4):
+            chunk = pts[a:a + self.cap4].contiguous()
+            n = chunk.shape[0]
+            sdf, feat, grad = ops.sdf_taps(sdf_grid, chunk, mn, mx, [1.0], m._voxel_size_host, use_grad_norm=False, xyz_order=True,
+                                           want_sdf=True)
+            viewdirs = (-(grad / (grad.norm(dim=-1, keepdim=True) + 1e-5))).contiguous()
+            ids = torch.arange(n, dtype=torch.int32, device=self.dev)
+            zi, zd = torch.zeros(n, dtype=torch.int32, device=self.dev), torch.zeros(n, 3, dtype=torch.float32, device=self.dev)
+            n_dev = torch.tensor([n], dtype=torch.int32, device=self.dev)
+            call('vx_fused_row_features', sdf_grid, _storage(m.k0.grid), X, Y, Z, self.C, self.k0_cl, mn, mx, ids, zi, chunk, zd, 1.0,
+                 ids, n_dev, self.cap4, viewdirs, sdf.contiguous(), grad.contiguous(), m._voxel_size_host, int(m.use_grad_norm),
+                 self.P, self.Vp, self.P2, self.V2, self.disp, self.L, self.ld1, self.ld2, self.X1, self.X2)
+            self.mlp1._n = self.mlp2._n = n_dev
+            run_chain_jobs([self.mlp1.forward_job(self.X1, self.logit1, False),
+                            self.mlp2.forward_job(self.X2, self.k_out, False, patch=(self.logit1, self.col_logit, 3, 0))],
+                           n_dev, self.cap4, self.mlp1.done)
+            out[a:a + n] = torch.sigmoid(self.logit1[:n] + self.k_out[:n])
+        return out
+
+    @torch.no_grad()
     def render_chunk(self, rays_o, rays_d, viewdirs, render_grad=True, render_depth=True):
         """render() of one chunk as ONE CUDA-graph replay (use_graph=True; run.py:123-126 renders a view as ~79 such
         chunks): static input buffers, results in the persistent output buffers (clone what you keep).  The NeuS
@@ -326,23 +373,41 @@ class FusedFineStep:
             main = torch.cuda.current_stream()
             self._dw_stream.wait_stream(main)
             with torch.cuda.stream(self._dw_stream):
-                run_dw_batch([self.mlp2, self.mlp1])
+                if self.deterministic:
+                    run_dw_batch([self.mlp2, self.mlp1], fx=(self.mlp_acc, self.mlp_grads, self.ACC_SCALE_MLP))
+                    call('vx_fx_accumulate', self.mlp_acc, self.mlp_acc.numel(), self.ACC_SCALE_MLP, self.mlp_grads, None, 1)
+                else:
+                    run_dw_batch([self.mlp2, self.mlp1])
         else:
             self.mlp2.backward(self.d_kout, self.dX2)
             if sparse_dp:
                 self._start_k0_exchange(n4)
             self.mlp1.backward(self.d_logit1, self.dX1)
         grad_target = self.d_smoothed if m.smooth_sdf else self.sdf_grad
-        call('vx_fused_row_backward', self._sdf_grid, X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(), self.idx4, n4,
-             self.cap4, m._voxel_size_host, int(m.use_grad_norm), self.P, self.Vp, self.P2, self.V2, self.disp, self.L,
-             self.ld1, self.ld2, self.dX1, self.dX2, self.d_sdf_s, self.d_grad_s, grad_target,
-             None if sparse_dp else _storage(self.k0_grad), None if sparse_dp else self.k0_touched)
         thres = float(m.fast_color_thres)
-        call('vx_alpha2weight_seg_backward', self.alpha, self.weight, self.T, self.keep if thres > 0 else None,
-             self.alphainv_last, self.keep_off, self.i_end, N, self.d_w, self.d_last, self.d_alpha)
-        call('vx_fused_alpha_sdf_backward', X, Y, Z, mn, mx, *self._pts(), n2, viewdirs.contiguous(), self.sdf_s, self.grad_s,
-             self.keep, self.d_alpha, self.d_sdf_s, self.d_grad_s, m._voxel_size_host, self.dist, self.inv_s, grad_target,
-             self._inv_s_dev)
+        if self.deterministic:
+            call('vx_fused_row_backward_fx', self._sdf_grid, X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(), self.idx4, n4,
+                 self.cap4, m._voxel_size_host, int(m.use_grad_norm), self.P, self.Vp, self.P2, self.V2, self.disp, self.L,
+                 self.ld1, self.ld2, self.dX1, self.dX2, self.d_sdf_s, self.d_grad_s, self.sdf_acc, self.k0_acc, self.ACC_SCALE,
+                 self.k0_touched)
+            call('vx_alpha2weight_seg_backward', self.alpha, self.weight, self.T, self.keep if thres > 0 else None,
+                 self.alphainv_last, self.keep_off, self.i_end, N, self.d_w, self.d_last, self.d_alpha)
+            call('vx_fused_alpha_sdf_backward_fx', X, Y, Z, mn, mx, *self._pts(), n2, viewdirs.contiguous(), self.sdf_s, self.grad_s,
+                 self.keep, self.d_alpha, self.d_sdf_s, self.d_grad_s, m._voxel_size_host, self.dist, self.inv_s, self.sdf_acc,
+                 self.ACC_SCALE, self._inv_s_dev)
+            call('vx_fx_accumulate', self.sdf_acc, self.sdf_acc.numel(), self.ACC_SCALE, grad_target.view(-1), None, 1)
+            call('vx_fx_accumulate', self.k0_acc, self.k0_acc.numel(), self.ACC_SCALE, _storage(self.k0_grad).reshape(-1),
+                 self.k0_touched if self.k0_cl else None, self.C if self.k0_cl else 1)
+        else:
+            call('vx_fused_row_backward', self._sdf_grid, X, Y, Z, self.C, self.k0_cl, mn, mx, *self._pts(), self.idx4, n4,
+                 self.cap4, m._voxel_size_host, int(m.use_grad_norm), self.P, self.Vp, self.P2, self.V2, self.disp, self.L,
+                 self.ld1, self.ld2, self.dX1, self.dX2, self.d_sdf_s, self.d_grad_s, grad_target,
+                 None if sparse_dp else _storage(self.k0_grad), None if sparse_dp else self.k0_touched)
+            call('vx_alpha2weight_seg_backward', self.alpha, self.weight, self.T, self.keep if thres > 0 else None,
+                 self.alphainv_last, self.keep_off, self.i_end, N, self.d_w, self.d_last, self.d_alpha)
+            call('vx_fused_alpha_sdf_backward', X, Y, Z, mn, mx, *self._pts(), n2, viewdirs.contiguous(), self.sdf_s, self.grad_s,
+                 self.keep, self.d_alpha, self.d_sdf_s, self.d_grad_s, m._voxel_size_host, self.dist, self.inv_s, grad_target,
+                 self._inv_s_dev)
         if m.smooth_sdf:
             call('vx_conv3d_replicate_separable', self.d_smoothed, 1, X, Y, Z, m.smooth_conv.weight1d_host, m.smooth_conv.ksize, 1, 1,
                  self.conv_scratch, self.sdf_grad)

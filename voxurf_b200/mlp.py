@@ -182,8 +182,9 @@ def _pad(v, m):
     return (v + m - 1) // m * m
 
 
-def run_dw_batch(mlps):
-    """Weight / bias gradients of several FlatMLPs (same row count and capacity) with one launch per 8 layers."""
+def run_dw_batch(mlps, fx=None):
+    """Weight / bias gradients of several FlatMLPs (same row count and capacity) with one launch per 8 layers.
+    fx = (int64 accumulators, gradient buffer they mirror, scale): deterministic fixed-point accumulation."""
     from ._lib import call
     ptrs, dims = [], []
     for m in mlps:
@@ -192,7 +193,10 @@ def run_dw_batch(mlps):
         ptrs += p; dims += d
     for j in range(0, len(ptrs) // 4, 8):
         n = min(8, len(ptrs) // 4 - j)
-        call('vx_mlp_dw_batch', n, ptrs[4 * j:4 * (j + n)], dims[5 * j:5 * (j + n)], mlps[0]._n, mlps[0].cap)
+        if fx is not None:
+            call('vx_mlp_dw_batch_fx', n, ptrs[4 * j:4 * (j + n)], dims[5 * j:5 * (j + n)], mlps[0]._n, mlps[0].cap, fx[0], fx[1], fx[2])
+        else:
+            call('vx_mlp_dw_batch', n, ptrs[4 * j:4 * (j + n)], dims[5 * j:5 * (j + n)], mlps[0]._n, mlps[0].cap)
 
 
 JOB_STRIDE, PTR_STRIDE = 26, 30   # csrc/mlp_tc.cu MC_JOB_STRIDE (dims per job), MC_PTR_STRIDE (pointers per job)

@@ -259,6 +259,25 @@ class Voxurf(VoxurfBase):
         return (u, g) if with_gradient else u
 
     @torch.no_grad()
+    def mesh_color_forward(self, ray_pts, **kwargs):
+        """lib/voxurf_fine.py:804-892: colours of mesh vertices (viewdirs = -normal).  Runs on the fused step's kernels
+        (FusedFineStep.mesh_colors: vx_sdf_taps, vx_fused_row_features, the tcgen05 MLP chains)."""
+        fs = getattr(self, '_fused', None)
+        if fs is None:
+            from .fused import FusedFineStep
+            fs = FusedFineStep(self, 8, None, dict(near=0.0, stepsize=0.5), row_capacity=65536)
+        return fs.mesh_colors(ray_pts)
+
+    def extract_geometry(self, bound_min=None, bound_max=None, resolution=128, threshold=0.0, smooth=True, sigma=0.5, **kwargs):
+        """lib/voxurf_fine.py:894-910: (vertices, triangles) of the iso-surface -sdf = threshold; field query and marching
+        cubes both on the GPU (voxurf_b200/marching.py).  Returns numpy arrays like the reference."""
+        from . import marching
+        if resolution is None:
+            resolution = int(self.world_size[0])
+        v, t = marching.extract_geometry(self, resolution, threshold, smooth, sigma)
+        return v.cpu().numpy(), t.cpu().numpy()
+
+    @torch.no_grad()
     def mesh_query_grid(self, smooth=True, sigma=0.5):
         """The grid extract_geometry queries: the per-iteration smoothed grid if the model has one, else the k=3 Gaussian
         smoothed grid (init_smooth_conv_test_k3), else the raw grid (lib/voxurf_fine.py:894-903)."""
