@@ -101,6 +101,13 @@ int vx_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, c
                  float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
                  float sqrt_bias_correction2, float eps, int skip_zero_grad, int zero_grad, const uint32_t* touched,
                  const uint32_t* live, int group, const float* step_dev, cudaStream_t stream);
+/* vx_adam_step for a single-channel grid with block-level skipping: blocks of 128 consecutive elements whose gradient is
+ * entirely zero and that never had a non-zero one (live_blocks[b] == 0, numel / 128 bytes, maintained by the kernel) are
+ * the identity under lib/utils.py:154-199 and are not touched; bit-identical to the dense pass */
+int vx_adam_step_blocklive(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float beta1,
+                           float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                           float sqrt_bias_correction2, float eps, int zero_grad, uint8_t* live_blocks,
+                           const float* step_dev, cudaStream_t stream);
 /* live |= touched; touched = 0 -- after the vx_adam_step that consumed both */
 int vx_bitmap_merge(uint32_t* live, uint32_t* touched, int64_t n_words, cudaStream_t stream);
 

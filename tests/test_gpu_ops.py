@@ -479,3 +479,28 @@ def test_cumdist_thres_bit_exact(n_rays, n_pts):
     mod = build_ref.load_ref('ub360_utils_cuda')
     if mod is not None:
         assert torch.equal(mod.cumdist_thres(dist.cuda(), thres), out)
+
+
+def test_adam_blocklive_is_bit_identical_to_dense():
+    """vx_adam_step_blocklive (sdf grid): blocks of 128 elements that never saw a gradient are skipped; three steps with
+    gradients appearing in new blocks give exactly the dense kernel's parameters and moments."""
+    from voxurf_b200._lib import call
+    n = 128 * 300
+    rs = np.random.RandomState(5)
+    p0 = T(rs.standard_normal(n).astype(np.float32)).cuda()
+    A = [p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')]
+    B = [p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')]
+    live = torch.zeros(n // 128, dtype=torch.uint8, device='cuda')
+    for step in range(1, 4):
+        g = np.zeros(n, np.float32)
+        for b in rs.choice(300, 20 * step, replace=False):
+            g[b * 128 + rs.randint(0, 128, 5)] = rs.standard_normal(5)
+        ga, gb = T(g).cuda(), T(g).cuda()
+        bc1, bc2 = 1 - 0.9 ** step, 1 - 0.99 ** step
+        args = (0.9, 0.99, 0.1, 0.01, 5e-3 / bc1, float(np.sqrt(bc2)), 1e-8)
+        call('vx_adam_step', A[0], ga, A[1], A[2], None, n, *args, 0, 1, None, None, 1, None)
+        call('vx_adam_step_blocklive', B[0], gb, B[1], B[2], n, *args, 1, live, None)
+        for x, y in zip(A, B):
+            assert torch.equal(x, y)
+        assert (gb == 0).all()
+    assert 0 < int(live.sum()) < 300

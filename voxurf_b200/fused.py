@@ -174,6 +174,10 @@ class FusedFineStep:
             per = self.X // world * self.Y * self.Z
             self.slab_x = (rank * (self.X // world), (rank + 1) * (self.X // world))
             self.slab = (rank * per, (rank + 1) * per)
+        # sdf Adam with block-level skipping (blocks of 128 voxels that never received a gradient are the identity)
+        self.sdf_live = None
+        if sparse_adam and m.sdf.grid.numel() % 128 == 0 and (not self.sharded or (self.slab[1] - self.slab[0]) % 128 == 0):
+            self.sdf_live = torch.zeros(m.sdf.grid.numel() // 128, dtype=torch.uint8, device=dev)
         self.bitmap_probe = None   # bench.py: list collecting copies of (touched, live) as the k0 Adam launch sees them
         self.timings = None   # bench.py: list collecting (group, (start, end) CUDA events) around the k0 / sdf Adam launches
         if self.cfg is not None:
@@ -464,6 +468,8 @@ class FusedFineStep:
                 flat = t.view(-1)
                 dist.all_gather_into_tensor(flat, flat[self.slab[0]:self.slab[1]])
         self.sharded = False
+        if self.sdf_live is not None:
+            self.sdf_live.fill_(1)       # the gathered moments of the other ranks' slabs may be non-zero anywhere
         self.release_graphs()
 
     def _sync_begin(self):
@@ -611,6 +617,7 @@ class FusedFineStep:
                 if touched is not None and self.bitmap_probe is not None:
                     self.bitmap_probe.append((touched.clone(), live.clone()))
                 tensors = [_storage(p.data), _storage(p.grad), _storage(st[0]), _storage(st[1])]
+                sdf_live = self.sdf_live if name == 'sdf' else None
                 if name == 'sdf' and self.sharded:
                     # the owned X-slab only; the other slabs of the gradient buffer still hold this rank's local
                     # (un-reduced) gradient and are cleared here, the Adam pass clears the slab itself
@@ -618,7 +625,15 @@ class FusedFineStep:
                     g = tensors[1].view(-1)
                     g[:lo].zero_(); g[hi:].zero_()
                     tensors = [t.view(-1)[lo:hi] for t in tensors]
+                    sdf_live = sdf_live[lo // 128:hi // 128] if sdf_live is not None else None
                     self._params_dirty = True
+                if sdf_live is not None:
+                    call('vx_adam_step_blocklive', *tensors, tensors[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
+                         math.sqrt(bc2), eps, 1, sdf_live, None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
+                    if timed:
+                        ev[1].record()
+                        self.timings.append((name, ev))
+                    continue
                 call('vx_adam_step', *tensors, None, tensors[0].numel(),
                      beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1, touched, live, self.C,
                      None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
@@ -666,6 +681,8 @@ class FusedFineStep:
                 self.k0_live.copy_(st['k0_live'])
             else:
                 self.mark_all_live()    # moments of unknown sparsity: every voxel may hold non-zero exp_avg / exp_avg_sq
+        if self.sdf_live is not None:
+            self.sdf_live.fill_(1)
         self.m._refresh_derived()
 
     def warm_up(self, batches, global_step):
@@ -688,6 +705,8 @@ class FusedFineStep:
         """Call after loading optimizer moments from elsewhere: every voxel may then hold non-zero exp_avg / exp_avg_sq."""
         if self.k0_live is not None:
             self.k0_live.fill_(-1)
+        if self.sdf_live is not None:
+            self.sdf_live.fill_(1)
 
     def apply_lr_decay(self):
         """run.py:679-683: every learning rate times 0.1 ** (1 / (lrate_decay * 1000)) after each optimizer step."""
