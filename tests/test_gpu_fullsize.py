@@ -91,8 +91,10 @@ def test_benchmarked_shape_follows_the_oracle_trajectory():
         # two trajectories whose fp32 atomics land in different orders: Adam's first steps are sign-like, so a voxel with a
         # borderline gradient can move by lr in one run and not in the other; a few rays see such a voxel
         d = (rgb.cpu() - oret['rgb_marched'].detach()).abs()
-        assert float((d > 1e-4 * oret['rgb_marched'].detach().abs() + 2e-5).float().mean()) < 5e-3 and float(d.max()) < 5e-3, \
+        # (measured run to run: 0.2 % - 0.7 % of the 24 576 values beyond 1e-4 relative after the first TV iteration, max 2e-3)
+        assert float((d > 1e-4 * oret['rgb_marched'].detach().abs() + 2e-5).float().mean()) < 1.5e-2 and float(d.max()) < 5e-3, \
             (gs, float((d > 1e-4).float().mean()), float(d.max()))
+        assert float(d.median()) < 1e-5, (gs, float(d.median()))      # the bulk of the rays agrees to fp32 round-off
     assert len(fs._graphs) >= 2 and fs.launches_replayed > 0
     fs.sync_params()          # the last step's deferred optimizer phase
     fs.poll_overflow(force=True)
