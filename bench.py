@@ -238,7 +238,7 @@ def oracle_bench_model(G, C, smooth, k0=None, mlps=None, sdf=None):
     return m, params, lrs, state
 
 
-def oracle_bench_step(m, params, lrs, state, batch, gs, adam_step, n_batch, G, lr_scale=1.0, grads_out=None):
+def oracle_bench_step(m, params, lrs, state, batch, gs, adam_step, n_batch, G, lr_scale=1.0, grads_out=None, grads_out_tv=None):
     """One full training iteration of the reference's formulation on CPU: forward + losses (run.py:604-636), backward,
     on TV iterations the smooth-gradient TV and the TV add-grad (run.py:612-655), the dense python Adam (lib/utils.py).
     -> (loss incl. regulariser, ret dict)"""
@@ -258,6 +258,8 @@ def oracle_bench_step(m, params, lrs, state, batch, gs, adam_step, n_batch, G, l
     if tv_iter:
         w = 0.01 * 0.1 / n_batch * G / 128
         K.total_variation_add_grad(m['sdf'].detach(), m['sdf'].grad, w, w, w, True)
+    if grads_out_tv is not None:  # parity tests: the gradients the optimizer consumes (after the TV add-grad)
+        grads_out_tv.extend(None if p.grad is None else p.grad.clone() for p in params)
     with torch.no_grad():
         for p, lr, (ea, es) in zip(params, lrs, state):
             if p.grad is not None:

@@ -108,6 +108,15 @@ int vx_adam_step_blocklive(float* param, float* grad, float* exp_avg, float* exp
                            float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
                            float sqrt_bias_correction2, float eps, int zero_grad, uint8_t* live_blocks,
                            const float* step_dev, cudaStream_t stream);
+/* The bitmap form of vx_adam_step (lib/utils.py:154-199 restricted to the voxels in touched | live) dealt through a
+ * compacted work list of the non-empty bitmap words instead of a static word -> warp mapping (the live voxels sit in
+ * the surface shell: balanced, and every lane keeps all of its loads of a word in flight).  3 <= group <= 12.
+ * work: numel / group / 32 + 1 uint32 of scratch.  merge != 0 also performs vx_bitmap_merge in the same pass.
+ * Bit-identical to the dense pass. */
+int vx_adam_step_worklist(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float beta1,
+                          float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                          float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched, uint32_t* live,
+                          int group, int merge, uint32_t* work, const float* step_dev, cudaStream_t stream);
 /* live |= touched; touched = 0 -- after the vx_adam_step that consumed both */
 int vx_bitmap_merge(uint32_t* live, uint32_t* touched, int64_t n_words, cudaStream_t stream);
 
@@ -211,6 +220,18 @@ int vx_march_flags(const float* rays_start, const float* rays_dir, const float* 
                    int mc_Z, const float* mc_min_host, const float* mc_max_host, float act_shift,
                    float voxel_size_ratio, float thres, uint32_t* bits_inbbox, uint32_t* bits_keep,
                    int* keep_count, int* keep_off /* n_rays+1 */, cudaStream_t stream);
+/* Per-cell verdicts of the mask-cache test for vx_march_flags_cells: cells (mc_X, mc_Y, mc_Z) uint8, 1 = every sample whose
+ * trilinear cell is (i,j,k) passes `alpha >= thres`, 0 = every one fails, 2 = evaluate exactly (the shell where the mask
+ * changes, and the last index of each axis).  Derived from the 8 corner densities of the cell with margins > 10x the fp32
+ * evaluation error, so the keep flags of the march are bit-identical with and without the table. */
+int vx_mask_cache_cells(const float* mc_density, int mc_X, int mc_Y, int mc_Z, float act_shift, float voxel_size_ratio,
+                        float thres, uint8_t* cells, cudaStream_t stream);
+/* vx_march_flags with the verdict table (mc_cells may be NULL = vx_march_flags) */
+int vx_march_flags_cells(const float* rays_start, const float* rays_dir, const float* xyz_min, const float* xyz_max,
+                         const int64_t* offsets, int n_rays, float stepdist, const float* mc_density, int mc_X, int mc_Y,
+                         int mc_Z, const float* mc_min_host, const float* mc_max_host, float act_shift,
+                         float voxel_size_ratio, float thres, const uint8_t* mc_cells, uint32_t* bits_inbbox,
+                         uint32_t* bits_keep, int* keep_count, int* keep_off /* n_rays+1 */, cudaStream_t stream);
 /* MaskCache.forward on explicit points  lib/voxurf_fine.py:930-942 */
 int vx_mask_cache_query(const float* mc_density, int mc_X, int mc_Y, int mc_Z, const float* mc_min_host,
                         const float* mc_max_host, float act_shift, float voxel_size_ratio, float thres,

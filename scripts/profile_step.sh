@@ -24,3 +24,5 @@ echo "full capture: skip $SKIP count $COUNT"
 timeout 1500 ncu --set full --clock-control none -s $SKIP -c $COUNT -f -o gpurun_out/${TAG}_full python $ARGS > gpurun_out/${TAG}_full.log 2>&1
 ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv
 ls -la gpurun_out/${TAG}_full.ncu-rep gpurun_out/${TAG}_full_raw.csv
+# the report itself (> 100 MB for ~80 launches) does not fit the 64 MiB return channel: the raw CSV page carries every metric
+rm -f gpurun_out/${TAG}_full.ncu-rep

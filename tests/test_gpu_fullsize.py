@@ -75,31 +75,60 @@ def test_benchmarked_shape_follows_the_oracle_trajectory():
         _grad_close(gw, grads[2 + 2 * i], f'grad W{i}', tol=4e-4); _grad_close(gb, grads[3 + 2 * i], f'grad b{i}', tol=4e-4)
     del grads, g_prod
 
-    # ---- steps 15002..15006 through step(): first occurrences eager, then capture, then replay of both variants
-    for it in range(1, 8):
+    # ---- steps 15002.. through step(): first occurrences eager, then capture, then replay of the variants.
+    # This run starts Adam from zero moments, so its first steps are sign-like (+-lr whatever the size of the gradient): a voxel
+    # whose gradient is zero up to round-off -- after the first TV iteration that is every voxel of a flat region -- moves by lr
+    # in one run and not in the other, and free-running trajectories whose fp32 sums are taken in different orders drift apart
+    # chaotically.  Measured on the B200 (scripts/traj_spread.py): two runs of the SAME product build differ in 0.02-0.1 % of
+    # the rgb values by > 1e-4 at steps 15005-15008 (max 1e-3..5e-3), product vs CPU oracle 0.4-2.6 %, while the deterministic
+    # mode is bit-identical run to run and across eager / graph / deferred execution.  So: steps 15002 stays free-running
+    # (tight), and from 15003 on every step STARTS from the oracle's parameters (the moments stay the product's own), which
+    # keeps the comparison about each step's arithmetic: forward, losses, gradients, regularisers, optimizer.
+    # Step 15003 -- the first TV iteration -- is taken in pieces: the gradients the optimizer consumes (data term +
+    # smooth-gradient TV through the FD gradient + TV add-grad, run.py:612-655) against the oracle's, element by element.
+    def start_from_oracle():
+        fs.flush()                       # the deferred optimizer phase of the previous step
+        with torch.no_grad():
+            m.sdf.grid.copy_(params[0].detach().to(DEV)); m.k0.grid.copy_(params[1].detach().to(DEV))
+            for i, l in enumerate([l for mlp in (fs.mlp1, fs.mlp2) for l in mlp.linears]):
+                l.weight.copy_(params[2 + 2 * i].detach().to(DEV)); l.bias.copy_(params[3 + 2 * i].detach().to(DEV))
+
+    for it in range(1, 9):
         gs = bench.START_STEP + it
         b = it % len(pool)
-        loss = fs.step(*dpool[b], gs).clone()
+        if it >= 2:
+            start_from_oracle()
+        if it == 2:
+            assert fs.tv_flags(gs)[0]
+            fs.forward_backward(*dpool[b], gs)
+            fs.regularise(gs)
+            loss = fs.loss.clone()
+            g_sdf = m.sdf.grid.grad.detach().clone().cpu()
+            fs.optimizer_step()
+            grads = []
+            oloss, oret = bench.oracle_bench_step(om, params, lrs, state, pool[b], gs, it + 1, N, G, lr_scale=decay ** it, grads_out_tv=grads)
+            _grad_close(g_sdf, grads[0], 'grad sdf, TV iteration', flips=1e-4)
+            del grads, g_sdf
+        else:
+            loss = fs.step(*dpool[b], gs).clone()
+            oloss, oret = bench.oracle_bench_step(om, params, lrs, state, pool[b], gs, it + 1, N, G, lr_scale=decay ** it)
         fs.apply_lr_decay()
         rgb = fs.rgb_marched.clone()
         M0, M2, M4 = fs.counts()
-        oloss, oret = bench.oracle_bench_step(om, params, lrs, state, pool[b], gs, it + 1, N, G, lr_scale=decay ** it)
         # (a sample whose interpolated mask-cache alpha sits exactly on the threshold may fall on either side: GPU vs CPU exp)
         assert M0 == oret['mask_outbbox'].shape[0] and abs(M2 - int((~oret['mask_outbbox']).sum())) <= 4
         assert abs(M4 - oret['weights'].shape[0]) <= 16, (M4, oret['weights'].shape[0])   # w > 1e-4 borderline samples
         _close(loss, oloss, 1e-4, 1e-7, f'loss {gs}')
-        # two trajectories whose fp32 atomics land in different orders: Adam's first steps are sign-like, so a voxel with a
-        # borderline gradient can move by lr in one run and not in the other; a few rays see such a voxel
         d = (rgb.cpu() - oret['rgb_marched'].detach()).abs()
-        # (measured run to run: 0.2 % - 0.7 % of the 24 576 values beyond 1e-4 relative after the first TV iteration, max 2e-3)
-        assert float((d > 1e-4 * oret['rgb_marched'].detach().abs() + 2e-5).float().mean()) < 1.5e-2 and float(d.max()) < 5e-3, \
+        assert float(d.median()) < 1e-5, (gs, float(d.median()))
+        assert float((d > 1e-4 * oret['rgb_marched'].detach().abs() + 2e-5).float().mean()) < 1e-3 and float(d.max()) < 5e-3, \
             (gs, float((d > 1e-4).float().mean()), float(d.max()))
-        assert float(d.median()) < 1e-5, (gs, float(d.median()))      # the bulk of the rays agrees to fp32 round-off
     assert len(fs._graphs) >= 2 and fs.launches_replayed > 0
     fs.sync_params()          # the last step's deferred optimizer phase
     fs.poll_overflow(force=True)
-    # parameters after six steps (Adam's first steps are sign-like: all but a small fraction within a fraction of lr)
+    # parameters after the last step, one optimizer step away from a common start (the product's moments have lived through
+    # its own slightly different history): all but a small fraction within a fraction of lr
     d = (m.sdf.grid.detach().cpu() - om['sdf'].detach()).abs()
-    assert float((d > 2e-2 * 5e-3).float().mean()) < 1e-4 and float(d.max()) <= 8 * 5e-3 * 1.01, (float((d > 1e-4).float().mean()), float(d.max()))
+    assert float((d > 2e-2 * 5e-3).float().mean()) < 1e-3 and float(d.max()) <= 10 * 5e-3, (float((d > 1e-4).float().mean()), float(d.max()))
     d = (m.k0.grid.detach().cpu() - om['k0'].detach()).abs()
     assert float((d > 2e-2 * 1e-1).float().mean()) < 1e-4, float((d > 2e-3).float().mean())

@@ -104,6 +104,55 @@ def test_fused_march_matches_staged_reference_path():
     exact(m.hit_coarse_geo(cu(o), cu(d), 0.3, 6.0, 0.5), hit, 'hit')
 
 
+@pytest.mark.parametrize('kind', ['smooth', 'noise', 'on_threshold'])
+def test_march_cell_verdicts_are_exact(kind):
+    """vx_march_flags_cells (per-cell pass / fail / evaluate verdicts, vx_mask_cache_cells) sets exactly the keep bits of
+    vx_march_flags (every sample through the 8-corner interpolation + softplus + exp of lib/voxurf_fine.py:930-942)."""
+    from voxurf_b200._lib import call
+    rs = np.random.RandomState(17)
+    G, N = 40, 3000
+    act_shift, ratio, thres = -4.0, 0.5, 1e-3
+    ax = np.linspace(-1, 1, G, dtype=np.float32)
+    r = np.sqrt(ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2)
+    if kind == 'smooth':
+        dens = (0.6 - r) * 30                                   # a ball of occupied space, free outside
+    elif kind == 'noise':
+        dens = rs.standard_normal((G, G, G)) * 6                # verdicts change from cell to cell
+    else:
+        # constant density sitting (in fp32) on the threshold itself, + noise of a few ulp: no cell may get a verdict
+        d0 = float(np.log(np.expm1(-np.log1p(-thres) / ratio))) - act_shift
+        dens = np.full((G, G, G), d0) * (1 + rs.randint(-3, 4, (G, G, G)) * 6e-8)
+    dens = cu(T(dens.astype(np.float32))).contiguous()
+    cells = torch.empty(G, G, G, dtype=torch.uint8, device=DEV)
+    call('vx_mask_cache_cells', dens, G, G, G, act_shift, ratio, thres, cells)
+    hist = torch.bincount(cells.view(-1).long(), minlength=3).tolist()
+    if kind == 'smooth':
+        assert hist[0] > 0.3 * G ** 3 and hist[1] > 0.05 * G ** 3 and 0 < hist[2] < 0.25 * G ** 3, hist
+    if kind == 'on_threshold':
+        assert hist[0] == 0 and hist[1] == 0, hist
+    o, d, _ = rays(N)
+    o, d = cu(o), cu(d)
+    mn, mx = cu(XYZ_MIN), cu(XYZ_MAX)
+    stepdist = 0.5 * 2.0 / 96
+    t_min, t_max = torch.empty(N, device=DEV), torch.empty(N, device=DEV)
+    n_steps = torch.empty(N, dtype=torch.int64, device=DEV)
+    start, dirs = torch.empty(N, 3, device=DEV), torch.empty(N, 3, device=DEV)
+    offsets = torch.empty(N + 1, dtype=torch.int64, device=DEV)
+    call('vx_ray_setup', o, d, mn, mx, 0.3, 1e9, stepdist, N, t_min, t_max, n_steps, start, dirs, offsets)
+    words = int(offsets[-1]) // 32 + N + 1
+    out = []
+    for tab in (None, cells):
+        bi, bk = (torch.zeros(words, dtype=torch.int32, device=DEV) for _ in range(2))
+        kc, ko = torch.zeros(N, dtype=torch.int32, device=DEV), torch.zeros(N + 1, dtype=torch.int32, device=DEV)
+        # the mask grid spans a smaller box than the rays' box: samples outside it take the exact (zero-padded) path
+        call('vx_march_flags_cells', start, dirs, mn, mx, offsets, N, stepdist, dens, G, G, G, [-0.9, -0.9, -0.9], [0.9, 0.9, 0.9],
+             act_shift, ratio, thres, tab, bi, bk, kc, ko)
+        out.append((bi, bk, kc, ko))
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+    assert int(out[0][3][-1]) > 0 or kind == 'on_threshold'
+
+
 # ------------------------------------------------------------------------------------------------ raw2alpha / alpha2weight
 def test_raw2alpha():
     from voxurf_b200 import render_utils_cuda as ru
@@ -220,10 +269,12 @@ def test_adam_touched_live_bitmaps_are_bit_identical_to_dense(C):
     N = V * C
     p0 = cu(T(rs.standard_normal(N).astype(np.float32)))
     state = {k: [p0.clone(), torch.zeros(N, device='cuda'), torch.zeros(N, device='cuda'), torch.zeros(N, device='cuda')]
-             for k in ('dense', 'sparse')}
+             for k in ('dense', 'sparse', 'worklist')}
     n_words = (V + 31) // 32
     touched = torch.zeros(n_words, dtype=torch.int32, device='cuda')
     live = torch.zeros(n_words, dtype=torch.int32, device='cuda')
+    touched_w, live_w = torch.zeros_like(touched), torch.zeros_like(live)     # the work-list form keeps its own pair
+    work = torch.zeros(n_words + 1, dtype=torch.int32, device='cuda')
     ever = np.zeros(V, bool)
     for it in range(5):
         vox = rs.choice(V, size=V // 7, replace=False)
@@ -235,8 +286,13 @@ def test_adam_touched_live_bitmaps_are_bit_identical_to_dense(C):
         words = np.packbits(bits.reshape(-1, 32), axis=1, bitorder='little').view(np.uint32).reshape(-1).astype(np.int64)
         touched.copy_(torch.from_numpy(np.where(words >= 2 ** 31, words - 2 ** 32, words)).to(torch.int32))
         bc1, bc2 = 1 - 0.9 ** (it + 1), 1 - 0.99 ** (it + 1)
+        touched_w.copy_(touched)
         for k, st in state.items():
             st[1].copy_(cu(T(g.reshape(-1))))
+            if k == 'worklist':     # vx_adam_step_worklist: compacted word list, vx_bitmap_merge folded in
+                call('vx_adam_step_worklist', st[0], st[1], st[2], st[3], N, 0.9, 0.99, 1 - 0.9, 1 - 0.99, 0.1 / bc1,
+                     float(np.sqrt(bc2)), 1e-8, 1, touched_w, live_w, C, 1, work, None)
+                continue
             bm = (touched, live) if k == 'sparse' else (None, None)
             call('vx_adam_step', st[0], st[1], st[2], st[3], None, N, 0.9, 0.99, 1 - 0.9, 1 - 0.99, 0.1 / bc1,
                  float(np.sqrt(bc2)), 1e-8, 0, 1, bm[0], bm[1], C, None)
@@ -244,9 +300,10 @@ def test_adam_touched_live_bitmaps_are_bit_identical_to_dense(C):
         assert (touched == 0).all()
         got = np.unpackbits(live.cpu().numpy().view(np.uint8), bitorder='little')[:V].astype(bool)
         assert (got == ever).all()
-        for a, b in zip(state['dense'], state['sparse']):
-            assert torch.equal(a, b)
-        assert (state['sparse'][1] == 0).all()
+        assert (touched_w == 0).all() and torch.equal(live_w, live)
+        for a, b, c in zip(state['dense'], state['sparse'], state['worklist']):
+            assert torch.equal(a, b) and torch.equal(a, c)
+        assert (state['sparse'][1] == 0).all() and (state['worklist'][1] == 0).all()
     assert not ever.all()       # the skip path was exercised
 
 

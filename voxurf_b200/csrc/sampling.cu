@@ -308,22 +308,82 @@ VX_API int vx_maskcache_lookup(const bool* world, const float* xyz, const float*
 // ---------------------------------------------------------------------------------------------
 struct VxMaskCache {
   const float* density;  // (X,Y,Z) max-pooled coarse density, or nullptr = no mask cache
+  const uint8_t* cells;  // optional (X,Y,Z) per-cell verdicts from vx_mask_cache_cells, or nullptr
   int X, Y, Z;
   float min[3], max[3];
   float act_shift, voxel_size_ratio, thres;
 };
 
+__device__ __forceinline__ float mask_cache_alpha(const VxMaskCache& mc, float d) {
+  const float x = d + mc.act_shift;
+  const float sp = (x > 20.f) ? x : log1pf(expf(x));
+  return 1.f - expf(__fmul_rn(-sp, mc.voxel_size_ratio));
+}
+
 __device__ __forceinline__ bool mask_cache_keep(const VxMaskCache& mc, float px, float py, float pz) {
   const float iz = vx_unnorm_coord(vx_norm_coord(px, mc.min[0], mc.max[0]), mc.X);
   const float iy = vx_unnorm_coord(vx_norm_coord(py, mc.min[1], mc.max[1]), mc.Y);
   const float ix = vx_unnorm_coord(vx_norm_coord(pz, mc.min[2], mc.max[2]), mc.Z);
+  if (mc.cells) {
+    // a sample strictly inside the lattice (all 8 corners valid; NaNs fail the comparisons) whose cell has a verdict
+    if (ix >= 0.f && ix < (float)(mc.Z - 1) && iy >= 0.f && iy < (float)(mc.Y - 1) && iz >= 0.f && iz < (float)(mc.X - 1)) {
+      const uint8_t c = __ldg(mc.cells + ((int)iz * mc.Y + (int)iy) * mc.Z + (int)ix);
+      if (c < 2) return c != 0;
+    }
+  }
   VxTap t;
   vx_make_tap(ix, iy, iz, mc.X, mc.Y, mc.Z, t);
   const float d = vx_tap_eval(mc.density, t);
-  const float x = d + mc.act_shift;
-  const float sp = (x > 20.f) ? x : log1pf(expf(x));
-  const float alpha = 1.f - expf(__fmul_rn(-sp, mc.voxel_size_ratio));
-  return alpha >= mc.thres;
+  return mask_cache_alpha(mc, d) >= mc.thres;
+}
+
+// Per-cell verdicts for the mask-cache test.  The interpolated density of a sample in cell (i,j,k) is a convex
+// combination of the cell's 8 corner values (ATen's fp32 weights sum to 1 within a few ulp) and alpha(d) is monotone
+// in d, so with generous margins for the fp32 evaluation (1e-5 (|d|max + 1) on the density: > 10x the worst-case
+// rounding of 8 weight products and 8 accumulations; 1e-5 + 1e-4 thres on alpha: > 10x the error of expf / log1pf /
+// 1 - exp cancellation)
+//   alpha(min corner - margin) >= thres + tol  =>  every sample of the cell passes   (code 1)
+//   alpha(max corner + margin) <= thres - tol  =>  every sample of the cell fails    (code 0)
+// and the cell needs the exact evaluation otherwise (code 2: the shell where the mask changes; also the last index along
+// each axis, which has no upper corner).  The march then spends the 8 loads + softplus + 2 exp only on the shell, with
+// bit-identical keep flags (tests/test_gpu_ops.py::test_march_cell_verdicts_are_exact).
+__global__ void k_mask_cache_cells(VxMaskCache mc, uint8_t* __restrict__ cells) {
+  const int64_t n = (int64_t)mc.X * mc.Y * mc.Z;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(v % mc.Z), j = (int)((v / mc.Z) % mc.Y), i = (int)(v / ((int64_t)mc.Z * mc.Y));
+    uint8_t code = 2;
+    if (i < mc.X - 1 && j < mc.Y - 1 && k < mc.Z - 1) {
+      float lo = INFINITY, hi = -INFINITY;
+      bool finite = true;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float d = mc.density[v + (c & 1) + ((c >> 1) & 1) * mc.Z + (c >> 2) * (int64_t)mc.Y * mc.Z];
+        finite &= (fabsf(d) <= 3.0e38f);
+        lo = fminf(lo, d); hi = fmaxf(hi, d);
+      }
+      if (finite) {
+        const float margin = 1e-5f * (fmaxf(fabsf(lo), fabsf(hi)) + 1.f);
+        const float tol = 1e-5f + 1e-4f * fabsf(mc.thres);
+        const float a_lo = mask_cache_alpha(mc, lo - margin), a_hi = mask_cache_alpha(mc, hi + margin);
+        if (a_lo >= mc.thres + tol) code = 1;
+        else if (a_hi <= mc.thres - tol) code = 0;
+      }
+    }
+    cells[v] = code;
+  }
+}
+
+VX_API int vx_mask_cache_cells(const float* mc_density, int mc_X, int mc_Y, int mc_Z, float act_shift,
+                               float voxel_size_ratio, float thres, uint8_t* cells, cudaStream_t st) {
+  const int64_t n = (int64_t)mc_X * mc_Y * mc_Z;
+  if (n <= 0) return 0;
+  VX_REQUIRE(n < ((int64_t)1 << 31), "vx_mask_cache_cells", "mask grid too large");
+  VxMaskCache mc;
+  mc.density = mc_density; mc.cells = nullptr; mc.X = mc_X; mc.Y = mc_Y; mc.Z = mc_Z;
+  for (int c = 0; c < 3; ++c) { mc.min[c] = 0.f; mc.max[c] = 1.f; }
+  mc.act_shift = act_shift; mc.voxel_size_ratio = voxel_size_ratio; mc.thres = thres;
+  k_mask_cache_cells<<<(int)min((int64_t)vx_blocks(n, 256), (int64_t)vx_num_sms() * 16), 256, 0, st>>>(mc, cells);
+  return vx_check_launch("vx_mask_cache_cells");
 }
 
 // standalone MaskCache.forward (voxurf_fine.py:930-942) on explicit points
@@ -337,7 +397,7 @@ VX_API int vx_mask_cache_query(const float* mc_density, int mc_X, int mc_Y, int 
                                const float* xyz, int64_t n, bool* out, cudaStream_t st) {
   if (n <= 0) return 0;
   VxMaskCache mc;
-  mc.density = mc_density; mc.X = mc_X; mc.Y = mc_Y; mc.Z = mc_Z;
+  mc.density = mc_density; mc.cells = nullptr; mc.X = mc_X; mc.Y = mc_Y; mc.Z = mc_Z;
   for (int c = 0; c < 3; ++c) { mc.min[c] = mc_min_host[c]; mc.max[c] = mc_max_host[c]; }
   mc.act_shift = act_shift; mc.voxel_size_ratio = voxel_size_ratio; mc.thres = thres;
   const int blocks = (int)min((int64_t)vx_blocks(n, 256), (int64_t)vx_num_sms() * 16);
@@ -456,14 +516,14 @@ __global__ void k_march_emit(const int64_t* __restrict__ offsets, int n_rays, co
   }
 }
 
-VX_API int vx_march_flags(const float* rays_start, const float* rays_dir, const float* xyz_min, const float* xyz_max,
-                          const int64_t* offsets, int n_rays, float stepdist, const float* mc_density, int mc_X, int mc_Y,
-                          int mc_Z, const float* mc_min_host, const float* mc_max_host, float act_shift,
-                          float voxel_size_ratio, float thres, uint32_t* bits_inbbox, uint32_t* bits_keep,
-                          int* keep_count, int* keep_off, cudaStream_t st) {
+VX_API int vx_march_flags_cells(const float* rays_start, const float* rays_dir, const float* xyz_min, const float* xyz_max,
+                                const int64_t* offsets, int n_rays, float stepdist, const float* mc_density, int mc_X,
+                                int mc_Y, int mc_Z, const float* mc_min_host, const float* mc_max_host, float act_shift,
+                                float voxel_size_ratio, float thres, const uint8_t* mc_cells, uint32_t* bits_inbbox,
+                                uint32_t* bits_keep, int* keep_count, int* keep_off, cudaStream_t st) {
   if (n_rays <= 0) return 0;
   VxMaskCache mc;
-  mc.density = mc_density; mc.X = mc_X; mc.Y = mc_Y; mc.Z = mc_Z;
+  mc.density = mc_density; mc.cells = mc_density ? mc_cells : nullptr; mc.X = mc_X; mc.Y = mc_Y; mc.Z = mc_Z;
   for (int c = 0; c < 3; ++c) { mc.min[c] = mc_density ? mc_min_host[c] : 0.f; mc.max[c] = mc_density ? mc_max_host[c] : 1.f; }
   mc.act_shift = act_shift; mc.voxel_size_ratio = voxel_size_ratio; mc.thres = thres;
   const int blocks = min(vx_blocks((int64_t)n_rays * 32, 256), vx_num_sms() * 8);
@@ -473,6 +533,16 @@ VX_API int vx_march_flags(const float* rays_start, const float* rays_dir, const 
   if (rc) return rc;
   k_scan_i32<<<1, 1024, 0, st>>>(keep_count, n_rays, keep_off);
   return vx_check_launch("vx_march_flags(scan)");
+}
+
+VX_API int vx_march_flags(const float* rays_start, const float* rays_dir, const float* xyz_min, const float* xyz_max,
+                          const int64_t* offsets, int n_rays, float stepdist, const float* mc_density, int mc_X, int mc_Y,
+                          int mc_Z, const float* mc_min_host, const float* mc_max_host, float act_shift,
+                          float voxel_size_ratio, float thres, uint32_t* bits_inbbox, uint32_t* bits_keep,
+                          int* keep_count, int* keep_off, cudaStream_t st) {
+  return vx_march_flags_cells(rays_start, rays_dir, xyz_min, xyz_max, offsets, n_rays, stepdist, mc_density, mc_X, mc_Y, mc_Z,
+                              mc_min_host, mc_max_host, act_shift, voxel_size_ratio, thres, nullptr, bits_inbbox, bits_keep,
+                              keep_count, keep_off, st);
 }
 
 VX_API int vx_march_emit(const int64_t* offsets, int n_rays, const uint32_t* bits_keep, const int* keep_off,
@@ -628,7 +698,7 @@ VX_API int vx_rays_hit_mask(const float* rays_o, const float* rays_d, int n_rays
   VxGrid box;
   box.X = box.Y = box.Z = box.C = 1; box.cl = 0;
   VxMaskCache mc;
-  mc.density = mc_density; mc.X = mc_X; mc.Y = mc_Y; mc.Z = mc_Z;
+  mc.density = mc_density; mc.cells = nullptr; mc.X = mc_X; mc.Y = mc_Y; mc.Z = mc_Z;
   for (int c = 0; c < 3; ++c) {
     box.min[c] = xyz_min_host[c]; box.max[c] = xyz_max_host[c];
     mc.min[c] = mc_min_host[c]; mc.max[c] = mc_max_host[c];

@@ -120,11 +120,12 @@ class FusedFineStep:
         # the whole voxel where not live (m = v = g = 0: the dense update is the identity) -- same result, bit for bit,
         # as utils.Adam over the dense grid (lib/utils.py:154-199), far less traffic.  Only the scatter kernels write
         # k0 gradients in the fine stage (weight_tv_k0 = 0, configs/default_fine_s.py).
-        self.k0_touched = self.k0_live = None
+        self.k0_touched = self.k0_live = self._k0_list = None
         if self.k0_cl and sparse_adam:
             n_words = (self.X * self.Y * self.Z + 31) // 32
             self.k0_touched = torch.zeros(n_words, dtype=torch.int32, device=dev)
             self.k0_live = torch.zeros(n_words, dtype=torch.int32, device=dev)
+            self._k0_list = torch.zeros(n_words + 1, dtype=torch.int32, device=dev)      # vx_adam_step_worklist scratch
         # deterministic=True: every scatter of the backward pass (k0 rows, sdf taps, split-K weight gradients) accumulates in
         # 64-bit fixed point (order-independent integer sums) and is folded into the fp32 gradient buffers afterwards:
         # gradients -- and with them the whole training trajectory -- are bit-reproducible run to run.  Costs one dense
@@ -222,8 +223,8 @@ class FusedFineStep:
         self._begin_param_gather()      # (sharded data-parallel step) runs under ray set-up and the march
         call('vx_ray_setup', rays_o, rays_d, m.xyz_min, m.xyz_max, near, 1e9, self.stepdist, N, self.t_min, self.t_max,
              self.n_steps, self.start, self.dirs, self.offsets)
-        mc = m.mask_cache.march_args() if m.mask_cache is not None else (None, 1, 1, 1, [0., 0., 0.], [1., 1., 1.], 0., 1., 0.)
-        call('vx_march_flags', self.start, self.dirs, m.xyz_min, m.xyz_max, self.offsets, N, self.stepdist, *mc,
+        mc = m.mask_cache.march_args_cells() if m.mask_cache is not None else (None, 1, 1, 1, [0., 0., 0.], [1., 1., 1.], 0., 1., 0., None)
+        call('vx_march_flags_cells', self.start, self.dirs, m.xyz_min, m.xyz_max, self.offsets, N, self.stepdist, *mc,
              self.bits_in, self.bits_keep, self.keep_count, self.keep_off)
         call('vx_march_emit', self.offsets, N, self.bits_keep, self.keep_off, self.cap2, self.ray_id, self.step_id, None)
         n2 = self.keep_off[N:]
@@ -634,11 +635,16 @@ class FusedFineStep:
                         ev[1].record()
                         self.timings.append((name, ev))
                     continue
-                call('vx_adam_step', *tensors, None, tensors[0].numel(),
-                     beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1, touched, live, self.C,
-                     None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
-                if touched is not None:
-                    call('vx_bitmap_merge', live, touched, touched.numel())
+                if touched is not None and self.C <= 12 and tensors[0].numel() < 2 ** 32:
+                    call('vx_adam_step_worklist', *tensors, tensors[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
+                         math.sqrt(bc2), eps, 1, touched, live, self.C, 1, self._k0_list,
+                         None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
+                else:
+                    call('vx_adam_step', *tensors, None, tensors[0].numel(),
+                         beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1, touched, live, self.C,
+                         None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
+                    if touched is not None:
+                        call('vx_bitmap_merge', live, touched, touched.numel())
                 if timed:
                     ev[1].record()
                     self.timings.append((name, ev))

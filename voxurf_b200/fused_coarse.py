@@ -135,7 +135,7 @@ class FusedCoarseStep:
         X, Y, Z, mn, mx = self._geom()
         call('vx_ray_setup', rays_o, rays_d, m.xyz_min, m.xyz_max, self.rk['near'], 1e9, self.stepdist, N, self.t_min, self.t_max,
              self.n_steps, self.start, self.dirs, self.offsets)
-        call('vx_march_flags', self.start, self.dirs, m.xyz_min, m.xyz_max, self.offsets, N, self.stepdist, *m.mask_cache.march_args(),
+        call('vx_march_flags_cells', self.start, self.dirs, m.xyz_min, m.xyz_max, self.offsets, N, self.stepdist, *m.mask_cache.march_args_cells(),
              self.bits_in, self.bits_keep, self.keep_count, self.keep_off)
         call('vx_march_emit', self.offsets, N, self.bits_keep, self.keep_off, self.cap2, self.ray_id, self.step_id, None)
         n2 = self.keep_off[N:]

@@ -148,6 +148,17 @@ class MaskCache(nn.Module):
              self.act_shift, self.voxel_size_ratio, float(self.mask_cache_thres), pts, pts.shape[0], out)
         return out.reshape(shape)
 
+    def march_args_cells(self):
+        """march_args() + the per-cell verdict table, for vx_march_flags_cells (built once per device / threshold)."""
+        d = self.density
+        key = (d.data_ptr(), d._version, float(self.mask_cache_thres))
+        if getattr(self, '_cells_key', None) != key:
+            self._cells = torch.empty(d.shape[2:], dtype=torch.uint8, device=d.device)
+            call('vx_mask_cache_cells', d, d.shape[2], d.shape[3], d.shape[4], self.act_shift, self.voxel_size_ratio,
+                 float(self.mask_cache_thres), self._cells)
+            self._cells_key = key
+        return self.march_args() + (self._cells,)
+
     def march_args(self):
         """(density, X, Y, Z, min_host, max_host, act_shift, voxel_size_ratio, thres) for vx_march_flags."""
         d = self.density
