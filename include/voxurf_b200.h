@@ -109,9 +109,9 @@ int vx_adam_step_blocklive(float* param, float* grad, float* exp_avg, float* exp
                            float sqrt_bias_correction2, float eps, int zero_grad, uint8_t* live_blocks,
                            const float* step_dev, cudaStream_t stream);
 /* The bitmap form of vx_adam_step (lib/utils.py:154-199 restricted to the voxels in touched | live) dealt through a
- * compacted work list of the non-empty bitmap words instead of a static word -> warp mapping (the live voxels sit in
- * the surface shell: balanced, and every lane keeps all of its loads of a word in flight).  3 <= group <= 12.
- * work: numel / group / 32 + 1 uint32 of scratch.  merge != 0 also performs vx_bitmap_merge in the same pass.
+ * compacted list of the live voxels instead of a static bitmap-word -> warp mapping (the live voxels sit in the surface
+ * shell, 1-3 per word: the list keeps every lane busy and every load independent).  group = elements per voxel.
+ * work: numel / group + 1 uint32 of scratch.  merge != 0 also performs vx_bitmap_merge in the same pass.
  * Bit-identical to the dense pass. */
 int vx_adam_step_worklist(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float beta1,
                           float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,

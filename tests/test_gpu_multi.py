@@ -29,7 +29,7 @@ def _batches(world, n_rays):
     return out
 
 
-def _worker(rank, world, port, n_rays, step, sparse, ret, dense_exchange=False, graph=False):
+def _worker(rank, world, port, n_rays, step, sparse, ret, dense_exchange=False, graph=False, defer=False):
     import torch.distributed as dist
     from voxurf_b200.fused import FusedFineStep
     from voxurf_b200.parallel import GradSync
@@ -40,7 +40,7 @@ def _worker(rank, world, port, n_rays, step, sparse, ret, dense_exchange=False, 
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     m = _build(dev)
     fs = FusedFineStep(m, n_rays, FINE_TRAIN, RK, row_capacity=8192, world=world, rank=rank, sparse_k0_exchange=sparse,
-                       dense_exchange=dense_exchange, use_graph=graph)
+                       dense_exchange=dense_exchange, use_graph=graph, defer_optimizer=defer)
     assert fs.sharded == (not dense_exchange)
     b = [t.to(dev) for t in _batches(world, n_rays)[rank]]
     if graph:
@@ -49,7 +49,7 @@ def _worker(rank, world, port, n_rays, step, sparse, ret, dense_exchange=False, 
             fs.step(*b, step + it)
         fs.sync_params()
         fs.poll_overflow(force=True)
-        assert len(fs._graphs) == 2
+        assert len(fs._graphs) == (3 if defer else 2), list(fs._graphs)
         ret[rank] = ({}, {'sdf': m.sdf.grid.detach().cpu(), 'k0': m.k0.grid.detach().contiguous().cpu(), 'mlp1': fs.mlp1.flat.detach().cpu()})
         fs.release_graphs()
         dist.barrier()
@@ -108,9 +108,11 @@ def test_two_gpu_gradients_equal_single_gpu_on_concatenated_batch(sparse, dense_
     np.testing.assert_allclose(ret[0][1]['k0'].numpy(), ret[1][1]['k0'].numpy(), rtol=1e-4, atol=2e-3)
 
 
-def test_two_gpu_graph_replayed_steps_follow_single_gpu():
+@pytest.mark.parametrize('defer', [False, True])
+def test_two_gpu_graph_replayed_steps_follow_single_gpu(defer):
     """Seven whole steps (TV iterations included) as CUDA-graph replays with the slab-sharded exchange captured inside,
-    against a single GPU stepping on the concatenated batch."""
+    against a single GPU stepping on the concatenated batch.  defer: as bench.py runs it -- the optimizer phase and the
+    gradient exchange of step k execute inside the launch of step k + 1, beside its march."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
@@ -119,7 +121,7 @@ def test_two_gpu_graph_replayed_steps_follow_single_gpu():
     world, n_rays, step = 2, 512, 15001
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, n_rays, step, True, ret, False, True), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n_rays, step, True, ret, False, True, defer), nprocs=world, join=True)
     dev = torch.device('cuda', 0)
     m = _build(dev)
     fs = FusedFineStep(m, n_rays * world, FINE_TRAIN, RK, row_capacity=16384)

@@ -259,13 +259,13 @@ def test_trainer_adam_semantics_and_fused_zero_grad():
             assert (p.grad == 0).all()
 
 
-@pytest.mark.parametrize('C', [12, 6, 8])
+@pytest.mark.parametrize('C', [12, 6, 8, 3])
 def test_adam_touched_live_bitmaps_are_bit_identical_to_dense(C):
     """vx_adam_step with the touched / live voxel bitmaps (the fused step's k0 update) == the dense pass, bit for bit,
     over several steps in which the touched set moves; vx_bitmap_merge maintains `live`."""
     from voxurf_b200._lib import call
     rs = np.random.RandomState(31 + C)
-    V = 4099 if C % 4 == 0 else 4098    # numel % 4 == 0; C = 6 makes float4 groups straddle two voxels
+    V = 4099 if C % 4 == 0 else (4098 if C % 2 == 0 else 4100)    # numel % 4 == 0; C = 6 makes float4 groups straddle two voxels
     N = V * C
     p0 = cu(T(rs.standard_normal(N).astype(np.float32)))
     state = {k: [p0.clone(), torch.zeros(N, device='cuda'), torch.zeros(N, device='cuda'), torch.zeros(N, device='cuda')]
@@ -274,7 +274,7 @@ def test_adam_touched_live_bitmaps_are_bit_identical_to_dense(C):
     touched = torch.zeros(n_words, dtype=torch.int32, device='cuda')
     live = torch.zeros(n_words, dtype=torch.int32, device='cuda')
     touched_w, live_w = torch.zeros_like(touched), torch.zeros_like(live)     # the work-list form keeps its own pair
-    work = torch.zeros(n_words + 1, dtype=torch.int32, device='cuda')
+    work = torch.zeros(V + 1, dtype=torch.int32, device='cuda')
     ever = np.zeros(V, bool)
     for it in range(5):
         vox = rs.choice(V, size=V // 7, replace=False)

@@ -257,86 +257,99 @@ VX_API int vx_adam_step(float* param, float* grad, float* exp_avg, float* exp_av
 }
 
 // ---------------------------------------------------------------------------------------------
-// Work-list form of the sparse-aware pass.  k_adam_sparse deals the bitmap words to the warps statically; the live words
+// Work-list form of the sparse-aware pass.  k_adam_sparse deals the bitmap words to the warps statically; the live voxels
 // sit in the shell around the surface, so a few warps own most of them and walk them one dependent round trip after the
-// other (measured: 112 us for 158 MB).  Here a first kernel compacts the indices of the non-empty words into a list
-// (warp-aggregated atomics; the order is irrelevant, every word is independent) and a second one deals the LIST to the
-// warps, each lane holding all of its float4s of a word (3 at 12 channels) in flight at once.  Same arithmetic per
-// element, bit-identical results.  kMerge folds vx_bitmap_merge (live |= touched; touched = 0) into the same pass: only
-// words on the list can have a touched bit.
+// other, most lanes idle (a word holds 1-3 live voxels: 112 us for 158 MB).  Here a first kernel expands the bitmaps into a
+// list of live voxels (warp-scanned counts, one atomic per warp; the order is irrelevant, every voxel is independent; the
+// touched flag rides in bit 31) and performs vx_bitmap_merge (live |= touched, touched = 0) on the way; a second kernel
+// deals the LIST to the threads, one 16-byte (8- / 4-byte for channel counts that are not multiples of 4 / 2) piece of a
+// voxel per thread: every lane busy, every load independent.  Same arithmetic per element: bit-identical results.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bitmap_worklist(const uint32_t* __restrict__ touched, const uint32_t* __restrict__ live,
-                                                         int64_t n_words, uint32_t* __restrict__ list,
-                                                         uint32_t* __restrict__ count) {
+__global__ void __launch_bounds__(256) k_bitmap_voxel_list(uint32_t* __restrict__ touched, uint32_t* __restrict__ live,
+                                                           int64_t n_words, int64_t n_vox, int merge,
+                                                           uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_round = (n_words + 31) & ~(int64_t)31;      // whole warps stay converged for the ballot
+  const int64_t n_round = (n_words + 31) & ~(int64_t)31;      // whole warps stay converged for the scan
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_round; w += stride) {
-    const bool busy = w < n_words && ((touched[w] | (live ? live[w] : 0xffffffffu)) != 0u);
-    const uint32_t b = __ballot_sync(0xffffffffu, busy);
-    if (!b) continue;
+    uint32_t tw = 0u, lw = 0u;
+    if (w < n_words) {
+      tw = touched[w];
+      lw = live ? live[w] : 0xffffffffu;
+      if (w == n_words - 1 && (n_vox & 31)) {          // bits beyond the last voxel do not exist
+        const uint32_t valid = (1u << (n_vox & 31)) - 1u;
+        tw &= valid; lw &= valid;
+      }
+    }
+    const uint32_t busy = tw | lw;
+    if (!__ballot_sync(0xffffffffu, busy != 0u)) continue;
+    const int n = __popc(busy);
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += y;
+    }
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(b));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (busy) list[base + __popc(b & ((1u << lane) - 1u))] = (uint32_t)w;
+    if (lane == 31) base = atomicAdd(count, (uint32_t)incl);
+    base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(incl - n);
+    uint32_t b = busy;
+    while (b) {
+      const int bit = __ffs(b) - 1;
+      b &= b - 1;
+      list[base++] = ((uint32_t)w * 32u + (uint32_t)bit) | (((tw >> bit) & 1u) << 31);
+    }
+    if (merge && tw) { if (live) live[w] = lw | tw; touched[w] = 0u; }
   }
 }
 
-template <bool kZeroGrad, bool kMerge, int kIters>
-__global__ void __launch_bounds__(256) k_adam_worklist(float* __restrict__ param, float* __restrict__ grad,
-                                                       float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                                                       int64_t n_vox, AdamCoef c, uint32_t* touched, uint32_t* live,
-                                                       uint32_t group, const uint32_t* __restrict__ list,
-                                                       const uint32_t* __restrict__ count,
-                                                       const float* __restrict__ step_dev) {
+template <int kW> struct VxVec;
+template <> struct VxVec<4> { typedef float4 T; };
+template <> struct VxVec<2> { typedef float2 T; };
+template <> struct VxVec<1> { typedef float T; };
+
+template <int kW, bool kZeroGrad>
+__global__ void __launch_bounds__(256) k_adam_voxel_list(float* __restrict__ param, float* __restrict__ grad,
+                                                         float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                         AdamCoef c, uint32_t parts, const uint32_t* __restrict__ list,
+                                                         const uint32_t* __restrict__ count,
+                                                         const float* __restrict__ step_dev) {
+  typedef typename VxVec<kW>::T V;
   if (step_dev) { c.step_size = __ldg(step_dev); c.sqrt_bc2 = __ldg(step_dev + 1); }
-  const int lane = threadIdx.x & 31;
-  const uint32_t n = *count;
-  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  float4* p4 = reinterpret_cast<float4*>(param);
-  float4* g4 = reinterpret_cast<float4*>(grad);
-  float4* m4 = reinterpret_cast<float4*>(exp_avg);
-  float4* v4 = reinterpret_cast<float4*>(exp_avg_sq);
-  const uint32_t per_word4 = 8u * group;
-  const int64_t f4_total = (n_vox * group) >> 2;
-  for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += n_warps) {
-    const uint32_t w = list[k];
-    uint32_t tw = 0u, lw = 0xffffffffu;
-    if (lane == 0) { tw = touched[w]; if (live) lw = live[w]; }
-    tw = __shfl_sync(0xffffffffu, tw, 0); lw = __shfl_sync(0xffffffffu, lw, 0);
-    const int64_t f4_base = (int64_t)w * per_word4;
-    float4 g[kIters], p[kIters], m[kIters], v[kIters];
-    bool on[kIters], tt[kIters];
+  const int64_t n = (int64_t)(*count) * parts;
+  V* p4 = reinterpret_cast<V*>(param);
+  V* g4 = reinterpret_cast<V*>(grad);
+  V* m4 = reinterpret_cast<V*>(exp_avg);
+  V* v4 = reinterpret_cast<V*>(exp_avg_sq);
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t e = __ldg(list + k / parts);
+    const bool t = (e >> 31) != 0u;
+    const int64_t i = (int64_t)(e & 0x7fffffffu) * parts + (k % parts);
+    V g;
+    float* gf = reinterpret_cast<float*>(&g);
+    if (t) g = g4[i];
+    else {
 #pragma unroll
-    for (int j = 0; j < kIters; ++j) {
-      const uint32_t o = lane + 32u * j;
-      const int64_t i = f4_base + o;
-      const uint32_t e = o << 2, b0 = min(e / group, 31u), b1 = min((e + 3u) / group, 31u);
-      const uint32_t t = ((tw >> b0) | (tw >> b1)) & 1u, l = ((lw >> b0) | (lw >> b1)) & 1u;
-      on[j] = o < per_word4 && i < f4_total && (t | l);
-      tt[j] = on[j] && t;
-      g[j] = tt[j] ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (on[j]) { p[j] = p4[i]; m[j] = m4[i]; v[j] = v4[i]; }
+      for (int j = 0; j < kW; ++j) gf[j] = 0.f;
     }
+    V p = p4[i], m = m4[i], v = v4[i];
+    float* pf = reinterpret_cast<float*>(&p);
+    float* mf = reinterpret_cast<float*>(&m);
+    float* vf = reinterpret_cast<float*>(&v);
 #pragma unroll
-    for (int j = 0; j < kIters; ++j) {
-      if (!on[j]) continue;
-      const int64_t i = f4_base + lane + 32u * j;
-      adam_one<false>(p[j].x, g[j].x, m[j].x, v[j].x, 1.f, c);
-      adam_one<false>(p[j].y, g[j].y, m[j].y, v[j].y, 1.f, c);
-      adam_one<false>(p[j].z, g[j].z, m[j].z, v[j].z, 1.f, c);
-      adam_one<false>(p[j].w, g[j].w, m[j].w, v[j].w, 1.f, c);
-      p4[i] = p[j]; m4[i] = m[j]; v4[i] = v[j];
-      if (kZeroGrad && tt[j]) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kW; ++j) adam_one<false>(pf[j], gf[j], mf[j], vf[j], 1.f, c);
+    p4[i] = p; m4[i] = m; v4[i] = v;
+    if (kZeroGrad && t) {
+#pragma unroll
+      for (int j = 0; j < kW; ++j) gf[j] = 0.f;
+      g4[i] = g;
     }
-    if (kMerge && lane == 0 && tw) { if (live) live[w] = lw | tw; touched[w] = 0u; }
   }
 }
 
 // trainer semantics (lib/utils.py:154-199) over the voxels flagged in touched | live (see k_adam above), work-list form.
-// group: elements per voxel, 3 <= group <= 12, group % 4 == 0 or numel % 4 == 0 with 8 * group float4s per bitmap word;
-// work: n_words + 1 uint32 of scratch (word list + its counter at work[n_words]); merge != 0: live |= touched, touched = 0
-// in the same pass (then vx_bitmap_merge is not needed).
+// group: elements per voxel; work: numel / group + 1 uint32 of scratch (voxel list + its counter at the end);
+// merge != 0: live |= touched, touched = 0 in the same pass (then vx_bitmap_merge is not needed).
 VX_API int vx_adam_step_worklist(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t N, float beta1,
                                  float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
                                  float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched, uint32_t* live,
@@ -344,26 +357,26 @@ VX_API int vx_adam_step_worklist(float* param, float* grad, float* exp_avg, floa
   if (N <= 0) return 0;
   const bool aligned = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                          reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0;
-  VX_REQUIRE(touched && work && aligned && group >= 3 && group <= 12 && N % group == 0 && N % 4 == 0 && N < ((int64_t)1 << 32),
-             "vx_adam_step_worklist", "needs touched, work, 16-byte aligned tensors, 3 <= group <= 12, numel % group == 0, numel % 4 == 0, numel < 2^32");
+  VX_REQUIRE(touched && work && aligned && group >= 1 && N % group == 0 && N / group < ((int64_t)1 << 31),
+             "vx_adam_step_worklist", "needs touched, work, 16-byte aligned tensors, numel % group == 0, numel / group < 2^31");
   AdamCoef c;
   c.beta1 = beta1; c.beta2 = beta2; c.omb1 = one_minus_beta1; c.omb2 = one_minus_beta2; c.eps = eps;
   c.step_size = step_size; c.sqrt_bc2 = sqrt_bias_correction2;
   const int64_t n_vox = N / group, n_words = (n_vox + 31) / 32;
-  uint32_t* count = work + n_words;
+  uint32_t* count = work + n_vox;
   cudaError_t e = cudaMemsetAsync(count, 0, sizeof(uint32_t), st);
   if (e != cudaSuccess) { vx_set_error("vx_adam_step_worklist", cudaGetErrorString(e)); return -1; }
-  k_bitmap_worklist<<<(int)min((n_words + 255) / 256, (int64_t)vx_num_sms() * 8), 256, 0, st>>>(touched, live, n_words, work, count);
+  k_bitmap_voxel_list<<<(int)min((n_words + 255) / 256, (int64_t)vx_num_sms() * 8), 256, 0, st>>>(touched, live, n_words, n_vox, merge, work, count);
   int rc = vx_check_launch("vx_adam_step_worklist(list)");
   if (rc) return rc;
   const int blocks = vx_num_sms() * 8;
-  const int iters = (8 * group + 31) / 32;
-#define VX_AWL(ZG, MG, IT) k_adam_worklist<ZG, MG, IT><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_vox, c, touched, live, (uint32_t)group, work, count, step_dev)
-#define VX_AWL_IT(ZG, MG) { if (iters == 1) VX_AWL(ZG, MG, 1); else if (iters == 2) VX_AWL(ZG, MG, 2); else VX_AWL(ZG, MG, 3); }
-  if (zero_grad) { if (merge) VX_AWL_IT(true, true) else VX_AWL_IT(true, false) }
-  else { if (merge) VX_AWL_IT(false, true) else VX_AWL_IT(false, false) }
-#undef VX_AWL_IT
-#undef VX_AWL
+  const int w = group % 4 == 0 ? 4 : (group % 2 == 0 ? 2 : 1);
+  const uint32_t parts = (uint32_t)(group / w);
+#define VX_AVL(W, ZG) k_adam_voxel_list<W, ZG><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, c, parts, work, count, step_dev)
+  if (w == 4) { if (zero_grad) VX_AVL(4, true); else VX_AVL(4, false); }
+  else if (w == 2) { if (zero_grad) VX_AVL(2, true); else VX_AVL(2, false); }
+  else { if (zero_grad) VX_AVL(1, true); else VX_AVL(1, false); }
+#undef VX_AVL
   return vx_check_launch("vx_adam_step_worklist");
 }
 

@@ -125,7 +125,7 @@ class FusedFineStep:
             n_words = (self.X * self.Y * self.Z + 31) // 32
             self.k0_touched = torch.zeros(n_words, dtype=torch.int32, device=dev)
             self.k0_live = torch.zeros(n_words, dtype=torch.int32, device=dev)
-            self._k0_list = torch.zeros(n_words + 1, dtype=torch.int32, device=dev)      # vx_adam_step_worklist scratch
+            self._k0_list = torch.zeros(self.X * self.Y * self.Z + 1, dtype=torch.int32, device=dev)      # vx_adam_step_worklist scratch
         # deterministic=True: every scatter of the backward pass (k0 rows, sdf taps, split-K weight gradients) accumulates in
         # 64-bit fixed point (order-independent integer sums) and is folded into the fp32 gradient buffers afterwards:
         # gradients -- and with them the whole training trajectory -- are bit-reproducible run to run.  Costs one dense
@@ -163,6 +163,7 @@ class FusedFineStep:
         self.defer_optimizer = bool(defer_optimizer)
         self._pending = None
         self._opt_stream = None
+        self._k0_work, self._works = [], []      # outstanding NCCL work of the data-parallel exchange
         # Slab-sharded data-parallel exchange (SURVEY.md 8e "preferred form"): reduce-scatter of the sdf gradient over X-slabs,
         # regularisers + Adam on the owned slab only, all-gather of the updated sdf PARAMETERS at the start of the next step
         # (it overlaps ray set-up and the march, which read rays and the mask cache only).  Non-owned slabs of this rank's sdf
@@ -186,6 +187,14 @@ class FusedFineStep:
             self.groups = [('sdf', [m.sdf.grid], c['lrate_sdf']), ('k0', [m.k0.grid], c['lrate_k0']),
                            ('rgbnet', [self.mlp1.flat], c['lrate_rgbnet']), ('k_rgbnet', [self.mlp2.flat], c['lrate_k_rgbnet'])]
             self.lr = {name: lr for name, _, lr in self.groups}
+
+    # the model keeps a back-reference to its step (model._fused): copies / pickles of the model do not drag the step's
+    # buffers, events and CUDA graphs along
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (type(None), ())
 
     def _alloc_rows(self, cap):
         dev = self.dev
@@ -489,6 +498,7 @@ class FusedFineStep:
         if self.sparse_k0_exchange:
             for w in self._k0_work:
                 w.wait()
+            self._k0_work = []
             cap, C = self.cap4, self.C
             for r in range(self.world):      # every rank's rows, as many as it sent
                 xyz, g = self._k0_recv[r, :cap * 3].view(cap, 3), self._k0_recv[r, cap * 3:cap * (3 + C)].view(cap, C)
@@ -635,7 +645,7 @@ class FusedFineStep:
                         ev[1].record()
                         self.timings.append((name, ev))
                     continue
-                if touched is not None and self.C <= 12 and tensors[0].numel() < 2 ** 32:
+                if touched is not None:
                     call('vx_adam_step_worklist', *tensors, tensors[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
                          math.sqrt(bc2), eps, 1, touched, live, self.C, 1, self._k0_list,
                          None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
@@ -725,6 +735,12 @@ class FusedFineStep:
         row re-scatter, the regularisers' gradients, the Adam passes (run.py:641-659).  pend: dict(flags, step, lrs)."""
         flags, kw = pend['flags'], dict(step=pend['step'], lrs=pend['lrs'])
         if self.world > 1:
+            if self.defer_optimizer:
+                # the sdf reduce-scatter / MLP all-reduce of the pending step start HERE, not at the end of that step's
+                # body: every collective then begins and ends inside one launch of the step (a CUDA-graph capture cannot
+                # leave NCCL work unjoined, nor wait for work of an earlier launch), and they still run beside the k0
+                # re-scatter below and the next step's march
+                self._sync_begin()
             self._sync_k0()
             self.optimizer_step(only=('k0',), **kw)
             self._sync_end()
@@ -784,7 +800,12 @@ class FusedFineStep:
         if flags[0] and self.cfg['tv_terms']['smooth_grad_tv'] > 0:
             self.loss.add_(self.tv_loss)   # run.py:622-625 adds the regulariser to the reported loss
         if self.world > 1:
-            self._sync_begin()       # the sdf reduce-scatter (or all-reduce) and the MLP all-reduce start right after the backward pass
+            if self.defer_optimizer:
+                for w in self._k0_work:      # the k0 row all-gather started in the backward pass: join it inside this launch
+                    w.wait()
+                self._k0_work = []
+            else:
+                self._sync_begin()   # the sdf reduce-scatter (or all-reduce) and the MLP all-reduce start right after the backward pass
         if self._dev_consts is None:
             self.adam_steps += 1
         pend = dict(flags=flags, step=max(self.adam_steps, 1), lrs=dict(self.lr))
