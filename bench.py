@@ -64,6 +64,7 @@ def parse(argv=None):
     ap.add_argument('--no-defer', action='store_true', help='run the optimizer phase at the end of its own step instead of beside the next step\'s march')
     ap.add_argument('--dense-adam', action='store_true', help='k0 Adam over every voxel (no touched/live bitmaps)')
     ap.add_argument('--dense-exchange', action='store_true', help='multi-GPU: plain dense all-reduces instead of the slab-sharded exchange')
+    ap.add_argument('--no-k0-ownership', action='store_true', help='multi-GPU: every rank re-scatters all k0 rows and steps every voxel (no peer-memory stores)')
     ap.add_argument('--sustain', type=float, default=2.0, help='seconds of back-to-back steps for the `sustained` figure (0 = skip)')
     ap.add_argument('--no-parity-check', action='store_true', help='N > 1: skip the untimed replica / gradient parity check')
     ap.add_argument('--phases', action='store_true', help='also print the per-kernel CUDA-event breakdown to stderr')
@@ -339,7 +340,8 @@ def main():
     if args.path == 'fused':
         from voxurf_b200.fused import FusedFineStep
         fused = FusedFineStep(model, rays, FINE_TRAIN, RENDER_KW, world=world, rank=rank, sparse_adam=not args.dense_adam,
-                              use_graph=not args.no_graph, dense_exchange=args.dense_exchange, defer_optimizer=not args.no_defer)
+                              use_graph=not args.no_graph, dense_exchange=args.dense_exchange, defer_optimizer=not args.no_defer,
+                              k0_ownership=not args.no_k0_ownership)
         fused.calibrate(*dev_pool[0][:3], global_step=START_STEP, headroom=1.35)
         step_fn = lambda b, gs: fused.step(*b, gs)
         decay = fused.apply_lr_decay
@@ -384,6 +386,13 @@ def main():
                  'optimizer': ('deferred: the Adam / regulariser phase of step k runs beside the march of step k + 1 (one optimizer phase per '
                                'timed step all the same)') if (fused is not None and fused.defer_optimizer) else 'end of step'}
 
+    if fused is not None and world > 1:
+        execution['exchange'] = ('sdf: in-place reduce-scatter over X-slabs + slab Adam + in-place all-gather of the parameters; '
+                                 'MLPs: one all-reduce; k0: rows all-gathered, ' +
+                                 ('each rank scatters / steps its own X-slab and stores the updated voxels into the peers\' replicas over '
+                                  'NVLink peer memory (vx_adam_step_worklist_peers)' if fused.k0_owned else
+                                  'every rank re-scatters all rows and steps every voxel' + (f' [{fused.k0_peer_note}]' if fused.k0_peer_note else ''))
+                                 ) if fused.sharded else 'dense all-reduces (sdf, MLPs) + k0 row exchange'
     with ClockSampler(local_rank) as clk:
         # ---- device-resident timing
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -560,7 +569,7 @@ def main():
         print(json.dumps(line))
     if world > 1:
         if fused is not None:
-            fused.release_graphs()     # captured NCCL work must go before the process group does
+            fused.shutdown()     # captured NCCL work and the peers' memory mappings must go before the process group does
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()

@@ -117,6 +117,24 @@ int vx_adam_step_worklist(float* param, float* grad, float* exp_avg, float* exp_
                           float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
                           float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched, uint32_t* live,
                           int group, int merge, uint32_t* work, const float* step_dev, cudaStream_t stream);
+/* vx_adam_step_worklist on the slice of a REPLICATED parameter array that this rank owns (data-parallel training, one
+ * process per GPU): the kernel also stores every updated parameter into the same slice of the replicas on n_peers other
+ * GPUs through NVLink peer memory (peer_params_host: host array of their device addresses) -- optimizer pass and parameter
+ * all-gather in one kernel, moving exactly the voxels that changed.  Peer stores are complete when the kernel is: order
+ * them against the replicas' readers with a cross-rank barrier on the same stream. */
+int vx_adam_step_worklist_peers(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float beta1,
+                                float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                                float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched, uint32_t* live,
+                                int group, int merge, uint32_t* work, const float* step_dev,
+                                const uint64_t* peer_params_host, int n_peers, cudaStream_t stream);
+/* CUDA IPC plumbing for the replicas above (one process per GPU, one node): the owner exports the 64-byte handle of a
+ * cudaMalloc allocation (its BASE pointer), a peer opens it with its own device current and gets an address its kernels can
+ * store to over NVLink; close before the owner frees the allocation. */
+int vx_ipc_get_handle(const void* base_ptr, uint8_t* handle_host);
+int vx_ipc_open_handle(const uint8_t* handle_host, uint64_t* ptr_out_host);
+int vx_ipc_close_handle(uint64_t ptr);
+/* cudaDeviceEnablePeerAccess(peer_device) for the current device; 0 also when it was enabled already */
+int vx_enable_peer_access(int peer_device);
 /* live |= touched; touched = 0 -- after the vx_adam_step that consumed both */
 int vx_bitmap_merge(uint32_t* live, uint32_t* touched, int64_t n_words, cudaStream_t stream);
 
@@ -212,6 +230,13 @@ int vx_smooth_grad_tv_masked_writes(const float* G, const bool* mask, int X, int
  * scratch: 3 * vx_smooth_grad_tv_scratch_floats() floats */
 int vx_total_variation_l1(const float* v, const bool* mask, int C, int X, int Y, int Z, const float* inv_cnt_host,
                           float* grad, float* scratch, float* loss_out, cudaStream_t stream);
+
+/* Data-parallel k0 exchange, owner side: the all-gathered rows of every rank, recv[r] = [cap x 3 positions | cap x C
+ * gradient rows | int32 row count + 3 pad] (what vx_fused_export_k0_rows wrote on rank r), scattered into grad_grid
+ * (channels-last, C = 6 or 12) in one launch, restricted to the corners whose voxel has x_lo <= x < x_hi (the X-slab this
+ * rank owns; 0, X = the whole grid).  ATen grid_sampler_3d backward arithmetic per corner. */
+int vx_k0_rows_scatter(int X, int Y, int Z, int C, const float* xyz_min_host, const float* xyz_max_host, const float* recv,
+                       int world, int cap, int x_lo, int x_hi, float* grad_grid, uint32_t* touched, cudaStream_t stream);
 
 /* ---- fused ray march (replaces sample_pts_on_rays + two compactions + MaskCache.forward) ---- */
 /* lib/voxurf_fine.py:593-617,631-636,917-942.  bits_* need (offsets[n_rays] >> 5) + n_rays + 1 words. */

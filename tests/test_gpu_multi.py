@@ -51,12 +51,15 @@ def _worker(rank, world, port, n_rays, step, sparse, ret, dense_exchange=False, 
         fs.poll_overflow(force=True)
         assert len(fs._graphs) == (3 if defer else 2), list(fs._graphs)
         ret[rank] = ({}, {'sdf': m.sdf.grid.detach().cpu(), 'k0': m.k0.grid.detach().contiguous().cpu(), 'mlp1': fs.mlp1.flat.detach().cpu()})
-        fs.release_graphs()
+        assert fs.k0_owned, fs.k0_peer_note
+        fs.shutdown()
         dist.barrier()
         dist.destroy_process_group()
         return
     fs.forward_backward(*b, step)
     fs.grad_sync()
+    assert fs.k0_owned == (fs.sharded and sparse), fs.k0_peer_note    # NVLink peer memory is there on the B200 boxes
+    fs.gather_k0_grad()      # (k0 ownership: each rank scattered the corners inside its own X-slab only)
     if fs.sharded:     # the reduce-scatter left every rank with its X-slab of the averaged sdf gradient
         flat = m.sdf.grid.grad.view(-1)
         dist.all_gather_into_tensor(flat, flat[fs.slab[0]:fs.slab[1]].clone())
@@ -68,6 +71,7 @@ def _worker(rank, world, port, n_rays, step, sparse, ret, dense_exchange=False, 
     params = {'sdf': m.sdf.grid.detach().cpu(), 'k0': m.k0.grid.detach().contiguous().cpu(), 'mlp1': fs.mlp1.flat.detach().cpu()}
     fs.counts()
     ret[rank] = (grads, params)
+    fs.shutdown()
     dist.destroy_process_group()
 
 
@@ -103,7 +107,8 @@ def test_two_gpu_gradients_equal_single_gpu_on_concatenated_batch(sparse, dense_
             np.testing.assert_allclose(params[k].numpy(), refp[k].numpy(), rtol=1e-4, atol=2e-2 * lr, err_msg=f'rank {r} param {k}')
     # both ranks hold identical replicas after the step (bit-identical with the dense all-reduce; the row exchange
     # re-scatters with fp32 atomics whose order differs per rank, so k0 agrees to rounding there)
-    for k in ('sdf', 'mlp1') + (() if sparse else ('k0',)):
+    # (with k0 ownership -- sharded + row exchange -- the owner's values are stored into every replica: bit-identical too)
+    for k in ('sdf', 'mlp1') + (('k0',) if (not sparse or not dense_exchange) else ()):
         assert torch.equal(ret[0][1][k], ret[1][1][k]), k
     np.testing.assert_allclose(ret[0][1]['k0'].numpy(), ret[1][1]['k0'].numpy(), rtol=1e-4, atol=2e-3)
 
@@ -135,3 +140,4 @@ def test_two_gpu_graph_replayed_steps_follow_single_gpu(defer):
             d = (ret[r][1][k] - refp[k]).abs()
             assert float((d > 2e-2 * lr).float().mean()) < 1e-3 and float(d.max()) <= 8 * lr, (r, k, float(d.max()))
     assert torch.equal(ret[0][1]['sdf'], ret[1][1]['sdf']) and torch.equal(ret[0][1]['mlp1'], ret[1][1]['mlp1'])
+    assert torch.equal(ret[0][1]['k0'], ret[1][1]['k0'])      # k0 ownership: the owner's update is stored into every replica

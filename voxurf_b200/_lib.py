@@ -20,7 +20,7 @@ _PTR_DTYPES = {
     'float': (torch.float32,), 'int': (torch.int32,), 'int64_t': (torch.int64,), 'bool': (torch.bool, torch.uint8),
     'uint8_t': (torch.uint8, torch.bool), 'uint32_t': (torch.int32,),
 }
-_SCALARS = {'float': ctypes.c_float, 'int': ctypes.c_int, 'int64_t': ctypes.c_int64}
+_SCALARS = {'float': ctypes.c_float, 'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'uint64_t': ctypes.c_uint64}
 
 
 def parse_header(path=HEADER):

@@ -9,6 +9,7 @@
 // Both are one streaming pass: read p,g,m,v once, write p,m,v once (28 B/element; 32 B/element with
 // the fused gradient zero-fill that replaces the reference's separate zero-allocation of .grad).
 // 128-bit accesses, grid sized as a multiple of the SM count, grid-stride loop.
+#include <cstring>
 #include "common.cuh"
 
 struct AdamCoef {
@@ -308,12 +309,21 @@ template <> struct VxVec<4> { typedef float4 T; };
 template <> struct VxVec<2> { typedef float2 T; };
 template <> struct VxVec<1> { typedef float T; };
 
+// Replicas of the parameter array on other GPUs (NVLink peer memory): the owner of a voxel computes its update and stores
+// the new parameters into every replica as well -- the "all-gather" of the updated voxels is fused into the optimizer
+// pass, moves exactly the bytes that changed, and needs no staging buffer, count or capacity.
+#define VX_MAX_PEERS 15
+struct VxPeers {
+  float* p[VX_MAX_PEERS];
+  int n;
+};
+
 template <int kW, bool kZeroGrad>
 __global__ void __launch_bounds__(256) k_adam_voxel_list(float* __restrict__ param, float* __restrict__ grad,
                                                          float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                                          AdamCoef c, uint32_t parts, const uint32_t* __restrict__ list,
                                                          const uint32_t* __restrict__ count,
-                                                         const float* __restrict__ step_dev) {
+                                                         const float* __restrict__ step_dev, const VxPeers peers) {
   typedef typename VxVec<kW>::T V;
   if (step_dev) { c.step_size = __ldg(step_dev); c.sqrt_bc2 = __ldg(step_dev + 1); }
   const int64_t n = (int64_t)(*count) * parts;
@@ -339,6 +349,7 @@ __global__ void __launch_bounds__(256) k_adam_voxel_list(float* __restrict__ par
 #pragma unroll
     for (int j = 0; j < kW; ++j) adam_one<false>(pf[j], gf[j], mf[j], vf[j], 1.f, c);
     p4[i] = p; m4[i] = m; v4[i] = v;
+    for (int r = 0; r < peers.n; ++r) reinterpret_cast<V*>(peers.p[r])[i] = p;
     if (kZeroGrad && t) {
 #pragma unroll
       for (int j = 0; j < kW; ++j) gf[j] = 0.f;
@@ -350,10 +361,11 @@ __global__ void __launch_bounds__(256) k_adam_voxel_list(float* __restrict__ par
 // trainer semantics (lib/utils.py:154-199) over the voxels flagged in touched | live (see k_adam above), work-list form.
 // group: elements per voxel; work: numel / group + 1 uint32 of scratch (voxel list + its counter at the end);
 // merge != 0: live |= touched, touched = 0 in the same pass (then vx_bitmap_merge is not needed).
-VX_API int vx_adam_step_worklist(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t N, float beta1,
-                                 float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
-                                 float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched, uint32_t* live,
-                                 int group, int merge, uint32_t* work, const float* step_dev, cudaStream_t st) {
+static int adam_step_worklist(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t N, float beta1,
+                              float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                              float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched, uint32_t* live,
+                              int group, int merge, uint32_t* work, const float* step_dev, const VxPeers& peers,
+                              cudaStream_t st) {
   if (N <= 0) return 0;
   const bool aligned = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                          reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0;
@@ -372,12 +384,81 @@ VX_API int vx_adam_step_worklist(float* param, float* grad, float* exp_avg, floa
   const int blocks = vx_num_sms() * 8;
   const int w = group % 4 == 0 ? 4 : (group % 2 == 0 ? 2 : 1);
   const uint32_t parts = (uint32_t)(group / w);
-#define VX_AVL(W, ZG) k_adam_voxel_list<W, ZG><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, c, parts, work, count, step_dev)
+#define VX_AVL(W, ZG) k_adam_voxel_list<W, ZG><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, c, parts, work, count, step_dev, peers)
   if (w == 4) { if (zero_grad) VX_AVL(4, true); else VX_AVL(4, false); }
   else if (w == 2) { if (zero_grad) VX_AVL(2, true); else VX_AVL(2, false); }
   else { if (zero_grad) VX_AVL(1, true); else VX_AVL(1, false); }
 #undef VX_AVL
   return vx_check_launch("vx_adam_step_worklist");
+}
+
+VX_API int vx_adam_step_worklist(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t N, float beta1,
+                                 float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                                 float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched, uint32_t* live,
+                                 int group, int merge, uint32_t* work, const float* step_dev, cudaStream_t st) {
+  VxPeers peers;
+  peers.n = 0;
+  return adam_step_worklist(param, grad, exp_avg, exp_avg_sq, N, beta1, beta2, one_minus_beta1, one_minus_beta2, step_size,
+                            sqrt_bias_correction2, eps, zero_grad, touched, live, group, merge, work, step_dev, peers, st);
+}
+
+// vx_adam_step_worklist on the slice of a replicated parameter array this rank owns; the updated parameters are also stored
+// into the same slice of the replicas on n_peers other GPUs (peer_params_host: their device addresses, peer access enabled --
+// vx_enable_peer_access).  Peer stores are complete when the kernel is; order them against the readers with a cross-rank
+// barrier on the same stream.
+VX_API int vx_adam_step_worklist_peers(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t N, float beta1,
+                                       float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                                       float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched,
+                                       uint32_t* live, int group, int merge, uint32_t* work, const float* step_dev,
+                                       const uint64_t* peer_params_host, int n_peers, cudaStream_t st) {
+  VX_REQUIRE(n_peers >= 0 && n_peers <= VX_MAX_PEERS && (n_peers == 0 || peer_params_host), "vx_adam_step_worklist_peers", "0 <= n_peers <= 15");
+  VxPeers peers;
+  peers.n = n_peers;
+  for (int r = 0; r < n_peers; ++r) {
+    VX_REQUIRE((peer_params_host[r] & 15) == 0, "vx_adam_step_worklist_peers", "peer arrays must be 16-byte aligned");
+    peers.p[r] = reinterpret_cast<float*>(peer_params_host[r]);
+  }
+  return adam_step_worklist(param, grad, exp_avg, exp_avg_sq, N, beta1, beta2, one_minus_beta1, one_minus_beta2, step_size,
+                            sqrt_bias_correction2, eps, zero_grad, touched, live, group, merge, work, step_dev, peers, st);
+}
+
+// CUDA IPC for the replicas of a parameter array held by the other ranks of the node (one process per GPU): the owner exports
+// the handle of the cudaMalloc allocation (base pointer), a peer opens it with ITS OWN device current -- the mapping is then
+// addressable by that device's kernels over NVLink (cudaIpcMemLazyEnablePeerAccess).
+VX_API int vx_ipc_get_handle(const void* base_ptr, uint8_t* handle_host /* 64 bytes */) {
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(base_ptr));
+  if (e != cudaSuccess) { vx_set_error("vx_ipc_get_handle", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_host, &h, sizeof(h));
+  return 0;
+}
+VX_API int vx_ipc_open_handle(const uint8_t* handle_host, uint64_t* ptr_out_host) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { vx_set_error("vx_ipc_open_handle", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+  *ptr_out_host = reinterpret_cast<uint64_t>(p);
+  return 0;
+}
+VX_API int vx_ipc_close_handle(uint64_t ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(reinterpret_cast<void*>(ptr));
+  if (e != cudaSuccess) { vx_set_error("vx_ipc_close_handle", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+  return 0;
+}
+
+// cudaDeviceEnablePeerAccess(peer) for the current device (already enabled = success)
+VX_API int vx_enable_peer_access(int peer_device) {
+  int cur = -1, can = 0;
+  cudaGetDevice(&cur);
+  if (cur == peer_device) return 0;
+  cudaError_t e = cudaDeviceCanAccessPeer(&can, cur, peer_device);
+  if (e != cudaSuccess || !can) { cudaGetLastError(); vx_set_error("vx_enable_peer_access", "no peer access between these devices"); return -1; }
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) { vx_set_error("vx_enable_peer_access", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+  return 0;
 }
 
 // live |= touched; touched = 0  (after the Adam pass that consumed both)

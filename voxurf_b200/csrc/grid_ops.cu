@@ -174,6 +174,64 @@ __global__ void k_grid_gather_bwd_cl4(VxGrid g, VxPts pts, const int* __restrict
   }
 }
 
+// Data-parallel k0 exchange, owner side: the all-gathered rows of EVERY rank -- recv[r] = [cap x 3 positions |
+// cap x C gradient rows | row count (int32) + 3 pad] -- scattered in one launch, restricted to the corners whose voxel lies
+// in the linear voxel range [v_lo, v_hi) (the X-slab this rank owns; the whole grid when the k0 grid is not sharded).
+// Four threads per row like k_grid_gather_bwd_cl4.
+template <int kC>
+__global__ void k_k0_rows_scatter(VxGrid g, const float* __restrict__ recv, int world, int cap, int v_lo, int v_hi,
+                                  float* __restrict__ grad_grid, uint32_t* __restrict__ touched) {
+  const int64_t stride_r = (int64_t)cap * (3 + kC) + 4;
+  const int64_t n_items = (int64_t)world * cap * 4;
+  for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(item / ((int64_t)cap * 4));
+    const int64_t q = item - (int64_t)r * cap * 4;
+    const int p = (int)(q >> 2), sub = (int)(q & 3);
+    const float* base = recv + r * stride_r;
+    const int n = min(__ldg(reinterpret_cast<const int*>(base + (int64_t)cap * (3 + kC))), cap);
+    if (p >= n) continue;
+    const float* gp = base + (int64_t)cap * 3 + (int64_t)p * kC;
+    float go[kC];
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) { go[c] = gp[c]; any |= (go[c] != 0.f); }
+    if (!any) continue;
+    float ix, iy, iz;
+    point_to_index(g, base[3 * p], base[3 * p + 1], base[3 * p + 2], ix, iy, iz);
+    VxTap t;
+    vx_make_tap(ix, iy, iz, g.X, g.Y, g.Z, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if ((k >> 1) != sub || t.off[k] < v_lo || t.off[k] >= v_hi) continue;
+      if (touched) atomicOr(touched + (t.off[k] >> 5), 1u << (t.off[k] & 31));
+      float* dst = grad_grid + (int64_t)t.off[k] * kC;
+      if (kC % 4 == 0) {
+#pragma unroll
+        for (int c = 0; c < kC; c += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + c),
+                    make_float4(go[c] * t.w[k], go[c + 1] * t.w[k], go[c + 2] * t.w[k], go[c + 3] * t.w[k]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < kC; c += 2)
+          atomicAdd(reinterpret_cast<float2*>(dst + c), make_float2(go[c] * t.w[k], go[c + 1] * t.w[k]));
+      }
+    }
+  }
+}
+
+VX_API int vx_k0_rows_scatter(int X, int Y, int Z, int C, const float* xyz_min_host, const float* xyz_max_host,
+                              const float* recv, int world, int cap, int x_lo, int x_hi, float* grad_grid,
+                              uint32_t* touched, cudaStream_t st) {
+  if (world <= 0 || cap <= 0) return 0;
+  VX_REQUIRE(C == 12 || C == 6, "vx_k0_rows_scatter", "channels-last k0 grid with 6 or 12 channels");
+  VX_REQUIRE((int64_t)X * Y * Z < ((int64_t)1 << 31) && 0 <= x_lo && x_lo <= x_hi && x_hi <= X, "vx_k0_rows_scatter", "bad grid / slab");
+  const VxGrid g = make_grid(X, Y, Z, C, 1, xyz_min_host, xyz_max_host);
+  const int blocks = (int)min((int64_t)vx_blocks((int64_t)world * cap * 4, 256), (int64_t)vx_num_sms() * 16);
+  if (C == 12) k_k0_rows_scatter<12><<<blocks, 256, 0, st>>>(g, recv, world, cap, x_lo * Y * Z, x_hi * Y * Z, grad_grid, touched);
+  else k_k0_rows_scatter<6><<<blocks, 256, 0, st>>>(g, recv, world, cap, x_lo * Y * Z, x_hi * Y * Z, grad_grid, touched);
+  return vx_check_launch("vx_k0_rows_scatter");
+}
+
 // xyz_min / xyz_max are HOST float[3] (grid geometry is static model configuration).
 VX_API int vx_grid_gather(const float* grid, int X, int Y, int Z, int C, int channels_last, const float* xyz_min_host,
                           const float* xyz_max_host, const float* xyz, const int* ray_id, const int* step_id,

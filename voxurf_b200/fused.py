@@ -39,7 +39,7 @@ from .optim import _storage
 class FusedFineStep:
     def __init__(self, model, n_rays, train_cfg=None, render_kwargs=None, row_capacity=65536, world=1, rank=0,
                  tensor_core=True, sparse_k0_exchange=True, sparse_adam=True, use_graph=False,
-                 graph_multi_gpu=True, dense_exchange=False, defer_optimizer=False, deterministic=False):
+                 graph_multi_gpu=True, dense_exchange=False, defer_optimizer=False, deterministic=False, k0_ownership=True):
         if model.k0_dim not in (6, 12):
             raise NotImplementedError('fused step: k0 channels must be 6 or 12')
         if model.k_center_sdf or not model.center_sdf or not model.k_res:
@@ -180,6 +180,14 @@ class FusedFineStep:
         self.sdf_live = None
         if sparse_adam and m.sdf.grid.numel() % 128 == 0 and (not self.sharded or (self.slab[1] - self.slab[0]) % 128 == 0):
             self.sdf_live = torch.zeros(m.sdf.grid.numel() // 128, dtype=torch.uint8, device=dev)
+        # k0 slab ownership (sharded step, channels-last k0 with bitmaps): each rank scatters only the rows' corners that fall
+        # into its X-slab, steps only those voxels, and stores the updated parameters straight into the other ranks' replicas
+        # of the k0 grid over NVLink peer memory (vx_adam_step_worklist_peers) -- re-scatter atomics and Adam traffic drop
+        # by the world size and the replicas become bit-identical.  Needs CUDA IPC + peer access between the ranks' GPUs.
+        self.k0_owned = False
+        self.k0_peer_note = None
+        if self.sharded and k0_ownership and self.k0_touched is not None and sparse_k0_exchange and self.C in (6, 12):
+            self._setup_k0_peers()
         self.bitmap_probe = None   # bench.py: list collecting copies of (touched, live) as the k0 Adam launch sees them
         self.timings = None   # bench.py: list collecting (group, (start, end) CUDA events) around the k0 / sdf Adam launches
         if self.cfg is not None:
@@ -187,6 +195,71 @@ class FusedFineStep:
             self.groups = [('sdf', [m.sdf.grid], c['lrate_sdf']), ('k0', [m.k0.grid], c['lrate_k0']),
                            ('rgbnet', [self.mlp1.flat], c['lrate_rgbnet']), ('k_rgbnet', [self.mlp2.flat], c['lrate_k_rgbnet'])]
             self.lr = {name: lr for name, _, lr in self.groups}
+
+    def _setup_k0_peers(self):
+        """Exchange CUDA IPC handles of the k0 parameter allocation between the ranks of this node and map the peers' replicas
+        (vx_ipc_*: opened with this rank's device current, so that its kernels can store to them over NVLink); on any failure
+        the step keeps the replicated k0 update."""
+        import ctypes
+        import torch.distributed as dist
+        from ._lib import library, last_error
+        W, r = self.world, self.rank
+        lib = library()
+        flat = _storage(self.m.k0.grid.data).view(-1)
+        ok, ptrs, note = 1, [0] * W, ''
+        mine = None
+        try:
+            if (self.slab[1] - self.slab[0]) % 32:
+                raise RuntimeError('slab size is not a multiple of the 32-voxel bitmap words')
+            ptr, cur = flat.data_ptr(), torch.cuda.current_device()
+            base = [sg['address'] for sg in torch.cuda.memory_snapshot()
+                    if sg['device'] == cur and sg['address'] <= ptr < sg['address'] + sg['total_size']]
+            if len(base) != 1:
+                raise RuntimeError('k0 storage is not inside one cudaMalloc segment of the caching allocator')
+            buf = (ctypes.c_uint8 * 64)()
+            if lib.vx_ipc_get_handle(ctypes.c_void_p(base[0]), ctypes.cast(buf, ctypes.c_void_p)) != 0:
+                raise RuntimeError(last_error())
+            mine = (bytes(buf), ptr - base[0], flat.numel())
+        except Exception as e:      # noqa: BLE001 -- capability probe: IPC / P2P may be unavailable (containers, MIG, PCIe boxes)
+            ok, note = 0, f'{type(e).__name__}: {e}'
+        handles = [None] * W
+        dist.all_gather_object(handles, mine)
+        opened = []
+        if ok and all(h is not None for h in handles):
+            try:
+                for q in range(W):
+                    if q == r:
+                        continue
+                    hb, off, n = handles[q]
+                    assert n == flat.numel()
+                    hbuf = (ctypes.c_uint8 * 64).from_buffer_copy(hb)
+                    out = ctypes.c_uint64(0)
+                    if lib.vx_ipc_open_handle(ctypes.cast(hbuf, ctypes.c_void_p), ctypes.cast(ctypes.pointer(out), ctypes.c_void_p)) != 0:
+                        raise RuntimeError(last_error())
+                    opened.append(int(out.value))
+                    ptrs[q] = int(out.value) + off
+                    assert ptrs[q] % 16 == 0
+            except Exception as e:      # noqa: BLE001
+                ok, note = 0, f'{type(e).__name__}: {e}'
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)       # all ranks or none
+        self._k0_ipc_opened = opened
+        if int(flag.item()) != 1:
+            self._close_k0_peers()
+            self.k0_peer_note = 'k0 ownership unavailable (%s): replicated k0 update' % (note or 'a peer failed')
+            return
+        per = (self.slab[1] - self.slab[0]) * self.C
+        self._k0_peer_ptrs = [ptrs[q] + 4 * self.rank * per for q in range(W) if q != r]
+        self._k0_bar = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.k0_owned = True
+
+    def _close_k0_peers(self):
+        from ._lib import library
+        for p in getattr(self, '_k0_ipc_opened', []):
+            library().vx_ipc_close_handle(p)
+        self._k0_ipc_opened = []
 
     # the model keeps a back-reference to its step (model._fused): copies / pickles of the model do not drag the step's
     # buffers, events and CUDA graphs along
@@ -457,6 +530,39 @@ class FusedFineStep:
             self._ag_work.wait()
             self._ag_work, self._params_dirty = None, False
 
+    def gather_k0_grad(self):
+        """k0 ownership: every rank holds the k0 gradient of its own X-slab only; all-gather the slabs (tests, parity_check)."""
+        if self.k0_owned:
+            import torch.distributed as dist
+            flat = _storage(self.k0_grad).view(-1)
+            lo, hi = self.slab[0] * self.C, self.slab[1] * self.C
+            dist.all_gather_into_tensor(flat, flat[lo:hi].clone())
+
+    def _gather_k0_state(self):
+        """k0 ownership: Adam moments and live bits of a voxel exist on its owner only; all-gather the slabs so that every rank
+        holds the full optimizer state (checkpoints, leaving the sharded mode)."""
+        if not self.k0_owned:
+            return
+        import torch.distributed as dist
+        C = self.C
+        lo, hi = self.slab
+        for t in (self.adam_state.get(id(self.m.k0.grid)) or ()):
+            flat = _storage(t).view(-1)
+            dist.all_gather_into_tensor(flat, flat[lo * C:hi * C].clone())
+        dist.all_gather_into_tensor(self.k0_live, self.k0_live[lo // 32:hi // 32].clone())
+
+    def shutdown(self):
+        """Release captured graphs (they hold NCCL work) and the peers' memory mappings: call before destroying the process group."""
+        self.flush()
+        self.release_graphs()
+        if self.k0_owned:
+            import torch.distributed as dist
+            self._gather_k0_state()
+            self.k0_owned = False
+            torch.cuda.synchronize()
+            self._close_k0_peers()            # unmap the peers' replicas ...
+            dist.barrier()                    # ... before any owner may free its own
+
     def sync_params(self):
         """Make this rank's copy of the sdf grid current (sharded step: the slabs other ranks own are stale between a
         step and the next step's all-gather; with defer_optimizer the last step's update is still pending).  Call before
@@ -477,6 +583,8 @@ class FusedFineStep:
             for t in st:
                 flat = t.view(-1)
                 dist.all_gather_into_tensor(flat, flat[self.slab[0]:self.slab[1]])
+        self._gather_k0_state()
+        self.k0_owned = False
         self.sharded = False
         if self.sdf_live is not None:
             self.sdf_live.fill_(1)       # the gathered moments of the other ranks' slabs may be non-zero anywhere
@@ -500,7 +608,13 @@ class FusedFineStep:
                 w.wait()
             self._k0_work = []
             cap, C = self.cap4, self.C
-            for r in range(self.world):      # every rank's rows, as many as it sent
+            if self.k0_cl and C in (6, 12):
+                # every rank's rows, as many as it sent, in one launch; with k0 ownership only the corners inside the owned slab
+                x_lo, x_hi = self.slab_x if self.k0_owned else (0, self.X)
+                call('vx_k0_rows_scatter', self.X, self.Y, self.Z, C, m._min_host, m._max_host, self._k0_recv.view(-1), self.world, cap,
+                     x_lo, x_hi, _storage(self.k0_grad).view(-1), self.k0_touched)
+                return
+            for r in range(self.world):
                 xyz, g = self._k0_recv[r, :cap * 3].view(cap, 3), self._k0_recv[r, cap * 3:cap * (3 + C)].view(cap, C)
                 call('vx_grid_gather_backward', self.X, self.Y, self.Z, self.C, self.k0_cl, m._min_host, m._max_host, xyz, None, None,
                      None, None, 0.0, self._k0_recv[r, cap * (3 + C):].view(torch.int32), cap, g, _storage(self.k0_grad), self.k0_touched)
@@ -645,7 +759,18 @@ class FusedFineStep:
                         ev[1].record()
                         self.timings.append((name, ev))
                     continue
-                if touched is not None:
+                if touched is not None and self.k0_owned:
+                    # the owned X-slab only; the new parameters go to every replica (peer stores), then a cross-rank barrier
+                    import torch.distributed as dist
+                    lo, hi = self.slab
+                    C = self.C
+                    sl = [t.view(-1)[lo * C:hi * C] for t in tensors]
+                    call('vx_adam_step_worklist_peers', *sl, sl[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
+                         math.sqrt(bc2), eps, 1, touched[lo // 32:hi // 32], live[lo // 32:hi // 32], C, 1, self._k0_list,
+                         None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi],
+                         self._k0_peer_ptrs, len(self._k0_peer_ptrs))
+                    dist.all_reduce(self._k0_bar)      # every rank's peer stores have landed before anyone reads k0 again
+                elif touched is not None:
                     call('vx_adam_step_worklist', *tensors, tensors[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
                          math.sqrt(bc2), eps, 1, touched, live, self.C, 1, self._k0_list,
                          None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
@@ -671,6 +796,7 @@ class FusedFineStep:
             mom = self.adam_state.get(id(self.m.sdf.grid))
             for t in (mom or ()):
                 dist.all_gather_into_tensor(t.view(-1), t.view(-1)[self.slab[0]:self.slab[1]])
+            self._gather_k0_state()
         st = {'adam_steps': self.adam_steps, 'lr': dict(self.lr), 'moments': {}}
         for name, params, _ in self.groups:
             m = self.adam_state.get(id(params[0]))
@@ -888,6 +1014,7 @@ class FusedFineStep:
         if self.sharded:      # put the reduced slabs of all ranks together (untimed)
             flat = self.sdf_grad.view(-1)
             dist.all_gather_into_tensor(flat, flat[self.slab[0]:self.slab[1]].clone())
+        self.gather_k0_grad()
         self.force_eager = was_eager
         cat = []
         for t in batch:
