@@ -387,7 +387,9 @@ def main():
                                'timed step all the same)') if (fused is not None and fused.defer_optimizer) else 'end of step'}
 
     if fused is not None and world > 1:
-        execution['exchange'] = ('sdf: in-place reduce-scatter over X-slabs + slab Adam + in-place all-gather of the parameters; '
+        execution['exchange'] = (('sdf: owners pull the non-zero 128-voxel gradient blocks of every rank over NVLink peer memory (vx_pull_reduce), slab '
+                                  'Adam stores the updated blocks into the peers\' replicas (vx_adam_step_blocklive_peers); ' if fused.sdf_peer else
+                                  'sdf: in-place reduce-scatter over X-slabs + slab Adam + in-place all-gather of the parameters; ') +
                                  'MLPs: one all-reduce; k0: rows all-gathered, ' +
                                  ('each rank scatters / steps its own X-slab and stores the updated voxels into the peers\' replicas over '
                                   'NVLink peer memory (vx_adam_step_worklist_peers)' if fused.k0_owned else

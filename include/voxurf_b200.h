@@ -127,6 +127,20 @@ int vx_adam_step_worklist_peers(float* param, float* grad, float* exp_avg, float
                                 float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched, uint32_t* live,
                                 int group, int merge, uint32_t* work, const float* step_dev,
                                 const uint64_t* peer_params_host, int n_peers, cudaStream_t stream);
+/* vx_adam_step_blocklive on the slab of a replicated single-channel grid (the sdf grid) this rank owns; the parameters of
+ * every updated block are also stored into the same slab of the replicas on n_peers other GPUs (peer memory) */
+int vx_adam_step_blocklive_peers(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float beta1,
+                                 float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                                 float sqrt_bias_correction2, float eps, int zero_grad, uint8_t* live_blocks,
+                                 const float* step_dev, const uint64_t* peer_params_host, int n_peers, cudaStream_t stream);
+/* Sparse reduce-scatter of a single-channel gradient grid over peer memory (data-parallel sdf gradient: the ray gradients
+ * live in ~10 % of the 128-voxel blocks).  vx_block_nonzero: mask[b] = block b of g has a non-zero element.
+ * vx_pull_reduce (after a cross-rank barrier): out = scale * sum, in rank order, of the flagged blocks of n_ranks arrays --
+ * grads_host / masks_host: device addresses of the SAME slab (and of its mask bytes) on every rank, own rank included; out
+ * may alias the own array; unflagged blocks keep their content.  Bytes moved over NVLink = the flagged blocks only. */
+int vx_block_nonzero(const float* g, int64_t numel, uint8_t* mask, cudaStream_t stream);
+int vx_pull_reduce(float* out, int64_t numel, const uint64_t* grads_host, const uint64_t* masks_host, int n_ranks,
+                   float scale, cudaStream_t stream);
 /* CUDA IPC plumbing for the replicas above (one process per GPU, one node): the owner exports the 64-byte handle of a
  * cudaMalloc allocation (its BASE pointer), a peer opens it with its own device current and gets an address its kernels can
  * store to over NVLink; close before the owner frees the allocation. */

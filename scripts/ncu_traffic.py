@@ -2,7 +2,7 @@
 read / written, tensor-pipe activity, issue activity, L2 hit rate, registers.  Writes profiles/traffic.json keyed by the
 hash of the CUDA sources (bench.py prints `roofline.traffic` only when the hash matches the build it runs).
 
-    python scripts/ncu_traffic.py gpurun_out/prof.ncu-rep [profiles/name.md]
+    python scripts/ncu_traffic.py gpurun_out/prof.ncu-rep | gpurun_out/prof_raw.csv [profiles/name.md]
 """
 import csv
 import json
@@ -18,7 +18,8 @@ sys.argv, argv = sys.argv[:1], sys.argv
 import bench  # noqa: E402
 
 rep = argv[1]
-out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+# (a report of ~80 launches is > 100 MB and cannot come back from the GPU box: scripts/profile_step.sh exports the raw page there)
+out = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h = rows[0]
 col = {c: i for i, c in enumerate(h)}

@@ -58,7 +58,7 @@ def _worker(rank, world, port, n_rays, step, sparse, ret, dense_exchange=False, 
         return
     fs.forward_backward(*b, step)
     fs.grad_sync()
-    assert fs.k0_owned == (fs.sharded and sparse), fs.k0_peer_note    # NVLink peer memory is there on the B200 boxes
+    assert fs.k0_owned == (fs.sharded and sparse) and fs.sdf_peer == fs.k0_owned, fs.k0_peer_note    # NVLink peer memory is there on the B200 boxes
     fs.gather_k0_grad()      # (k0 ownership: each rank scattered the corners inside its own X-slab only)
     if fs.sharded:     # the reduce-scatter left every rank with its X-slab of the averaged sdf gradient
         flat = m.sdf.grid.grad.view(-1)

@@ -18,6 +18,15 @@ struct AdamCoef {
   float sqrt_bc2;     // (2) only
 };
 
+// Replicas of the parameter array on other GPUs (NVLink peer memory): the owner of a voxel computes its update and stores
+// the new parameters into every replica as well -- the "all-gather" of the updated voxels is fused into the optimizer
+// pass, moves exactly the bytes that changed, and needs no staging buffer, count or capacity.
+#define VX_MAX_PEERS 15
+struct VxPeers {
+  float* p[VX_MAX_PEERS];
+  int n;
+};
+
 // mode: 0 dense, 1 skip where grad == 0, 2 per-voxel lr.  kRef = reference-CUDA semantics (1) else (2).
 template <bool kRef>
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float perlr, const AdamCoef& c) {
@@ -183,7 +192,7 @@ template <bool kZeroGrad>
 __global__ void __launch_bounds__(256) k_adam_blocklive(float* __restrict__ param, float* __restrict__ grad,
                                                         float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                                         int64_t n_blocks, AdamCoef c, uint8_t* __restrict__ live_blocks,
-                                                        const float* __restrict__ step_dev) {
+                                                        const float* __restrict__ step_dev, const VxPeers peers) {
   if (step_dev) { c.step_size = __ldg(step_dev); c.sqrt_bc2 = __ldg(step_dev + 1); }
   const int lane = threadIdx.x & 31;
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -204,6 +213,7 @@ __global__ void __launch_bounds__(256) k_adam_blocklive(float* __restrict__ para
     adam_one<false>(p.z, g.z, m.z, v.z, 1.f, c);
     adam_one<false>(p.w, g.w, m.w, v.w, 1.f, c);
     p4[i] = p; m4[i] = m; v4[i] = v;
+    for (int r = 0; r < peers.n; ++r) reinterpret_cast<float4*>(peers.p[r])[i] = p;     // the replicas on the other GPUs
     if (kZeroGrad && nz) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!lv && lane == 0) live_blocks[b] = 1;
   }
@@ -211,10 +221,10 @@ __global__ void __launch_bounds__(256) k_adam_blocklive(float* __restrict__ para
 
 // trainer semantics (lib/utils.py:154-199), numel % 128 == 0, 16-byte aligned tensors; live_blocks: numel / 128 bytes,
 // zero-initialised by the caller once (all ones after loading moments from elsewhere)
-VX_API int vx_adam_step_blocklive(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t N, float beta1,
-                                  float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
-                                  float sqrt_bias_correction2, float eps, int zero_grad, uint8_t* live_blocks,
-                                  const float* step_dev, cudaStream_t st) {
+static int adam_step_blocklive(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t N, float beta1,
+                               float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                               float sqrt_bias_correction2, float eps, int zero_grad, uint8_t* live_blocks,
+                               const float* step_dev, const VxPeers& peers, cudaStream_t st) {
   if (N <= 0) return 0;
   const bool aligned = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                          reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0;
@@ -224,9 +234,115 @@ VX_API int vx_adam_step_blocklive(float* param, float* grad, float* exp_avg, flo
   c.step_size = step_size; c.sqrt_bc2 = sqrt_bias_correction2;
   const int64_t n_blocks = N / 128;
   const int blocks = (int)min((n_blocks + 7) / 8, (int64_t)vx_num_sms() * 8);
-  if (zero_grad) k_adam_blocklive<true><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_blocks, c, live_blocks, step_dev);
-  else k_adam_blocklive<false><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_blocks, c, live_blocks, step_dev);
+  if (zero_grad) k_adam_blocklive<true><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_blocks, c, live_blocks, step_dev, peers);
+  else k_adam_blocklive<false><<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_blocks, c, live_blocks, step_dev, peers);
   return vx_check_launch("vx_adam_step_blocklive");
+}
+
+static int make_peers(const uint64_t* peer_ptrs_host, int n_peers, VxPeers& peers, const char* where) {
+  VX_REQUIRE(n_peers >= 0 && n_peers <= VX_MAX_PEERS && (n_peers == 0 || peer_ptrs_host), where, "0 <= n_peers <= 15");
+  peers.n = n_peers;
+  for (int r = 0; r < n_peers; ++r) {
+    VX_REQUIRE((peer_ptrs_host[r] & 15) == 0, where, "peer arrays must be 16-byte aligned");
+    peers.p[r] = reinterpret_cast<float*>(peer_ptrs_host[r]);
+  }
+  return 0;
+}
+
+VX_API int vx_adam_step_blocklive(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t N, float beta1,
+                                  float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                                  float sqrt_bias_correction2, float eps, int zero_grad, uint8_t* live_blocks,
+                                  const float* step_dev, cudaStream_t st) {
+  VxPeers peers;
+  peers.n = 0;
+  return adam_step_blocklive(param, grad, exp_avg, exp_avg_sq, N, beta1, beta2, one_minus_beta1, one_minus_beta2, step_size,
+                             sqrt_bias_correction2, eps, zero_grad, live_blocks, step_dev, peers, st);
+}
+
+// vx_adam_step_blocklive on the slab of a replicated single-channel grid this rank owns, storing the parameters of every
+// updated block into the same slab of the replicas on n_peers other GPUs (see vx_adam_step_worklist_peers)
+VX_API int vx_adam_step_blocklive_peers(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t N, float beta1,
+                                        float beta2, float one_minus_beta1, float one_minus_beta2, float step_size,
+                                        float sqrt_bias_correction2, float eps, int zero_grad, uint8_t* live_blocks,
+                                        const float* step_dev, const uint64_t* peer_params_host, int n_peers,
+                                        cudaStream_t st) {
+  VxPeers peers;
+  if (int rc = make_peers(peer_params_host, n_peers, peers, "vx_adam_step_blocklive_peers")) return rc;
+  return adam_step_blocklive(param, grad, exp_avg, exp_avg_sq, N, beta1, beta2, one_minus_beta1, one_minus_beta2, step_size,
+                             sqrt_bias_correction2, eps, zero_grad, live_blocks, step_dev, peers, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sparse reduce-scatter of a single-channel gradient grid over peer memory.  The ray gradients of the sdf grid live in
+// the shell around the surface (~10 % of the 128-voxel blocks): instead of an NCCL reduce-scatter of the dense 64 MB grid,
+// every rank flags its non-zero blocks (vx_block_nonzero), and after a cross-rank barrier the owner of a slab PULLS, block
+// by block, only the flagged blocks of every rank's gradient (its own included, in rank order: a fixed summation order)
+// over NVLink and leaves scale * sum in its own slab.  The other ranks' copies of the slab are stale afterwards and are
+// cleared by their holders behind a second barrier.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_block_nonzero(const float* __restrict__ g, int64_t n_blocks, uint8_t* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n_blocks; b += n_warps) {
+    const float4 v = g4[b * 32 + lane];
+    const bool nz = (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+    const bool any = __any_sync(0xffffffffu, nz);
+    if (lane == 0) mask[b] = any ? 1 : 0;
+  }
+}
+
+VX_API int vx_block_nonzero(const float* g, int64_t N, uint8_t* mask, cudaStream_t st) {
+  if (N <= 0) return 0;
+  VX_REQUIRE(N % 128 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, "vx_block_nonzero", "numel % 128 == 0, 16-byte aligned");
+  const int64_t n_blocks = N / 128;
+  k_block_nonzero<<<(int)min((n_blocks + 7) / 8, (int64_t)vx_num_sms() * 8), 256, 0, st>>>(g, n_blocks, mask);
+  return vx_check_launch("vx_block_nonzero");
+}
+
+struct VxRanks {
+  const float* g[VX_MAX_PEERS + 1];
+  const uint8_t* m[VX_MAX_PEERS + 1];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) k_pull_reduce(float* out, const VxRanks ranks, int64_t n_blocks, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n_blocks; b += n_warps) {
+    uint32_t has = 0u;
+    if (lane < ranks.n) has = ranks.m[lane][b];          // one flag per rank, fetched in parallel
+    const uint32_t bits = __ballot_sync(0xffffffffu, has != 0u);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v[VX_MAX_PEERS + 1];
+#pragma unroll
+    for (int q = 0; q <= VX_MAX_PEERS; ++q)             // issue every load before the first use
+      if (q < ranks.n && ((bits >> q) & 1u)) v[q] = reinterpret_cast<const float4*>(ranks.g[q])[b * 32 + lane];
+#pragma unroll
+    for (int q = 0; q <= VX_MAX_PEERS; ++q)
+      if (q < ranks.n && ((bits >> q) & 1u)) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+    if (bits) reinterpret_cast<float4*>(out)[b * 32 + lane] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+  }
+}
+
+// out (this rank's own slab, N elements; may alias grads_host[own rank]) = scale * sum over the n_ranks arrays (device addresses
+// of the same slab on every rank, own included, in rank order) of the blocks their masks flag; blocks no rank flags keep
+// their (zero) content.
+VX_API int vx_pull_reduce(float* out, int64_t N, const uint64_t* grads_host, const uint64_t* masks_host, int n_ranks,
+                          float scale, cudaStream_t st) {
+  if (N <= 0) return 0;
+  VX_REQUIRE(N % 128 == 0 && n_ranks >= 1 && n_ranks <= VX_MAX_PEERS + 1 && grads_host && masks_host, "vx_pull_reduce",
+             "numel % 128 == 0, 1 <= n_ranks <= 16");
+  VxRanks r;
+  r.n = n_ranks;
+  for (int q = 0; q < n_ranks; ++q) {
+    VX_REQUIRE((grads_host[q] & 15) == 0, "vx_pull_reduce", "16-byte aligned arrays");
+    r.g[q] = reinterpret_cast<const float*>(grads_host[q]);
+    r.m[q] = reinterpret_cast<const uint8_t*>(masks_host[q]);
+  }
+  const int64_t n_blocks = N / 128;
+  k_pull_reduce<<<(int)min((n_blocks + 7) / 8, (int64_t)vx_num_sms() * 8), 256, 0, st>>>(out, r, n_blocks, scale);
+  return vx_check_launch("vx_pull_reduce");
 }
 
 // bias corrections are computed by the caller in Python doubles exactly like lib/utils.py:176-177,192
@@ -308,15 +424,6 @@ template <int kW> struct VxVec;
 template <> struct VxVec<4> { typedef float4 T; };
 template <> struct VxVec<2> { typedef float2 T; };
 template <> struct VxVec<1> { typedef float T; };
-
-// Replicas of the parameter array on other GPUs (NVLink peer memory): the owner of a voxel computes its update and stores
-// the new parameters into every replica as well -- the "all-gather" of the updated voxels is fused into the optimizer
-// pass, moves exactly the bytes that changed, and needs no staging buffer, count or capacity.
-#define VX_MAX_PEERS 15
-struct VxPeers {
-  float* p[VX_MAX_PEERS];
-  int n;
-};
 
 template <int kW, bool kZeroGrad>
 __global__ void __launch_bounds__(256) k_adam_voxel_list(float* __restrict__ param, float* __restrict__ grad,
@@ -411,13 +518,8 @@ VX_API int vx_adam_step_worklist_peers(float* param, float* grad, float* exp_avg
                                        float sqrt_bias_correction2, float eps, int zero_grad, uint32_t* touched,
                                        uint32_t* live, int group, int merge, uint32_t* work, const float* step_dev,
                                        const uint64_t* peer_params_host, int n_peers, cudaStream_t st) {
-  VX_REQUIRE(n_peers >= 0 && n_peers <= VX_MAX_PEERS && (n_peers == 0 || peer_params_host), "vx_adam_step_worklist_peers", "0 <= n_peers <= 15");
   VxPeers peers;
-  peers.n = n_peers;
-  for (int r = 0; r < n_peers; ++r) {
-    VX_REQUIRE((peer_params_host[r] & 15) == 0, "vx_adam_step_worklist_peers", "peer arrays must be 16-byte aligned");
-    peers.p[r] = reinterpret_cast<float*>(peer_params_host[r]);
-  }
+  if (int rc = make_peers(peer_params_host, n_peers, peers, "vx_adam_step_worklist_peers")) return rc;
   return adam_step_worklist(param, grad, exp_avg, exp_avg_sq, N, beta1, beta2, one_minus_beta1, one_minus_beta2, step_size,
                             sqrt_bias_correction2, eps, zero_grad, touched, live, group, merge, work, step_dev, peers, st);
 }

@@ -184,10 +184,14 @@ class FusedFineStep:
         # into its X-slab, steps only those voxels, and stores the updated parameters straight into the other ranks' replicas
         # of the k0 grid over NVLink peer memory (vx_adam_step_worklist_peers) -- re-scatter atomics and Adam traffic drop
         # by the world size and the replicas become bit-identical.  Needs CUDA IPC + peer access between the ranks' GPUs.
-        self.k0_owned = False
+        # The sdf grid goes the same way (sdf_peer): instead of NCCL's dense reduce-scatter + all-gather (2 x 56 MB per rank and
+        # step at 8 GPUs, the term that bounded the 8-GPU step), the owner of a slab pulls only the non-zero 128-voxel blocks
+        # of every rank's gradient (vx_block_nonzero / vx_pull_reduce) and its block-live Adam stores the updated blocks into
+        # the peers' replicas (vx_adam_step_blocklive_peers).
+        self.k0_owned = self.sdf_peer = False
         self.k0_peer_note = None
         if self.sharded and k0_ownership and self.k0_touched is not None and sparse_k0_exchange and self.C in (6, 12):
-            self._setup_k0_peers()
+            self._setup_peers()
         self.bitmap_probe = None   # bench.py: list collecting copies of (touched, live) as the k0 Adam launch sees them
         self.timings = None   # bench.py: list collecting (group, (start, end) CUDA events) around the k0 / sdf Adam launches
         if self.cfg is not None:
@@ -196,70 +200,90 @@ class FusedFineStep:
                            ('rgbnet', [self.mlp1.flat], c['lrate_rgbnet']), ('k_rgbnet', [self.mlp2.flat], c['lrate_k_rgbnet'])]
             self.lr = {name: lr for name, _, lr in self.groups}
 
-    def _setup_k0_peers(self):
-        """Exchange CUDA IPC handles of the k0 parameter allocation between the ranks of this node and map the peers' replicas
-        (vx_ipc_*: opened with this rank's device current, so that its kernels can store to them over NVLink); on any failure
-        the step keeps the replicated k0 update."""
+    def _setup_peers(self):
+        """Map the other ranks' replicas of the k0 parameters, the sdf parameters, the sdf gradient and its block mask into this
+        process (CUDA IPC handles of the containing cudaMalloc segments, exchanged over the process group and opened with this
+        rank's device current: vx_ipc_*), so that this rank's kernels can store to / load from them over NVLink.  All ranks or
+        none: on any failure the step keeps the NCCL exchange and the replicated k0 update."""
         import ctypes
         import torch.distributed as dist
         from ._lib import library, last_error
         W, r = self.world, self.rank
         lib = library()
-        flat = _storage(self.m.k0.grid.data).view(-1)
-        ok, ptrs, note = 1, [0] * W, ''
-        mine = None
+        m = self.m
+        self.sdf_mask = torch.zeros(m.sdf.grid.numel() // 128, dtype=torch.uint8, device=self.dev)
+        tensors = {'k0': _storage(m.k0.grid.data).view(-1), 'sdf': m.sdf.grid.data.view(-1), 'sdf_grad': self.sdf_grad.view(-1),
+                   'sdf_mask': self.sdf_mask}
+        ok, note, mine = 1, '', None
         try:
-            if (self.slab[1] - self.slab[0]) % 32:
-                raise RuntimeError('slab size is not a multiple of the 32-voxel bitmap words')
-            ptr, cur = flat.data_ptr(), torch.cuda.current_device()
-            base = [sg['address'] for sg in torch.cuda.memory_snapshot()
-                    if sg['device'] == cur and sg['address'] <= ptr < sg['address'] + sg['total_size']]
-            if len(base) != 1:
-                raise RuntimeError('k0 storage is not inside one cudaMalloc segment of the caching allocator')
-            buf = (ctypes.c_uint8 * 64)()
-            if lib.vx_ipc_get_handle(ctypes.c_void_p(base[0]), ctypes.cast(buf, ctypes.c_void_p)) != 0:
-                raise RuntimeError(last_error())
-            mine = (bytes(buf), ptr - base[0], flat.numel())
+            per = self.slab[1] - self.slab[0]
+            if per % 128 or m.sdf.grid.numel() % 128:
+                raise RuntimeError('slab size is not a multiple of the 128-voxel blocks')
+            cur = torch.cuda.current_device()
+            segs = [(sg['address'], sg['total_size']) for sg in torch.cuda.memory_snapshot() if sg['device'] == cur]
+            mine = {}
+            for name, t in tensors.items():
+                ptr = t.data_ptr()
+                base = [a for a, n in segs if a <= ptr and ptr + t.numel() * t.element_size() <= a + n]
+                if len(base) != 1:
+                    raise RuntimeError(f'{name} is not inside one cudaMalloc segment of the caching allocator')
+                buf = (ctypes.c_uint8 * 64)()
+                if lib.vx_ipc_get_handle(ctypes.c_void_p(base[0]), ctypes.cast(buf, ctypes.c_void_p)) != 0:
+                    raise RuntimeError(last_error())
+                mine[name] = (bytes(buf), ptr - base[0], t.numel())
         except Exception as e:      # noqa: BLE001 -- capability probe: IPC / P2P may be unavailable (containers, MIG, PCIe boxes)
-            ok, note = 0, f'{type(e).__name__}: {e}'
+            ok, note, mine = 0, f'{type(e).__name__}: {e}', None
         handles = [None] * W
         dist.all_gather_object(handles, mine)
-        opened = []
+        ptrs = {name: [t.data_ptr()] * W for name, t in tensors.items()}      # own address at index `rank`
+        self._ipc_opened = []
         if ok and all(h is not None for h in handles):
             try:
                 for q in range(W):
                     if q == r:
                         continue
-                    hb, off, n = handles[q]
-                    assert n == flat.numel()
-                    hbuf = (ctypes.c_uint8 * 64).from_buffer_copy(hb)
-                    out = ctypes.c_uint64(0)
-                    if lib.vx_ipc_open_handle(ctypes.cast(hbuf, ctypes.c_void_p), ctypes.cast(ctypes.pointer(out), ctypes.c_void_p)) != 0:
-                        raise RuntimeError(last_error())
-                    opened.append(int(out.value))
-                    ptrs[q] = int(out.value) + off
-                    assert ptrs[q] % 16 == 0
+                    bases = {}
+                    for name, (hb, off, n) in handles[q].items():
+                        assert n == tensors[name].numel()
+                        if hb not in bases:       # (two tensors may share a segment: a handle is opened once per process)
+                            hbuf = (ctypes.c_uint8 * 64).from_buffer_copy(hb)
+                            out = ctypes.c_uint64(0)
+                            if lib.vx_ipc_open_handle(ctypes.cast(hbuf, ctypes.c_void_p), ctypes.cast(ctypes.pointer(out), ctypes.c_void_p)) != 0:
+                                raise RuntimeError(last_error())
+                            bases[hb] = int(out.value)
+                            self._ipc_opened.append(bases[hb])
+                        ptrs[name][q] = bases[hb] + off
             except Exception as e:      # noqa: BLE001
                 ok, note = 0, f'{type(e).__name__}: {e}'
         else:
             ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)       # all ranks or none
-        self._k0_ipc_opened = opened
         if int(flag.item()) != 1:
             self._close_k0_peers()
-            self.k0_peer_note = 'k0 ownership unavailable (%s): replicated k0 update' % (note or 'a peer failed')
+            self.k0_peer_note = 'peer memory unavailable (%s): NCCL exchange, replicated k0 update' % (note or 'a peer failed')
             return
-        per = (self.slab[1] - self.slab[0]) * self.C
-        self._k0_peer_ptrs = [ptrs[q] + 4 * self.rank * per for q in range(W) if q != r]
-        self._k0_bar = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        lo, per, C = self.slab[0], self.slab[1] - self.slab[0], self.C
+        others = [q for q in range(W) if q != r]
+        self._k0_peer_ptrs = [ptrs['k0'][q] + 4 * lo * C for q in others]        # my slab inside the peers' k0 replicas
+        self._sdf_peer_ptrs = [ptrs['sdf'][q] + 4 * lo for q in others]          # ... inside their sdf parameter replicas
+        self._sdf_grad_ptrs = [ptrs['sdf_grad'][q] + 4 * lo for q in range(W)]   # my slab of every rank's gradient (own included)
+        self._sdf_mask_ptrs = [ptrs['sdf_mask'][q] + lo // 128 for q in range(W)]
+        self._bar = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.k0_owned = True
+        self.sdf_peer = bool(self.sdf_live is not None)      # (the peer-store Adam is the block-live kernel)
+
+    def _barrier(self, async_op=False):
+        """cross-rank barrier on the current stream (a 4-byte NCCL all-reduce): every rank's earlier kernels on its stream --
+        peer loads and stores included -- are complete when it completes"""
+        import torch.distributed as dist
+        return dist.all_reduce(self._bar, async_op=async_op)
 
     def _close_k0_peers(self):
         from ._lib import library
-        for p in getattr(self, '_k0_ipc_opened', []):
+        for p in getattr(self, '_ipc_opened', []):
             library().vx_ipc_close_handle(p)
-        self._k0_ipc_opened = []
+        self._ipc_opened = []
 
     # the model keeps a back-reference to its step (model._fused): copies / pickles of the model do not drag the step's
     # buffers, events and CUDA graphs along
@@ -558,7 +582,7 @@ class FusedFineStep:
         if self.k0_owned:
             import torch.distributed as dist
             self._gather_k0_state()
-            self.k0_owned = False
+            self.k0_owned = self.sdf_peer = False
             torch.cuda.synchronize()
             self._close_k0_peers()            # unmap the peers' replicas ...
             dist.barrier()                    # ... before any owner may free its own
@@ -584,7 +608,7 @@ class FusedFineStep:
                 flat = t.view(-1)
                 dist.all_gather_into_tensor(flat, flat[self.slab[0]:self.slab[1]])
         self._gather_k0_state()
-        self.k0_owned = False
+        self.k0_owned = self.sdf_peer = False
         self.sharded = False
         if self.sdf_live is not None:
             self.sdf_live.fill_(1)       # the gathered moments of the other ranks' slabs may be non-zero anywhere
@@ -593,7 +617,12 @@ class FusedFineStep:
     def _sync_begin(self):
         import torch.distributed as dist
         AVG = dist.ReduceOp.AVG
-        if self.sharded:
+        if self.sdf_peer:
+            # peer-memory exchange: flag the non-zero blocks of this rank's gradient; the barrier (joined in _sync_end, before the
+            # owners pull) says that every rank's backward pass and flags are complete
+            call('vx_block_nonzero', self.sdf_grad.view(-1), self.sdf_grad.numel(), self.sdf_mask)
+            self._works = [self._barrier(async_op=True)]
+        elif self.sharded:
             flat = self.sdf_grad.view(-1)      # in place: the owned slab of this buffer receives the rank-averaged gradient
             self._works = [dist.reduce_scatter_tensor(flat[self.slab[0]:self.slab[1]], flat, op=AVG, async_op=True)]
         else:
@@ -626,6 +655,12 @@ class FusedFineStep:
     def _sync_end(self):
         for w in self._works:
             w.wait()
+        self._works = []
+        if self.sdf_peer:
+            # this rank's slab <- mean over ranks of the flagged blocks, pulled over NVLink in rank order
+            lo, hi = self.slab
+            call('vx_pull_reduce', self.sdf_grad.view(-1)[lo:hi], hi - lo, self._sdf_grad_ptrs, self._sdf_mask_ptrs, self.world,
+                 1.0 / self.world)
 
     def grad_sync(self):
         """Average gradients over ranks: dense NCCL all-reduce (AVG) for the sdf grid (67 MB at 256^3) and the two flat
@@ -687,6 +722,10 @@ class FusedFineStep:
         if self.sharded:    # only the owned X-slab of the gradient is regularised (and stepped); _slab_covers(flags) holds
             call('vx_sdf_regularisers_backward_slab', self.dG if tv['smooth_grad_tv'] > 0 else None, m.sdf.grid, X, Y, Z,
                  m._voxel_size_host, wt, wt, wt, self.sdf_grad, self.tv_active if tv['smooth_grad_tv'] > 0 else None, *self.slab_x)
+            if self.sdf_peer:
+                # the slab kernel read one halo plane of the neighbouring slabs from this rank's parameter replica: their owners
+                # must not store updated parameters into it before every rank is past this point
+                self._barrier()
             return
         if tv['smooth_grad_tv'] > 0 and tv['sdf_tv'] > 0 and dense:
             # both regularisers land in the sdf gradient with one read-modify-write
@@ -714,7 +753,7 @@ class FusedFineStep:
         self.regularise_apply(flags, global_batch)
 
     @torch.no_grad()
-    def optimizer_step(self, only=None, advance=True, step=None, lrs=None):
+    def optimizer_step(self, only=None, advance=True, step=None, lrs=None, barrier=True):
         """lib/utils.py:83-199 with betas (0.9, 0.99), eps 1e-8 (lib/utils.py:229); grads are zeroed in the same pass.
         only: restrict to these group names (the multi-GPU step updates k0 while the sdf all-reduce is in flight).
         step / lrs: the Adam step number and learning rates to apply (default: advance the counter, current rates)."""
@@ -725,6 +764,7 @@ class FusedFineStep:
         lrs = lrs if lrs is not None else self.lr
         beta1, beta2, eps = 0.9, 0.99, 1e-8
         bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        peer_stores = False
         for gi, (name, params, _) in enumerate(self.groups):
             if only is not None and name not in only:
                 continue
@@ -748,20 +788,28 @@ class FusedFineStep:
                     # (un-reduced) gradient and are cleared here, the Adam pass clears the slab itself
                     lo, hi = self.slab
                     g = tensors[1].view(-1)
-                    g[:lo].zero_(); g[hi:].zero_()
+                    if not self.sdf_peer:
+                        g[:lo].zero_(); g[hi:].zero_()
                     tensors = [t.view(-1)[lo:hi] for t in tensors]
                     sdf_live = sdf_live[lo // 128:hi // 128] if sdf_live is not None else None
-                    self._params_dirty = True
-                if sdf_live is not None:
+                    self._params_dirty = not self.sdf_peer
+                if sdf_live is not None and name == 'sdf' and self.sharded and self.sdf_peer:
+                    # the updated blocks go straight into the peers' replicas; the other slabs of the gradient buffer (this rank's
+                    # local gradient, pulled by their owners) are cleared behind the closing barrier below
+                    call('vx_adam_step_blocklive_peers', *tensors, tensors[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
+                         math.sqrt(bc2), eps, 1, sdf_live, None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi],
+                         self._sdf_peer_ptrs, len(self._sdf_peer_ptrs))
+                    peer_stores = 'sdf'
+                elif sdf_live is not None:
                     call('vx_adam_step_blocklive', *tensors, tensors[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
                          math.sqrt(bc2), eps, 1, sdf_live, None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
+                if sdf_live is not None:
                     if timed:
                         ev[1].record()
                         self.timings.append((name, ev))
                     continue
                 if touched is not None and self.k0_owned:
-                    # the owned X-slab only; the new parameters go to every replica (peer stores), then a cross-rank barrier
-                    import torch.distributed as dist
+                    # the owned X-slab only; the new parameters go to every replica (peer stores); cross-rank barrier below
                     lo, hi = self.slab
                     C = self.C
                     sl = [t.view(-1)[lo * C:hi * C] for t in tensors]
@@ -769,7 +817,7 @@ class FusedFineStep:
                          math.sqrt(bc2), eps, 1, touched[lo // 32:hi // 32], live[lo // 32:hi // 32], C, 1, self._k0_list,
                          None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi],
                          self._k0_peer_ptrs, len(self._k0_peer_ptrs))
-                    dist.all_reduce(self._k0_bar)      # every rank's peer stores have landed before anyone reads k0 again
+                    peer_stores = peer_stores or 'k0'
                 elif touched is not None:
                     call('vx_adam_step_worklist', *tensors, tensors[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
                          math.sqrt(bc2), eps, 1, touched, live, self.C, 1, self._k0_list,
@@ -783,6 +831,14 @@ class FusedFineStep:
                 if timed:
                     ev[1].record()
                     self.timings.append((name, ev))
+        if peer_stores and barrier:
+            # every rank's peer stores have landed (and every owner has pulled the gradient blocks it reduces) before anyone
+            # reads the parameters again / clears the gradient slabs it does not own
+            self._barrier()
+            if peer_stores == 'sdf':
+                lo, hi = self.slab
+                g = self.sdf_grad.view(-1)
+                g[:lo].zero_(); g[hi:].zero_()
 
     def state_dict(self):
         """Optimizer state of the fused step (the model's own state_dict holds the parameters): Adam moments per
@@ -868,7 +924,7 @@ class FusedFineStep:
                 # re-scatter below and the next step's march
                 self._sync_begin()
             self._sync_k0()
-            self.optimizer_step(only=('k0',), **kw)
+            self.optimizer_step(only=('k0',), barrier=not self.sdf_peer, **kw)     # (sdf_peer: one closing barrier for both grids)
             self._sync_end()
             self.regularise_apply(flags, add_loss=False)
             self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet'), **kw)
@@ -983,7 +1039,7 @@ class FusedFineStep:
             self._graph_launches[key] = launch_count() - l0
         g.replay()
         self._pending = cur if self.defer_optimizer else None
-        self._params_dirty = self.sharded      # (host flags do not move during a replay)
+        self._params_dirty = self.sharded and not self.sdf_peer      # (host flags do not move during a replay)
         self.launches_replayed += self._graph_launches[key]
         return self.loss
 
