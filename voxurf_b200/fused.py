@@ -164,6 +164,7 @@ class FusedFineStep:
         self._pending = None
         self._opt_stream = None
         self._k0_work, self._works = [], []      # outstanding NCCL work of the data-parallel exchange
+        self._k0_stream = None
         # Slab-sharded data-parallel exchange (SURVEY.md 8e "preferred form"): reduce-scatter of the sdf gradient over X-slabs,
         # regularisers + Adam on the owned slab only, all-gather of the updated sdf PARAMETERS at the start of the next step
         # (it overlaps ray set-up and the march, which read rays and the mask cache only).  Non-owned slabs of this rank's sdf
@@ -923,10 +924,24 @@ class FusedFineStep:
                 # leave NCCL work unjoined, nor wait for work of an earlier launch), and they still run beside the k0
                 # re-scatter below and the next step's march
                 self._sync_begin()
-            self._sync_k0()
-            self.optimizer_step(only=('k0',), barrier=not self.sdf_peer, **kw)     # (sdf_peer: one closing barrier for both grids)
-            self._sync_end()
-            self.regularise_apply(flags, add_loss=False)
+            if self.sdf_peer:
+                # the k0 path (row scatter + owner-side Adam with peer stores) and the sdf path (barrier, pull-reduce, regulariser,
+                # slab Adam with peer stores) are independent: side by side on two streams, one closing barrier for both grids
+                cur = torch.cuda.current_stream()
+                if self._k0_stream is None:
+                    self._k0_stream = torch.cuda.Stream(device=self.dev)
+                self._k0_stream.wait_stream(cur)
+                with torch.cuda.stream(self._k0_stream):
+                    self._sync_k0()
+                    self.optimizer_step(only=('k0',), barrier=False, **kw)
+                self._sync_end()
+                self.regularise_apply(flags, add_loss=False)
+                cur.wait_stream(self._k0_stream)
+            else:
+                self._sync_k0()
+                self.optimizer_step(only=('k0',), **kw)
+                self._sync_end()
+                self.regularise_apply(flags, add_loss=False)
             self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet'), **kw)
         else:
             self.regularise_apply(flags, add_loss=False)
