@@ -376,6 +376,9 @@ def main():
                 loss_host.copy_(loss.reshape(1), non_blocking=False)
 
     # ---- warm-up: every execution variant (TV / non-TV) run eagerly once and captured BEFORE anything is timed
+    # (the clock sampler starts here: nvidia-smi needs a few hundred ms before its first sample)
+    clk = ClockSampler(local_rank, period_ms=10)
+    clk.__enter__()
     if fused is not None:
         gs_next[0] = fused.warm_up(dev_pool, START_STEP)
         run(max(0, START_STEP + PRE_STEPS - gs_next[0]))     # the timed window starts at the same global step in every configuration
@@ -395,7 +398,7 @@ def main():
                                   'NVLink peer memory (vx_adam_step_worklist_peers)' if fused.k0_owned else
                                   'every rank re-scatters all rows and steps every voxel' + (f' [{fused.k0_peer_note}]' if fused.k0_peer_note else ''))
                                  ) if fused.sharded else 'dense all-reduces (sdf, MLPs) + k0 row exchange'
-    with ClockSampler(local_rank) as clk:
+    try:
         # ---- device-resident timing
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
@@ -433,6 +436,8 @@ def main():
             barrier()
             ts1 = time.perf_counter()
             sustained = {'steps': n_sus, 'ms_per_step': s0.elapsed_time(s1) / n_sus}
+    finally:
+        clk.__exit__()
     t = torch.tensor([ms, ms_e2e, sustained['ms_per_step'] if sustained else 0.0], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -485,6 +490,12 @@ def main():
     if rank == 0:
         total_rays = rays * world * args.steps
         value = total_rays / (ms * 1e-3)
+        clocks = clk.summary(tw0, tw2)          # the device-resident and end-to-end timed regions
+        if clocks['samples'] < 3 and sustained:
+            # 2 x 30 steps are shorter than three nvidia-smi samples: take the samples of the whole measurement (timed, e2e and
+            # the sustained repeat of the same steps, back to back)
+            clocks = clk.summary(tw0, ts1)
+            clocks['window'] = 'timed + e2e + sustained regions'
         V = G ** 3
         peak, peak_src = measured_peak()
         tf_peak, tf_src = measured_tensor_peak()
@@ -492,7 +503,7 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': args.scaling,
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'execution': execution,
-                'clocks': clk.summary(tw0, tw2), 'gpu_launches': int(launches),
+                'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': total_rays / (ms_e2e * 1e-3), 'unit': 'rays/s',
                         'h2d_bytes_per_step': sum(t_.numel() * t_.element_size() for t_ in pool[0]), 'd2h_bytes_per_step': 4,
                         'ms_per_step': ms_e2e / args.steps}}
