@@ -546,17 +546,25 @@ def main():
             line['kernel_ms_per_step'] = {k: round(v[0], 5) for k, v in sorted(kt.items(), key=lambda x: -x[1][0])}
             if t_adam.get('k0'):
                 tk = float(np.mean(t_adam['k0']))
-                line['roofline_k0_adam'] = {'bound': 'hbm', 'kernel': 'k_adam_sparse (k0 grid, sparse-aware)', 'achieved': adam_bytes / (tk * 1e-3) / 1e9,
+                line['roofline_k0_adam'] = {'bound': 'hbm', 'kernel': 'k_bitmap_voxel_list + k_adam_voxel_list (k0 grid, voxels in touched | live only)', 'achieved': adam_bytes / (tk * 1e-3) / 1e9,
                                             'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': adam_bytes / (tk * 1e-3) / 1e9 / peak,
                                             'ms_per_launch': tk, 'algorithmic_bytes_per_launch': adam_bytes, 'sparse': sparse,
-                                            'traffic': measured_traffic('k_adam_sparse')}
+                                            'traffic': measured_traffic('k_adam_voxel_list')}
             if t_adam.get('sdf'):
                 tsd = float(np.mean(t_adam['sdf']))
-                bytes_sdf = 32 * V // (world if fused.sharded else 1)
-                line['roofline_sdf_adam'] = {'bound': 'hbm', 'kernel': 'k_adam (sdf grid, %d^3 fp32, dense%s, 32 B/element)' % (G, ', X-slab of this rank' if fused.sharded else ''),
+                n_el = V // (world if fused.sharded else 1)
+                bytes_sdf, kname, live_frac = 32 * n_el, 'k_adam (sdf grid, %d^3 fp32, dense, 32 B/element' % G, None
+                if fused.sdf_live is not None:
+                    # block-live pass: 4 B/element of gradient everywhere, + 28 B/element in the blocks that are (or become) live
+                    lv = fused.sdf_live[fused.slab[0] // 128:fused.slab[1] // 128] if fused.sharded else fused.sdf_live
+                    live_frac = float(lv.float().mean())
+                    bytes_sdf = int(n_el * (4 + 28 * live_frac))
+                    kname = 'k_adam_blocklive (sdf grid, %d^3 fp32, 128-voxel blocks: 4 B/element + 28 B/element where live' % G
+                line['roofline_sdf_adam'] = {'bound': 'hbm', 'kernel': kname + (', X-slab of this rank)' if fused.sharded else ')'),
                                              'achieved': bytes_sdf / (tsd * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                                             'frac': bytes_sdf / (tsd * 1e-3) / 1e9 / peak, 'ms_per_launch': tsd,
-                                             'algorithmic_bytes_per_launch': bytes_sdf, 'traffic': measured_traffic('k_adam')}
+                                             'frac': bytes_sdf / (tsd * 1e-3) / 1e9 / peak, 'ms_per_launch': tsd, 'live_block_fraction': live_frac,
+                                             'algorithmic_bytes_per_launch': bytes_sdf,
+                                             'traffic': measured_traffic('k_adam_blocklive' if fused.sdf_live is not None else 'k_adam')}
             # ---- step-level bounds: the dense-equivalent HBM figure of SURVEY 8d, and the honest combined bound
             B_dense = algorithmic_bytes(V, C, 1 / 3, M2, M3, M4, rays, 1 / 3)
             n_act = int(fused.tv_active.sum()) if getattr(fused, 'tv_active', None) is not None else V

@@ -50,7 +50,7 @@ def num(r, key):
 agg = defaultdict(list)
 for r in rows[2:]:
     name = re.sub(r'\(.*', '', r[col['Kernel Name']])
-    name = re.sub(r'<.*', '', name)
+    name = re.sub(r'<.*', '', name).replace('void ', '')
     agg[name].append({k: num(r, k) for k in want})
 summary = {}
 for name, ls in agg.items():
