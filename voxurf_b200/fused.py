@@ -1117,7 +1117,8 @@ class FusedFineStep:
             self.k0_touched.zero_()
         r = [float(v) for v in res.cpu()]
         return {'ok': bool(identical and r[4] == 1.0 and k0_spread < 1e-6), 'replicas_identical_sdf_mlps': bool(identical),
-                'k0_checksum_rel_spread': k0_spread, 'exchange': 'slab reduce-scatter + sharded Adam + param all-gather' if self.sharded else 'dense all-reduce',
+                'k0_checksum_rel_spread': k0_spread, 'exchange': ('peer-memory pull-reduce + slab Adam with peer stores (sdf, k0), NCCL all-reduce (MLPs)' if self.sdf_peer else
+                             'slab reduce-scatter + sharded Adam + param all-gather') if self.sharded else 'dense all-reduce',
                 'grad_vs_single_gpu_max_err_over_max': {'sdf': r[0], 'k0': r[1], 'rgbnet': r[2], 'k_rgbnet': r[3]},
                 'tolerance': f'|d| <= {rtol} |g| + {rtol} max|g| (all but <= 1e-5 of the elements: ReLU-gate flips)', 'world': W}
 
