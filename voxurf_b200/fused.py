@@ -165,6 +165,7 @@ class FusedFineStep:
         self._opt_stream = None
         self._k0_work, self._works = [], []      # outstanding NCCL work of the data-parallel exchange
         self._k0_stream = None
+        self._k0_hook, self._k0_forked = None, False
         # Slab-sharded data-parallel exchange (SURVEY.md 8e "preferred form"): reduce-scatter of the sdf gradient over X-slabs,
         # regularisers + Adam on the owned slab only, all-gather of the updated sdf PARAMETERS at the start of the next step
         # (it overlaps ray set-up and the march, which read rays and the mask cache only).  Non-owned slabs of this rank's sdf
@@ -476,6 +477,8 @@ class FusedFineStep:
                            n4, self.cap4, None)
             if sparse_dp:      # dL/dk0 of this rank's rows is final here: its all-gather runs under the rest of the backward
                 self._start_k0_exchange(n4)
+                if self._k0_hook is not None:
+                    self._k0_hook()      # (deferred step) ... and so do the row scatter and the k0 Adam pass, on their own stream
             # The weight-gradient launch (one persistent CTA per SM, tensor / latency bound, ~220 us) only feeds the
             # optimizer; the scatter kernels below (atomics / ALU bound, independent inputs) run beside it on the main
             # stream.  Fork here, join at the end of this method; inside a CUDA-graph capture the side stream joins
@@ -515,6 +518,8 @@ class FusedFineStep:
                  self.cap4, m._voxel_size_host, int(m.use_grad_norm), self.P, self.Vp, self.P2, self.V2, self.disp, self.L,
                  self.ld1, self.ld2, self.dX1, self.dX2, self.d_sdf_s, self.d_grad_s, grad_target,
                  None if sparse_dp else _storage(self.k0_grad), None if sparse_dp else self.k0_touched)
+            if self._k0_hook is not None and not sparse_dp:
+                self._k0_hook()          # (deferred step, one GPU) the k0 gradient is final: its Adam pass runs beside the rest of the backward
             call('vx_alpha2weight_seg_backward', self.alpha, self.weight, self.T, self.keep if thres > 0 else None,
                  self.alphainv_last, self.keep_off, self.i_end, N, self.d_w, self.d_last, self.d_alpha)
             call('vx_fused_alpha_sdf_backward', X, Y, Z, mn, mx, *self._pts(), n2, viewdirs.contiguous(), self.sdf_s, self.grad_s,
@@ -754,7 +759,7 @@ class FusedFineStep:
         self.regularise_apply(flags, global_batch)
 
     @torch.no_grad()
-    def optimizer_step(self, only=None, advance=True, step=None, lrs=None, barrier=True):
+    def optimizer_step(self, only=None, advance=True, step=None, lrs=None, barrier=True, early=False):
         """lib/utils.py:83-199 with betas (0.9, 0.99), eps 1e-8 (lib/utils.py:229); grads are zeroed in the same pass.
         only: restrict to these group names (the multi-GPU step updates k0 while the sdf all-reduce is in flight).
         step / lrs: the Adam step number and learning rates to apply (default: advance the counter, current rates)."""
@@ -816,13 +821,13 @@ class FusedFineStep:
                     sl = [t.view(-1)[lo * C:hi * C] for t in tensors]
                     call('vx_adam_step_worklist_peers', *sl, sl[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
                          math.sqrt(bc2), eps, 1, touched[lo // 32:hi // 32], live[lo // 32:hi // 32], C, 1, self._k0_list,
-                         None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi],
+                         None if self._dev_consts is None else (self._dev_consts[10:12] if early else self._dev_consts[2 + 2 * gi:4 + 2 * gi]),
                          self._k0_peer_ptrs, len(self._k0_peer_ptrs))
                     peer_stores = peer_stores or 'k0'
                 elif touched is not None:
                     call('vx_adam_step_worklist', *tensors, tensors[0].numel(), beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1,
                          math.sqrt(bc2), eps, 1, touched, live, self.C, 1, self._k0_list,
-                         None if self._dev_consts is None else self._dev_consts[2 + 2 * gi:4 + 2 * gi])
+                         None if self._dev_consts is None else (self._dev_consts[10:12] if early else self._dev_consts[2 + 2 * gi:4 + 2 * gi]))
                 else:
                     call('vx_adam_step', *tensors, None, tensors[0].numel(),
                          beta1, beta2, 1 - beta1, 1 - beta2, lr / bc1, math.sqrt(bc2), eps, 0, 1, touched, live, self.C,
@@ -917,35 +922,59 @@ class FusedFineStep:
         """Everything between a step's backward pass and the next forward: completion of the gradient exchange, the k0
         row re-scatter, the regularisers' gradients, the Adam passes (run.py:641-659).  pend: dict(flags, step, lrs)."""
         flags, kw = pend['flags'], dict(step=pend['step'], lrs=pend['lrs'])
+        k0_done = bool(pend.get('k0_done'))      # the k0 grid was stepped inside its own step's launch (_k0_early)
         if self.world > 1:
             if self.defer_optimizer:
-                # the sdf reduce-scatter / MLP all-reduce of the pending step start HERE, not at the end of that step's
+                # the sdf exchange / MLP all-reduce of the pending step start HERE, not at the end of that step's
                 # body: every collective then begins and ends inside one launch of the step (a CUDA-graph capture cannot
-                # leave NCCL work unjoined, nor wait for work of an earlier launch), and they still run beside the k0
-                # re-scatter below and the next step's march
+                # leave NCCL work unjoined, nor wait for work of an earlier launch), and they still run beside the next step's march
                 self._sync_begin()
             if self.sdf_peer:
                 # the k0 path (row scatter + owner-side Adam with peer stores) and the sdf path (barrier, pull-reduce, regulariser,
                 # slab Adam with peer stores) are independent: side by side on two streams, one closing barrier for both grids
                 cur = torch.cuda.current_stream()
-                if self._k0_stream is None:
-                    self._k0_stream = torch.cuda.Stream(device=self.dev)
-                self._k0_stream.wait_stream(cur)
-                with torch.cuda.stream(self._k0_stream):
-                    self._sync_k0()
-                    self.optimizer_step(only=('k0',), barrier=False, **kw)
+                if not k0_done:
+                    if self._k0_stream is None:
+                        self._k0_stream = torch.cuda.Stream(device=self.dev)
+                    self._k0_stream.wait_stream(cur)
+                    with torch.cuda.stream(self._k0_stream):
+                        self._sync_k0()
+                        self.optimizer_step(only=('k0',), barrier=False, **kw)
                 self._sync_end()
                 self.regularise_apply(flags, add_loss=False)
-                cur.wait_stream(self._k0_stream)
+                if not k0_done:
+                    cur.wait_stream(self._k0_stream)
             else:
-                self._sync_k0()
-                self.optimizer_step(only=('k0',), **kw)
+                if not k0_done:
+                    self._sync_k0()
+                    self.optimizer_step(only=('k0',), **kw)
+                elif self.k0_owned:
+                    self._barrier()      # the early k0 pass's peer stores
                 self._sync_end()
                 self.regularise_apply(flags, add_loss=False)
             self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet'), **kw)
         else:
             self.regularise_apply(flags, add_loss=False)
-            self.optimizer_step(**kw)
+            self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet') if k0_done else None, **kw)
+
+    def _k0_early_enabled(self):
+        return bool(self.defer_optimizer and self.k0_touched is not None and self.k0_cl and not self.deterministic and self.tensor_core
+                    and (self.world == 1 or self.sparse_k0_exchange))
+
+    def _k0_early(self, kw):
+        """(deferred step) The k0 grid's share of the optimizer phase inside its own step's launch, as soon as its gradient is
+        final -- after k_row_backward on one GPU; at N > 1 after the k0 rows are exported: all-gather, owned-corner scatter --
+        then the voxel-list Adam pass (with the peer stores), on a stream of its own beside the rest of the backward pass, which
+        neither reads nor writes the k0 grid.  The deferred phase of the next launch is then the sdf grid and the MLPs only."""
+        main = torch.cuda.current_stream()
+        if self._k0_stream is None:
+            self._k0_stream = torch.cuda.Stream(device=self.dev)
+        self._k0_stream.wait_stream(main)
+        with torch.cuda.stream(self._k0_stream):
+            if self.world > 1:
+                self._sync_k0()
+            self.optimizer_step(only=('k0',), barrier=False, early=True, **kw)
+        self._k0_forked = True
 
     def flush(self):
         """Apply a deferred optimizer phase now (defer_optimizer=True): call before reading parameters."""
@@ -991,7 +1020,17 @@ class FusedFineStep:
                 if self._ag_work is not None:
                     self._ag_work.wait()     # the FD gradient reads the whole sdf grid
                 self.regularise_prepare(flags)
-        loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
+        k0_early = self._k0_early_enabled()
+        if k0_early:
+            kw0 = dict(step=max(self.adam_steps + (1 if self._dev_consts is None else 0), 1), lrs=dict(self.lr))
+            self._k0_hook = lambda: self._k0_early(kw0)
+        try:
+            loss = self.forward_backward(rays_o, rays_d, viewdirs, target, global_step)
+        finally:
+            self._k0_hook = None
+        if self._k0_forked:
+            main.wait_stream(self._k0_stream)      # join inside this launch
+            self._k0_forked = False
         if not early_tv:
             self.regularise_prepare(flags)
         if flags[0] and self.cfg['tv_terms']['smooth_grad_tv'] > 0:
@@ -1005,7 +1044,7 @@ class FusedFineStep:
                 self._sync_begin()   # the sdf reduce-scatter (or all-reduce) and the MLP all-reduce start right after the backward pass
         if self._dev_consts is None:
             self.adam_steps += 1
-        pend = dict(flags=flags, step=max(self.adam_steps, 1), lrs=dict(self.lr))
+        pend = dict(flags=flags, step=max(self.adam_steps, 1), lrs=dict(self.lr), k0_done=k0_early)
         if self.defer_optimizer:
             self._pending = pend
         else:
@@ -1027,7 +1066,7 @@ class FusedFineStep:
         s_val = 1. / (global_step + m.s_ratio / m.s_start - m.step_start) * m.s_ratio          # lib/voxurf_fine.py:466-473
         m._s_val_host = float(np.float32(s_val))
         self.adam_steps += 1
-        cur = dict(flags=flags, step=self.adam_steps, lrs=dict(self.lr))
+        cur = dict(flags=flags, step=self.adam_steps, lrs=dict(self.lr), k0_done=self._k0_early_enabled())
         opt = pend_in if self.defer_optimizer else cur      # the optimizer phase that executes inside this launch
         host = [float(np.float32(1.0) / np.float32(m._s_val_host)), 0.0]
         for name, _, _ in self.groups:
@@ -1036,6 +1075,8 @@ class FusedFineStep:
             else:
                 bc1, bc2 = 1 - 0.9 ** opt['step'], 1 - 0.99 ** opt['step']
                 host += [opt['lrs'][name] / bc1, math.sqrt(bc2)]
+        bc1, bc2 = 1 - 0.9 ** cur['step'], 1 - 0.99 ** cur['step']
+        host += [cur['lrs']['k0'] / bc1, math.sqrt(bc2)]      # [10:12]: THIS step's k0 pass (_k0_early runs it inside this launch)
         self.consts[:len(host)].copy_(torch.tensor(host, dtype=torch.float32))
         torch._foreach_copy_([self.in_o, self.in_d, self.in_v, self.in_t], [rays_o, rays_d, viewdirs, target])
         g = self._graphs.get(key)
