@@ -958,8 +958,11 @@ class FusedFineStep:
             self.optimizer_step(only=('sdf', 'rgbnet', 'k_rgbnet') if k0_done else None, **kw)
 
     def _k0_early_enabled(self):
+        # One GPU only.  Measured at N > 1 (profiles/r02_bench_n8_k0_early_experiment.json): the k0 path then hangs off the row
+        # all-gather, i.e. off the slowest rank's backward pass, and joining it at the end of the launch costs more than it hides
+        # (N = 8: 1.26 -> 1.32 ms; N = 2: 1.156 -> 1.143 ms); there it stays in the deferred phase beside the next step's march.
         return bool(self.defer_optimizer and self.k0_touched is not None and self.k0_cl and not self.deterministic and self.tensor_core
-                    and (self.world == 1 or self.sparse_k0_exchange))
+                    and self.world == 1)
 
     def _k0_early(self, kw):
         """(deferred step) The k0 grid's share of the optimizer phase inside its own step's launch, as soon as its gradient is
