@@ -561,3 +561,131 @@ def test_adam_blocklive_is_bit_identical_to_dense():
             assert torch.equal(x, y)
         assert (gb == 0).all()
     assert 0 < int(live.sum()) < 300
+
+
+# ------------------------------------------------------------------------------------------------ data-parallel exchange kernels
+# (one GPU: "ranks" and "peers" are arrays on the same device -- the kernels only see device addresses; the multi-GPU wiring
+# over CUDA IPC / NVLink is covered by tests/test_gpu_multi.py on boxes with >= 2 GPUs)
+def test_block_nonzero_and_pull_reduce_fixed_order_sum():
+    """vx_block_nonzero + vx_pull_reduce (sparse reduce-scatter of the sdf gradient by the slab owner): scale * sum, in rank
+    order, of the 128-element blocks the ranks flagged; unflagged blocks keep their content; `out` aliases the own array."""
+    from voxurf_b200._lib import call
+    rs = np.random.RandomState(11)
+    W, nb = 3, 96
+    N = nb * 128
+    gs, ms = [], []
+    for q in range(W):
+        g = np.zeros((nb, 128), np.float32)
+        for b in rs.choice(nb, 30, replace=False):
+            g[b, rs.randint(0, 128, 7)] = rs.standard_normal(7)
+        g[5 + q, 3] = 1e-30          # a denormal-ish single element still flags its block
+        gs.append(cu(T(g.reshape(-1))))
+        m = torch.full((nb,), 7, dtype=torch.uint8, device=DEV)
+        call('vx_block_nonzero', gs[q], N, m)
+        assert torch.equal(m.bool().cpu(), torch.from_numpy((g != 0).any(1)))
+        ms.append(m)
+    own = 1
+    acc = torch.zeros(N, device=DEV)
+    for q in range(W):        # fp32, rank order (adding the exact zeros of unflagged blocks changes nothing)
+        acc = acc + gs[q] * ms[q].repeat_interleave(128).float()
+    anyb = torch.stack(ms).bool().any(0).repeat_interleave(128)
+    want = torch.where(anyb, acc * torch.tensor(np.float32(1.0 / W), device=DEV), gs[own])
+    call('vx_pull_reduce', gs[own], N, [g.data_ptr() for g in gs], [m.data_ptr() for m in ms], W, float(np.float32(1.0 / W)))
+    assert torch.equal(gs[own], want)
+    assert int((~anyb).sum()) > 0
+
+
+@pytest.mark.parametrize('C', [12, 6])
+def test_k0_rows_scatter_equals_per_rank_gather_backward(C):
+    """vx_k0_rows_scatter (all ranks' exported k0 rows in one launch, optionally only the corners inside an X-slab) ==
+    vx_grid_gather_backward rank by rank (ATen grid_sampler_3d backward arithmetic), then restricted to the slab."""
+    from voxurf_b200._lib import call
+    rs = np.random.RandomState(3 + C)
+    X, Y, Z, W, cap = 10, 12, 8, 3, 400
+    V = X * Y * Z
+    stride = cap * (3 + C) + 4
+    recv = torch.zeros(W, stride, device=DEV)
+    counts = [cap, 123, 0]
+    for r in range(W):
+        recv[r, :cap * 3] = cu(T(rs.uniform(-1.08, 1.08, cap * 3).astype(np.float32)))
+        g = rs.standard_normal((cap, C)).astype(np.float32)
+        g[::7] = 0                                                   # rows without a gradient are skipped
+        recv[r, cap * 3:cap * (3 + C)] = cu(T(g.reshape(-1)))
+        recv[r, cap * (3 + C):].view(torch.int32)[0] = counts[r]
+    n_words = (V + 31) // 32
+    ref, ref_t = torch.zeros(V * C, device=DEV), torch.zeros(n_words, dtype=torch.int32, device=DEV)
+    for r in range(W):
+        xyz = recv[r, :cap * 3].view(cap, 3).contiguous()
+        g = recv[r, cap * 3:cap * (3 + C)].view(cap, C).contiguous()
+        n_dev = recv[r, cap * (3 + C):].view(torch.int32).contiguous()
+        call('vx_grid_gather_backward', X, Y, Z, C, 1, MN, MX, xyz, None, None, None, None, 0.0, n_dev, cap, g, ref, ref_t)
+    assert float(ref.abs().sum()) > 0
+    for x_lo, x_hi in ((0, X), (3, 6)):
+        got, got_t = torch.zeros(V * C, device=DEV), torch.zeros(n_words, dtype=torch.int32, device=DEV)
+        call('vx_k0_rows_scatter', X, Y, Z, C, MN, MX, recv.view(-1), W, cap, x_lo, x_hi, got, got_t)
+        want = ref.view(X, -1).clone()
+        want[:x_lo] = 0; want[x_hi:] = 0
+        close(got.view(X, -1), want, 1e-5, 1e-6)      # (fp32 atomics land in a different order)
+        bits = np.unpackbits(ref_t.cpu().numpy().view(np.uint8), bitorder='little')[:V].reshape(X, -1).copy()
+        bits[:x_lo] = 0; bits[x_hi:] = 0
+        assert (np.unpackbits(got_t.cpu().numpy().view(np.uint8), bitorder='little')[:V].reshape(X, -1) == bits).all()
+
+
+def test_peer_store_adam_passes_keep_replicas_identical():
+    """vx_adam_step_worklist_peers / vx_adam_step_blocklive_peers: the owner's pass on its slice, every updated element also
+    stored into the replicas -- bit-identical to the plain passes, replicas == owner afterwards, nothing else touched."""
+    from voxurf_b200._lib import call
+    rs = np.random.RandomState(21)
+    # ---- k0-like grid: C = 12, voxel list from the touched / live bitmaps, the owner steps voxels [lo, hi)
+    C, V = 12, 64 * 40
+    lo, hi = 64 * 10, 64 * 30
+    p0 = cu(T(rs.standard_normal(V * C).astype(np.float32)))
+    reps = [p0.clone(), p0.clone()]
+    own = [p0.clone(), torch.zeros(V * C, device=DEV), torch.zeros(V * C, device=DEV), torch.zeros(V * C, device=DEV)]
+    ref = [t.clone() for t in own]
+    work = torch.zeros(V + 1, dtype=torch.int32, device=DEV)
+    tch = [torch.zeros(V // 32, dtype=torch.int32, device=DEV) for _ in range(2)]
+    liv = [torch.zeros(V // 32, dtype=torch.int32, device=DEV) for _ in range(2)]
+    for step in range(1, 4):
+        vox = rs.choice(np.arange(lo, hi), 150, replace=False)
+        g = np.zeros((V, C), np.float32); g[vox] = rs.standard_normal((150, C))
+        bits = np.zeros(V, bool); bits[vox] = True
+        words = np.packbits(bits.reshape(-1, 32), axis=1, bitorder='little').view(np.uint32).reshape(-1).astype(np.int64)
+        wt = torch.from_numpy(np.where(words >= 2 ** 31, words - 2 ** 32, words)).to(torch.int32)
+        bc1, bc2 = 1 - 0.9 ** step, 1 - 0.99 ** step
+        args = (0.9, 0.99, 0.1, 0.01, 0.1 / bc1, float(np.sqrt(bc2)), 1e-8)
+        for st, t_, l_, peers in ((own, tch[0], liv[0], True), (ref, tch[1], liv[1], False)):
+            st[1].copy_(cu(T(g.reshape(-1)))); t_.copy_(wt)
+            sl = [x[lo * C:hi * C] for x in st]
+            if peers:
+                call('vx_adam_step_worklist_peers', *sl, (hi - lo) * C, *args, 1, t_[lo // 32:hi // 32], l_[lo // 32:hi // 32], C, 1, work, None,
+                     [r.data_ptr() + 4 * lo * C for r in reps], len(reps))
+            else:
+                call('vx_adam_step_worklist', *sl, (hi - lo) * C, *args, 1, t_[lo // 32:hi // 32], l_[lo // 32:hi // 32], C, 1, work, None)
+        for a, b in zip(own, ref):
+            assert torch.equal(a, b)
+        for r in reps:
+            assert torch.equal(r, own[0])
+        assert torch.equal(own[0][:lo * C], p0[:lo * C]) and torch.equal(own[0][hi * C:], p0[hi * C:])
+    # ---- sdf-like grid: block-live pass on the slab [lo, hi) of a single-channel array
+    n, lo, hi = 128 * 200, 128 * 50, 128 * 150
+    p0 = cu(T(rs.standard_normal(n).astype(np.float32)))
+    reps = [p0.clone(), p0.clone(), p0.clone()]
+    own = [p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)]
+    ref = [t.clone() for t in own]
+    live = [torch.zeros(n // 128, dtype=torch.uint8, device=DEV) for _ in range(2)]
+    for step in range(1, 4):
+        g = np.zeros(n, np.float32)
+        for b in rs.choice(np.arange(50, 150), 15, replace=False):
+            g[b * 128 + rs.randint(0, 128, 4)] = rs.standard_normal(4)
+        bc1, bc2 = 1 - 0.9 ** step, 1 - 0.99 ** step
+        args = (0.9, 0.99, 0.1, 0.01, 5e-3 / bc1, float(np.sqrt(bc2)), 1e-8)
+        own[1].copy_(cu(T(g))); ref[1].copy_(cu(T(g)))
+        call('vx_adam_step_blocklive_peers', *[x[lo:hi] for x in own], hi - lo, *args, 1, live[0][lo // 128:hi // 128], None,
+             [r.data_ptr() + 4 * lo for r in reps], len(reps))
+        call('vx_adam_step_blocklive', *[x[lo:hi] for x in ref], hi - lo, *args, 1, live[1][lo // 128:hi // 128], None)
+        for a, b in zip(own, ref):
+            assert torch.equal(a, b)
+        for r in reps:
+            assert torch.equal(r, own[0])
+    assert 0 < int(live[0].sum()) < 100
