@@ -2,28 +2,34 @@
 per-voxel Adam (lib/voxurf_fine.py:620-802, run.py:600-659) on persistent device buffers.
 
 What this replaces, per training iteration of the reference: ~150 kernel launches, >= 13 host syncs, ~10
-boolean-mask compactions and a dense autograd graph.  Here the iteration is 29 kernels (34 on TV iterations), replayed
-as ONE CUDA graph on a single GPU (use_graph=True), ZERO host syncs and no per-step allocation: every data-dependent count (M2 = samples after bbox + mask cache, M4 = MLP rows) stays in
-device memory and is read by the consuming kernels; threshold compactions are a keep-flag and one index list.
-Results are the same numbers as `voxurf_fine.Voxurf.forward` + autograd (tests/test_gpu_fused.py).
+boolean-mask compactions and a dense autograd graph.  Here the iteration is ~25 kernels (+3 on TV iterations), replayed
+as ONE CUDA graph (use_graph=True; at N > 1 with its collectives captured), ZERO host syncs and no per-step allocation:
+every data-dependent count (M2 = samples after bbox + mask cache, M4 = MLP rows) stays in device memory and is read by the
+consuming kernels; threshold compactions are a keep-flag and one index list.
+Results are the same numbers as `voxurf_fine.Voxurf.forward` + autograd (tests/test_gpu_fused.py, test_gpu_fullsize.py).
 
-Sequence (kernel -> reference lines):
-  vx_ray_setup            t_min/t_max, N_steps, start/dir, scan          render_utils_kernel.cu:12-79,210-212
-  vx_march_flags/emit     bbox + MaskCache keep bits -> (ray_id, step_id) voxurf_fine.py:593-617,631-636,930-942
-  vx_fused_sdf_alpha      sdf, 6-tap gradient, NeuS alpha, alpha > thres  voxurf_fine.py:640-648
-  vx_alpha2weight_seg     T / weights (bit-exact recurrence), w > thres   voxurf_fine.py:667-669
-  vx_scan_i32, vx_fused_emit_rows   row list                              voxurf_fine.py:670-676
-  vx_fused_row_features   k0 gather, sample_sdfs (L=4), PEs -> X1, X2     voxurf_fine.py:678-739
-  vx_mlp_prep_batch       hi / lo TF32 weight images of both networks     (mlp.py, csrc/mlp_tc.cu)
-  vx_mlp_chain x2         rgbnet, k_rgbnet forward (tcgen05, TF32x3)      voxurf_fine.py:718,749
-  vx_fused_composite_loss sigmoid, segment sums, losses, their backward   voxurf_fine.py:752-763, run.py:604-636
-  vx_mlp_chain x2         dX chains of both networks
-  vx_mlp_dw_batch         all 8 weight / bias gradient GEMMs, one launch
-  vx_fused_row_backward   k0 scatter, sample_sdfs scatter                 (ATen grid_sampler backward)
-  vx_alpha2weight_seg_backward                                            render_utils_kernel.cu:653-677
+Sequence (C entry point -> reference lines):
+  vx_ray_setup                 t_min/t_max, N_steps, start/dir, scan           render_utils_kernel.cu:12-79,210-212
+  vx_march_flags_cells / emit  bbox + MaskCache keep bits -> (ray_id, step_id) voxurf_fine.py:593-617,631-636,930-942
+  vx_fused_sdf_alpha           sdf, 6-tap gradient, NeuS alpha, alpha > thres   voxurf_fine.py:640-648
+  vx_alpha2weight_seg          T / weights (bit-exact recurrence), w > thres    voxurf_fine.py:667-669
+  vx_scan_i32, vx_fused_emit_rows   row list                                    voxurf_fine.py:670-676
+  vx_fused_row_features        k0 gather, sample_sdfs (L=4), PEs -> X1, X2      voxurf_fine.py:678-739
+  vx_mlp_prep_batch            hi / lo TF32 weight images of both networks      (mlp.py, csrc/mlp_tc.cu)
+  vx_mlp_chain_batch           rgbnet + k_rgbnet forward, one launch (tcgen05)  voxurf_fine.py:718,749
+  vx_fused_composite_loss      sigmoid, segment sums, losses, their backward    voxurf_fine.py:752-763, run.py:604-636
+  vx_mlp_chain_batch           the dX chains of both networks, one launch
+  vx_mlp_dw_batch              all 8 weight / bias gradient GEMMs, one launch (side stream)
+  vx_fused_row_backward        k0 scatter, sample_sdfs scatter                  (ATen grid_sampler backward)
+  vx_alpha2weight_seg_backward                                                  render_utils_kernel.cu:653-677
   vx_fused_alpha_sdf_backward  NeuS alpha backward + 7-tap sdf scatter
-  [TV iters] vx_fd_gradient_active, vx_smooth_grad_tv_masked_writes, vx_sdf_regularisers_backward  run.py:612-655
-  vx_adam_step x4         sdf, k0 (sparse-aware, touched / live bitmaps), rgbnet, k_rgbnet    lib/utils.py:154-199
+  [TV iters] vx_fd_gradient_active, vx_smooth_grad_tv_masked_writes (side stream, beside the forward pass),
+             vx_sdf_regularisers_backward(_slab)                                run.py:612-655
+  vx_adam_step_blocklive (sdf), vx_adam_step_worklist (k0: voxels in touched | live), vx_adam_step x2 (MLPs)   lib/utils.py:154-199
+defer_optimizer: the regulariser + Adam phase of step k runs at the start of step k + 1 beside its ray set-up and march (the k0
+pass already inside step k, beside the rest of its backward pass).  world > 1: rays shard, optimizer state shards by X-slab, the
+gradient / parameter exchange goes over NVLink peer memory (vx_block_nonzero, vx_pull_reduce, vx_k0_rows_scatter,
+vx_adam_step_*_peers) with an NCCL fallback -- DESIGN.md section 7.
 """
 import math
 
